@@ -1,0 +1,107 @@
+"""Kernel-level GPU tests through the C ABI: tcgen05 GEMM / attention vs torch on the same inputs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+torch = pytest.importorskip("torch")
+
+
+def _lib():
+    from b200_whisper import _lib as L
+
+    return L, L.load()
+
+
+def _gemm(impl, A, B, bias=None, residual=None, gelu=False, out_fp32=False):
+    L, lib = _lib()
+    M, K = A.shape
+    N = B.shape[0]
+    Cout = torch.empty((M, N), device="cuda", dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    torch.cuda.synchronize()
+    st = lib.bw_gemm_bf16(impl, A.data_ptr(), B.data_ptr(), Cout.data_ptr(), bias.data_ptr() if bias is not None else None,
+                          residual.data_ptr() if residual is not None else None, M, N, K, int(gelu), int(out_fp32), None)
+    L.check(st, "bw_gemm_bf16")
+    torch.cuda.synchronize()
+    return Cout
+
+
+def _ref(A, B, bias, residual, gelu):
+    r = A.float() @ B.float().t()
+    if bias is not None:
+        r = r + bias
+    if gelu:
+        r = torch.nn.functional.gelu(r)
+    if residual is not None:
+        r = r + residual
+    return r
+
+
+SHAPES = [(128, 128, 64), (256, 256, 128), (1500, 384, 384), (3000, 384, 240), (200, 1536, 384), (1500, 1280, 1280),
+          (333, 2560, 640), (1500, 5120, 1280), (4500, 1280, 5120)]
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_gemm_plain(impl, shape):
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = (torch.randn((M, K), device="cuda", generator=g) * 0.5).bfloat16()
+    B = (torch.randn((N, K), device="cuda", generator=g) * 0.5).bfloat16()
+    out = _gemm(impl, A, B, out_fp32=True)
+    ref = _ref(A, B, None, None, False)
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-2 * (K ** 0.5) * 0.25 + 1e-3, f"impl {impl} shape {shape}: max abs err {err}"
+    rel = ((out - ref).norm() / ref.norm()).item()
+    assert rel < 1e-3, f"impl {impl} shape {shape}: rel-L2 {rel}"
+
+
+@pytest.mark.parametrize("impl", [0, 1, 2])
+def test_gemm_epilogues(impl):
+    M, N, K = 1500, 768, 768
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = (torch.randn((M, K), device="cuda", generator=g) * 0.3).bfloat16()
+    B = (torch.randn((N, K), device="cuda", generator=g) * 0.3).bfloat16()
+    bias = torch.randn((N,), device="cuda", generator=g)
+    res = torch.randn((M, N), device="cuda", generator=g)
+    for gelu in (False, True):
+        for use_res in (False, True):
+            for out_fp32 in (True, False):
+                out = _gemm(impl, A, B, bias, res if use_res else None, gelu, out_fp32).float()
+                ref = _ref(A, B, bias, res if use_res else None, gelu)
+                tol = 3e-2 if not out_fp32 else 5e-3
+                rel = ((out - ref).norm() / ref.norm()).item()
+                assert rel < tol, f"impl {impl} gelu={gelu} res={use_res} fp32={out_fp32}: rel-L2 {rel}"
+
+
+@pytest.mark.parametrize("rows", [1, 5, 16, 37, 128, 300])
+def test_gemm_swap_ab_skinny(rows):
+    """decoder path: few rows against a big [N, K] weight (incl. the 51866-row tied embedding)"""
+    for N, K in ((1280, 1280), (51866, 384)):
+        g = torch.Generator(device="cuda").manual_seed(rows + N)
+        A = (torch.randn((rows, K), device="cuda", generator=g) * 0.3).bfloat16()
+        B = (torch.randn((N, K), device="cuda", generator=g) * 0.3).bfloat16()
+        out = _gemm(2, A, B, out_fp32=True)
+        ref = _ref(A, B, None, None, False)
+        rel = ((out - ref).norm() / ref.norm()).item()
+        assert rel < 1e-3, f"rows {rows} N {N}: rel-L2 {rel}"
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("cfg", [(1, 1500, 2), (2, 1500, 6), (1, 300, 1)])
+def test_encoder_attention(impl, cfg):
+    L, lib = _lib()
+    batch, T, H = cfg
+    d = 64 * H
+    g = torch.Generator(device="cuda").manual_seed(11 + T + H)
+    qkv = (torch.randn((batch * T, 3 * d), device="cuda", generator=g)).bfloat16()
+    out = torch.zeros((batch * T, d), device="cuda", dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    L.check(lib.bw_attention_bf16(impl, qkv.data_ptr(), out.data_ptr(), batch, T, H, None), "bw_attention_bf16")
+    torch.cuda.synchronize()
+    q, k, v = [t.reshape(batch, T, H, 64).permute(0, 2, 1, 3).float() for t in qkv.split(d, dim=1)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(batch * T, d)
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    assert rel < 2e-2, f"impl {impl} cfg {cfg}: rel-L2 {rel}"

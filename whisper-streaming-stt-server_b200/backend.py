@@ -1,0 +1,325 @@
+"""`B200WhisperBackend` -- the drop-in `ModelBackend` for `--model-backend b200_whisper`.
+
+Mirrors the reference's backend interface (stt_server/model/backends/base.py:24-35): same constructor
+`(model_size, device, compute_type)`, same `transcribe(audio, options) -> (List[Segment], BackendInfo)`,
+same option handling and result mapping as `TorchWhisperBackend`
+(stt_server/model/backends/torch_whisper.py:49-110), whose semantics are this backend's parity target.
+The host side keeps upstream `whisper.transcribe`'s seek loop and segment assembly in Python (the
+reference's host language); mel, encoder and the batched decoder run in libb200whisper.so.
+
+Deviations, all explicit:
+* temperature > 0 / fallback ladders are not implemented (server profiles use scalar 0.0): a warning is
+  logged and the window is decoded at temperature 0;
+* `word_timestamps` (DTW alignment) is accepted and ignored; `initial_prompt` needs the tokenizer rank
+  file (`B200_WHISPER_VOCAB_DIR`) and is dropped with a warning without it;
+* like torch_whisper, `without_timestamps` is converted to `word_timestamps` and so does NOT disable
+  timestamp tokens, unless B200_WHISPER_HONOR_WITHOUT_TIMESTAMPS=1 (faster_whisper-like behaviour).
+"""
+from __future__ import annotations
+
+import atexit
+import itertools
+import logging
+import os
+import threading
+import zlib
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .engine import Engine
+from .synth import MODEL_DIMS, ModelDims, random_state_dict
+from .vocab import Detokenizer, Vocab, normalize_language, vocab_for
+
+LOGGER = logging.getLogger("stt_server.model_backend")
+
+try:  # use the server's own dataclasses when running inside it
+    from stt_server.model.backends.base import BackendInfo, Segment  # type: ignore
+except Exception:  # pragma: no cover - exercised when the reference is not importable
+
+    @dataclass(frozen=True)
+    class Segment:  # stt_server/model/backends/base.py:7-13
+        start: float
+        end: float
+        text: str
+
+    @dataclass(frozen=True)
+    class BackendInfo:  # stt_server/model/backends/base.py:16-21
+        language: str
+        language_probability: float
+
+
+N_FRAMES = 3000
+HOP_LENGTH = 160
+SAMPLE_RATE = 16000
+FP32_ALIASES = {"float32", "fp32"}
+BF16_ALIASES = {"bfloat16", "bf16", "float16", "fp16", "half", "int8", "int8_float16", "int8_bfloat16", "default", "auto"}
+
+SUPPORTED_OPTIONS = {  # torch_whisper.py:79-97
+    "temperature", "compression_ratio_threshold", "logprob_threshold", "no_speech_threshold",
+    "condition_on_previous_text", "initial_prompt", "word_timestamps", "prepend_punctuations",
+    "append_punctuations", "language", "task", "beam_size", "best_of", "patience", "length_penalty", "fp16", "prompt",
+}
+
+_ENGINES: Dict[tuple, Engine] = {}
+_ENGINES_LOCK = threading.Lock()
+_INSTANCE_COUNTER = itertools.count()
+
+
+def _close_engines() -> None:
+    with _ENGINES_LOCK:
+        for e in _ENGINES.values():
+            try:
+                e.close()
+            except Exception:
+                pass
+        _ENGINES.clear()
+
+
+atexit.register(_close_engines)
+
+
+def parse_device(device: str, instance_index: int) -> int:
+    """`cuda` / `cuda:N` -> ordinal; `cuda:auto` spreads pool handles round-robin over the visible GPUs
+    (SURVEY.md section 8e option B).  Anything else is refused: there is no CPU path."""
+    dev = (device or "cuda").lower()
+    if not dev.startswith("cuda"):
+        raise ValueError(f"b200_whisper backend needs a CUDA device, got device={device!r} (no CPU fallback)")
+    if dev == "cuda":
+        return 0
+    suffix = dev.split(":", 1)[1]
+    if suffix == "auto":
+        from . import _lib
+
+        n = max(1, _lib.load().bw_device_count())
+        return instance_index % n
+    return int(suffix)
+
+
+def load_checkpoint(model_size: str) -> Tuple[ModelDims, Dict[str, Any], str]:
+    """Resolve `model_size` to (dims, state_dict, canonical name).
+
+    * `random:<name>[:seed[:emb_std[:eot_bias]]]` -- seeded random init (tests / bench; no network here);
+    * a path to an openai-whisper `.pt` checkpoint (`{"dims": ..., "model_state_dict": ...}`);
+    * a model name looked up as `<name>.pt` under $B200_WHISPER_MODEL_DIR and ~/.cache/whisper
+      (where `whisper.load_model`, reference torch_whisper.py:21, caches its downloads).
+    """
+    if model_size.startswith("random:"):
+        parts = model_size.split(":")
+        name = parts[1]
+        if name not in MODEL_DIMS:
+            raise ValueError(f"unknown model name {name!r}")
+        seed = int(parts[2]) if len(parts) > 2 else 0
+        emb_std = float(parts[3]) if len(parts) > 3 else 0.1
+        eot_bias = float(parts[4]) if len(parts) > 4 else 0.0
+        return MODEL_DIMS[name], random_state_dict(MODEL_DIMS[name], seed, emb_std=emb_std, eot_bias=eot_bias), model_size
+    candidates = [model_size]
+    for root in (os.environ.get("B200_WHISPER_MODEL_DIR"), os.path.expanduser("~/.cache/whisper")):
+        if root:
+            candidates.append(os.path.join(root, f"{model_size}.pt"))
+    for path in candidates:
+        if os.path.isfile(path):
+            import torch
+
+            ckpt = torch.load(path, map_location="cpu", weights_only=False)
+            dims = ModelDims(**{k: int(v) for k, v in ckpt["dims"].items()})
+            return dims, ckpt["model_state_dict"], os.path.abspath(path)
+    raise RuntimeError(
+        f"b200_whisper: no checkpoint for model {model_size!r} (looked at {candidates}); set B200_WHISPER_MODEL_DIR "
+        "or pass a .pt path, or use 'random:<name>' for random-init weights")
+
+
+def get_engine(model_size: str, device_index: int, compute: str, **engine_kwargs) -> Engine:
+    """One engine (= one weight copy, one KV pool, one scheduler) per (model, GPU, compute mode); every
+    pool handle the reference creates with identical arguments (model_registry.py:230-247) shares it."""
+    key = (model_size, device_index, compute)
+    with _ENGINES_LOCK:
+        eng = _ENGINES.get(key)
+        if eng is None:
+            dims, state, _ = load_checkpoint(model_size)
+            eng = Engine(dims, state, device_index=device_index, compute=compute, **engine_kwargs)
+            _ENGINES[key] = eng
+        return eng
+
+
+def compression_ratio(text: str) -> float:
+    b = text.encode("utf-8")
+    return len(b) / len(zlib.compress(b))
+
+
+class B200WhisperBackend:
+    """Backend wrapper for the B200-native engine (see module docstring)."""
+
+    def __init__(self, model_size: str, device: str, compute_type: str, **engine_kwargs) -> None:
+        self.model_size = model_size
+        self.device = device
+        self.compute_type = compute_type
+        ct = (compute_type or "default").lower()
+        if ct in FP32_ALIASES:
+            self.compute = "fp32"
+        else:
+            if ct not in BF16_ALIASES:
+                LOGGER.warning("Unsupported compute_type=%s for b200_whisper; using bfloat16", compute_type)
+            self.compute = "bf16"
+        self._instance = next(_INSTANCE_COUNTER)
+        self.device_index = parse_device(device, self._instance)
+        self.engine = get_engine(model_size, self.device_index, self.compute, **engine_kwargs)
+        self.vocab: Vocab = self.engine.vocab
+        self.detok = Detokenizer(self.vocab)
+        self.honor_without_timestamps = os.environ.get("B200_WHISPER_HONOR_WITHOUT_TIMESTAMPS", "0") == "1"
+        self.report_language_probability = os.environ.get("B200_WHISPER_REPORT_LANGUAGE_PROB", "0") == "1"
+        self.last_language_probability: Optional[float] = None
+        LOGGER.info("b200_whisper loaded model=%s device=cuda:%d compute=%s", model_size, self.device_index, self.compute)
+
+    # ---- torch_whisper.py:78-110 ----
+    def _normalize_options(self, options: Dict[str, Any]) -> Dict[str, Any]:
+        opts = dict(options)
+        if "log_prob_threshold" in opts and "logprob_threshold" not in opts:
+            opts["logprob_threshold"] = opts.pop("log_prob_threshold")
+        without_ts = False
+        if "without_timestamps" in opts and "word_timestamps" not in opts:
+            without_ts = bool(opts.pop("without_timestamps"))
+            opts["word_timestamps"] = not without_ts
+        dropped = {k: v for k, v in opts.items() if k not in SUPPORTED_OPTIONS}
+        for key, value in dropped.items():
+            LOGGER.warning("Dropping unsupported b200_whisper option %s=%s", key, value)
+            opts.pop(key, None)
+        if self.honor_without_timestamps and without_ts:
+            opts["_without_timestamps"] = True
+        return opts
+
+    def transcribe(self, audio: Any, options: Dict[str, Any]) -> Tuple[List[Segment], BackendInfo]:
+        opts = self._normalize_options(options)
+        result = self.transcribe_raw(audio, **opts)
+        segments: List[Segment] = []
+        for seg in result.get("segments", []):
+            segments.append(Segment(float(seg.get("start", 0.0)), float(seg.get("end", 0.0)), str(seg.get("text", "") or "")))
+        language = result.get("language") or ""
+        # parity with torch_whisper.py:76: the probability is reported as -1.0 ("unknown"); the detected
+        # value stays available as `last_language_probability` (B200_WHISPER_REPORT_LANGUAGE_PROB=1 returns it)
+        self.last_language_probability = result.get("language_probability")
+        prob = -1.0
+        if self.report_language_probability and self.last_language_probability is not None:
+            prob = float(self.last_language_probability)
+        return segments, BackendInfo(language, prob)
+
+    # ---- upstream whisper/transcribe.py seek loop over the engine ----
+    def transcribe_raw(self, audio: Any, *, temperature: Any = 0.0, compression_ratio_threshold: Optional[float] = 2.4,
+                       logprob_threshold: Optional[float] = -1.0, no_speech_threshold: Optional[float] = 0.6,
+                       condition_on_previous_text: bool = True, initial_prompt: Optional[str] = None,
+                       language: Optional[str] = None, task: Optional[str] = None, beam_size: Optional[int] = None,
+                       best_of: Optional[int] = None, patience: Optional[float] = None,
+                       length_penalty: Optional[float] = None, **ignored) -> dict:
+        v = self.vocab
+        if hasattr(audio, "detach"):
+            audio = audio.detach().cpu().numpy()
+        audio = np.ascontiguousarray(audio, dtype=np.float32).reshape(-1)
+        if audio.size == 0:
+            return {"text": "", "segments": [], "language": language or "", "language_probability": None}
+        if isinstance(temperature, (list, tuple)):
+            if len(temperature) > 1:
+                LOGGER.warning("b200_whisper: temperature fallback ladder not supported; using %s only", temperature[0])
+            temperature = temperature[0] if temperature else 0.0
+        if temperature and float(temperature) > 0:
+            LOGGER.warning("b200_whisper: sampling at temperature %.2f is not supported; decoding at temperature 0", temperature)
+        # scalar temperature 0: best_of is dropped (transcribe.py decode_with_fallback)
+        without_ts = bool(ignored.get("_without_timestamps", False))
+        beam = int(beam_size) if beam_size is not None else None
+        if beam is not None and not (1 <= beam <= 8):
+            raise ValueError(f"beam_size must be in [1, 8], got {beam_size}")
+
+        with self.engine.open_call(audio) as call:
+            content_frames = call.content_frames
+            language_probability = None
+            if language is None:
+                if not v.multilingual:
+                    language = "en"
+                else:
+                    tok, probs = call.detect_language(0)
+                    language = v.language_of_token(tok)
+                    language_probability = float(probs[tok - v.first_language_token])
+            else:
+                language = normalize_language(language)
+            sot_sequence = v.sot_sequence(language, task)
+            if without_ts:
+                sot_sequence = sot_sequence + [v.no_timestamps]
+            n_ctx = self.engine.dims.n_text_ctx
+
+            all_tokens: List[int] = []
+            if initial_prompt is not None:
+                enc = self.detok.encode(" " + initial_prompt.strip())
+                if enc is None:
+                    LOGGER.warning("b200_whisper: initial_prompt dropped (no tokenizer rank file)")
+                else:
+                    all_tokens.extend(enc)
+            n_initial_prompt = len(all_tokens)
+            all_segments: List[dict] = []
+            prompt_reset_since = 0
+            seek = 0
+            input_stride = 2
+            time_precision = 0.02
+            while seek < content_frames:
+                time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
+                segment_size = min(N_FRAMES, content_frames - seek)
+                segment_duration = segment_size * HOP_LENGTH / SAMPLE_RATE
+                prompt = all_tokens[prompt_reset_since:]
+                initial = list(sot_sequence)
+                if prompt:
+                    initial = [v.sot_prev] + prompt[-(n_ctx // 2 - 1):] + initial
+                res = call.decode(seek, initial, initial.index(v.sot), beam, patience, length_penalty,
+                                  without_timestamps=without_ts)
+                tokens: List[int] = res["tokens"]
+                if no_speech_threshold is not None:
+                    should_skip = res["no_speech_prob"] > no_speech_threshold
+                    if logprob_threshold is not None and res["avg_logprob"] > logprob_threshold:
+                        should_skip = False
+                    if should_skip:
+                        seek += segment_size
+                        continue
+                text_all = self.detok.decode([t for t in tokens if t < v.eot]).strip()
+                cr = compression_ratio(text_all) if text_all else 0.0
+
+                def new_segment(start: float, end: float, toks: Sequence[int]) -> dict:
+                    return {"seek": seek, "start": start, "end": end,
+                            "text": self.detok.decode([t for t in toks if t < v.eot]), "tokens": list(toks),
+                            "temperature": 0.0, "avg_logprob": res["avg_logprob"], "compression_ratio": cr,
+                            "no_speech_prob": res["no_speech_prob"]}
+
+                current: List[dict] = []
+                is_ts = [t >= v.timestamp_begin for t in tokens]
+                single_timestamp_ending = is_ts[-2:] == [False, True]
+                consecutive = [i + 1 for i in range(len(tokens) - 1) if is_ts[i] and is_ts[i + 1]]
+                if consecutive:
+                    slices = list(consecutive)
+                    if single_timestamp_ending:
+                        slices.append(len(tokens))
+                    last_slice = 0
+                    for cur_slice in slices:
+                        sliced = tokens[last_slice:cur_slice]
+                        start_pos = sliced[0] - v.timestamp_begin
+                        end_pos = sliced[-1] - v.timestamp_begin
+                        current.append(new_segment(time_offset + start_pos * time_precision,
+                                                   time_offset + end_pos * time_precision, sliced))
+                        last_slice = cur_slice
+                    if single_timestamp_ending:
+                        seek += segment_size
+                    else:
+                        seek += (tokens[last_slice - 1] - v.timestamp_begin) * input_stride
+                else:
+                    duration = segment_duration
+                    stamps = [t for t in tokens if t >= v.timestamp_begin]
+                    if stamps and stamps[-1] != v.timestamp_begin:
+                        duration = (stamps[-1] - v.timestamp_begin) * time_precision
+                    current.append(new_segment(time_offset, time_offset + duration, tokens))
+                    seek += segment_size
+                for seg in current:
+                    if seg["start"] == seg["end"] or seg["text"].strip() == "":
+                        seg["text"] = ""
+                        seg["tokens"] = []
+                all_segments.extend({"id": i, **seg} for i, seg in enumerate(current, start=len(all_segments)))
+                all_tokens.extend(t for seg in current for t in seg["tokens"])
+                if not condition_on_previous_text:
+                    prompt_reset_since = len(all_tokens)
+        return {"text": self.detok.decode(all_tokens[n_initial_prompt:]), "segments": all_segments, "language": language,
+                "language_probability": language_probability}

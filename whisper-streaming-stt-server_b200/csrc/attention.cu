@@ -1,0 +1,456 @@
+// Attention kernels (head dim 64 for every Whisper size).
+//  * attn_encoder_simt : non-causal encoder self-attention, SIMT online softmax (fp32 validation mode
+//    and cross-check for the tcgen05 kernel in attention_tc.cu).
+//  * dec_self_attention : one query per live hypothesis over its paged self-KV (page = 1 token; the
+//    beam ancestry table `anc` redirects each position to the beam slot that wrote it).
+//  * dec_cross_attention: the decoder step's HBM-bound kernel -- streams the cached encoder K/V of a
+//    segment ONCE for all beams of that segment (NQ queries share each 16-byte load), split along T.
+// Upstream: whisper/model.py MultiHeadAttention.qkv_attention (SDPA, scale 1/sqrt(64)).
+#include "kernels.cuh"
+
+namespace bw {
+namespace {
+
+// fp32 validation mode uses the accurate expf; bf16 mode the fast intrinsic
+template <typename T> __device__ __forceinline__ float exp_t(float x) { return __expf(x); }
+template <> __device__ __forceinline__ float exp_t<float>(float x) { return expf(x); }
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+attn_encoder_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int T_len, int n_head) {
+  constexpr int QT = 32, KT = 32;
+  __shared__ float Qs[QT][65];
+  __shared__ float Ks[KT][65];
+  __shared__ float Vs[KT][64];
+  __shared__ float Ps[QT][KT + 1];
+  const int d = n_head * 64;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
+  const int tid = threadIdx.x;
+  const int qi = tid >> 2, part = tid & 3;
+  const T* base = qkv + (long long)b * T_len * 3 * d;
+  for (int i = tid; i < QT * 64; i += 128) {
+    const int r = i >> 6, c = i & 63;
+    Qs[r][c] = (q0 + r < T_len) ? to_f(base[(long long)(q0 + r) * 3 * d + h * 64 + c]) * 0.125f : 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  float o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = 0.f;
+  for (int k0 = 0; k0 < T_len; k0 += KT) {
+    __syncthreads();
+    for (int i = tid; i < KT * 64; i += 128) {
+      const int r = i >> 6, c = i & 63;
+      const bool ok = k0 + r < T_len;
+      const T* row = base + (long long)(k0 + r) * 3 * d + h * 64 + c;
+      Ks[r][c] = ok ? to_f(row[d]) : 0.f;
+      Vs[r][c] = ok ? to_f(row[2 * d]) : 0.f;
+    }
+    __syncthreads();
+    float s[8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = part * 8 + j;
+      float acc = 0.f;
+#pragma unroll 16
+      for (int c = 0; c < 64; ++c) acc = fmaf(Qs[qi][c], Ks[key][c], acc);
+      s[j] = (k0 + key < T_len) ? acc : -INFINITY;
+      mx = fmaxf(mx, s[j]);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(m, mx);
+    const float alpha = (m == -INFINITY) ? 0.f : exp_t<T>(m - m_new);
+    float ps = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p = (s[j] == -INFINITY) ? 0.f : exp_t<T>(s[j] - m_new);
+      Ps[qi][part * 8 + j] = p;
+      ps += p;
+    }
+    ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+    ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+    l = l * alpha + ps;
+    m = m_new;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] *= alpha;
+    for (int key = 0; key < KT; ++key) {
+      const float p = Ps[qi][key];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = fmaf(p, Vs[key][part * 16 + i], o[i]);
+    }
+  }
+  if (q0 + qi < T_len) {
+    const float inv = 1.f / l;
+    T* orow = out + ((long long)b * T_len + q0 + qi) * d + h * 64 + part * 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) orow[i] = from_f<T>(o[i] * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Vec16;
+template <> struct Vec16<bf16> {
+  static constexpr int N = 8;
+  __device__ static void load(const bf16* p, float* f) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  // streaming load: cached K/V are touched once per step -> do not pollute L1
+  __device__ static void load_stream(const bf16* p, float* f) {
+    uint4 u;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+};
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float* f) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
+  }
+  __device__ static void load_stream(const float* p, float* f) { load(p, f); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const T* __restrict__ qkv,
+                          const T* __restrict__ pool, long long unit_stride, int n_ctx, const int* __restrict__ seq_first,
+                          const unsigned char* __restrict__ anc, int layer, int d, T* __restrict__ out) {
+  constexpr int VEC = Vec16<T>::N, LPR = 64 / VEC, RPW = 32 / LPR;
+  __shared__ float sc[448];
+  __shared__ float red[4];
+  __shared__ float osm[4][64];
+  const int h = blockIdx.x, r = blockIdx.y;
+  const int s = row_seq[r], pos = row_pos[r];
+  const int first = seq_first[s];
+  const unsigned char* my_anc = anc + (long long)s * n_ctx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane % LPR, rg = lane / LPR;
+  float qf[VEC];
+  Vec16<T>::load(qkv + (long long)r * 3 * d + h * 64 + sub * VEC, qf);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) qf[i] *= 0.125f;
+  const long long koff = ((long long)(layer * 2 + 0) * n_ctx) * d + h * 64 + sub * VEC;
+  const long long voff = ((long long)(layer * 2 + 1) * n_ctx) * d + h * 64 + sub * VEC;
+  const int n = pos + 1;
+  for (int tg = warp * RPW; tg < n; tg += 4 * RPW) {
+    const int t = tg + rg;
+    float acc = 0.f;
+    if (t < n) {
+      float kf[VEC];
+      Vec16<T>::load(pool + (long long)(first + my_anc[t]) * unit_stride + koff + (long long)t * d, kf);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc = fmaf(qf[i], kf[i], acc);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (t < n && sub == 0) sc[t] = acc;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int t = threadIdx.x; t < n; t += 128) mx = fmaxf(mx, sc[t]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int t = threadIdx.x; t < n; t += 128) {
+    const float p = exp_t<T>(sc[t] - mx);
+    sc[t] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = red[0] + red[1] + red[2] + red[3];
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  for (int tg = warp * RPW; tg < n; tg += 4 * RPW) {
+    const int t = tg + rg;
+    if (t < n) {
+      float vf[VEC];
+      Vec16<T>::load(pool + (long long)(first + my_anc[t]) * unit_stride + voff + (long long)t * d, vf);
+      const float p = sc[t];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
+    }
+  }
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  if (rg == 0)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) osm[warp][sub * VEC + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    const float v = (osm[0][c] + osm[1][c] + osm[2][c] + osm[3][c]) / sum;
+    out[(long long)r * d + h * 64 + c] = from_f<T>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int XW = 8;  // warps per cross-attention CTA
+constexpr int kMaxSplit = 8;
+
+template <typename T, int NQ>
+__global__ void __launch_bounds__(XW * 32)
+dec_cross_attention_kernel(const int* __restrict__ group_first_row, const int* __restrict__ group_n_rows,
+                           const int* __restrict__ group_xslot, const T* __restrict__ q, const T* __restrict__ cache,
+                           long long slot_stride, int T_enc, int layer, int d, int n_split, T* __restrict__ out,
+                           float* __restrict__ ws) {
+  constexpr int VEC = Vec16<T>::N, LPR = 64 / VEC, RPW = 32 / LPR;
+  constexpr int ROWS_IT = XW * RPW;  // rows per CTA iteration
+  extern __shared__ float smx[];
+  const int h = blockIdx.x, g = blockIdx.y, sp = blockIdx.z;
+  const int n_head = gridDim.x;
+  const int row0 = group_first_row[g], nq = group_n_rows[g];
+  const int chunk = (T_enc + n_split - 1) / n_split;
+  const int t0 = sp * chunk, t1 = min(T_enc, t0 + chunk);
+  const int len = t1 - t0;
+  float* sc = smx;                        // [NQ][chunk]
+  float* osm = smx + NQ * chunk;          // [XW][NQ][64]
+  __shared__ float red[NQ][XW];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane % LPR, rg = lane / LPR;
+  const T* kbase = cache + (long long)group_xslot[g] * slot_stride + (long long)layer * T_enc * 2 * d + h * 64 + sub * VEC;
+  const T* vbase = kbase + d;
+  const long long rstride = 2LL * d;
+
+  float qf[NQ][VEC];
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi) {
+    if (qi < nq) {
+      Vec16<T>::load(q + (long long)(row0 + qi) * d + h * 64 + sub * VEC, qf[qi]);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) qf[qi][i] *= 0.125f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) qf[qi][i] = 0.f;
+    }
+  }
+  // ---- scores: 4 independent 16-byte loads in flight per lane ----
+  constexpr int U = 4;
+  for (int tb = warp * RPW; tb < len; tb += ROWS_IT * U) {
+    float kf[U][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = tb + u * ROWS_IT + rg;
+      if (t < len) Vec16<T>::load_stream(kbase + (long long)(t0 + t) * rstride, kf[u]);
+      else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) kf[u][i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = tb + u * ROWS_IT + rg;
+      if (tb + u * ROWS_IT >= len) break;  // warp-uniform
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc = fmaf(qf[qi][i], kf[u][i], acc);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (sub == 0 && t < len) sc[qi * chunk + t] = acc;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- softmax statistics per query over this chunk ----
+  float mloc[NQ], lloc[NQ];
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi) {
+    float mx = -INFINITY;
+    for (int t = threadIdx.x; t < len; t += XW * 32) mx = fmaxf(mx, sc[qi * chunk + t]);
+    mx = warp_max(mx);
+    if (lane == 0) red[qi][warp] = mx;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi) {
+    float mx = red[qi][0];
+#pragma unroll
+    for (int w = 1; w < XW; ++w) mx = fmaxf(mx, red[qi][w]);
+    mloc[qi] = mx;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi) {
+    float sum = 0.f;
+    for (int t = threadIdx.x; t < len; t += XW * 32) {
+      const float p = exp_t<T>(sc[qi * chunk + t] - mloc[qi]);
+      sc[qi * chunk + t] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[qi][warp] = sum;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < XW; ++w) sum += red[qi][w];
+    lloc[qi] = sum;
+  }
+  // ---- P.V ----
+  float acc[NQ][VEC];
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[qi][i] = 0.f;
+  for (int tb = warp * RPW; tb < len; tb += ROWS_IT * U) {
+    float vf[U][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = tb + u * ROWS_IT + rg;
+      if (t < len) Vec16<T>::load_stream(vbase + (long long)(t0 + t) * rstride, vf[u]);
+      else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) vf[u][i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = tb + u * ROWS_IT + rg;
+      if (t < len) {
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+          const float p = sc[qi * chunk + t];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[qi][i] = fmaf(p, vf[u][i], acc[qi][i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float v = acc[qi][i];
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (rg == 0) osm[(warp * NQ + qi) * 64 + sub * VEC + i] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ * 64; i += XW * 32) {
+    const int qi = i >> 6, c = i & 63;
+    if (qi >= nq) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < XW; ++w) v += osm[(w * NQ + qi) * 64 + c];
+    const int row = row0 + qi;
+    if (n_split == 1) {
+      out[(long long)row * d + h * 64 + c] = from_f<T>(v / lloc[qi]);
+    } else {
+      float* w = ws + (((long long)row * n_head + h) * kMaxSplit + sp) * 66;
+      w[2 + c] = v;
+      if (c == 0) { w[0] = mloc[qi]; w[1] = lloc[qi]; }
+    }
+  }
+}
+
+template <typename T>
+__global__ void dec_cross_combine_kernel(const float* __restrict__ ws, int n_split, int d, T* __restrict__ out) {
+  const int h = blockIdx.x, row = blockIdx.y, n_head = gridDim.x, c = threadIdx.x;
+  const float* w = ws + ((long long)row * n_head + h) * kMaxSplit * 66;
+  float M = -INFINITY;
+  for (int s = 0; s < n_split; ++s) M = fmaxf(M, w[s * 66]);
+  float num = 0.f, den = 0.f;
+  for (int s = 0; s < n_split; ++s) {
+    const float e = exp_t<T>(w[s * 66] - M);
+    num = fmaf(e, w[s * 66 + 2 + c], num);
+    den = fmaf(e, w[s * 66 + 1], den);
+  }
+  out[(long long)row * d + h * 64 + c] = from_f<T>(num / den);
+}
+
+}  // namespace
+
+template <typename T>
+void attn_encoder_simt(const T* qkv, T* out, int batch, int T_len, int n_head, cudaStream_t stream) {
+  dim3 grid((T_len + 31) / 32, n_head, batch);
+  attn_encoder_simt_kernel<T><<<grid, 128, 0, stream>>>(qkv, out, T_len, n_head);
+  BW_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+template void attn_encoder_simt<float>(const float*, float*, int, int, int, cudaStream_t);
+template void attn_encoder_simt<bf16>(const bf16*, bf16*, int, int, int, cudaStream_t);
+
+template <typename T>
+void dec_self_attention(const DecRows& rows, const T* qkv, const SelfKV& kv, int layer, int d, int n_head, T* out,
+                        cudaStream_t stream) {
+  if (rows.n_rows <= 0) return;
+  BW_CHECK(kv.n_ctx <= 448, "n_text_ctx > 448 unsupported");
+  dim3 grid(n_head, rows.n_rows);
+  dec_self_attention_kernel<T><<<grid, 128, 0, stream>>>(rows.row_seq, rows.row_pos, qkv, reinterpret_cast<const T*>(kv.pool),
+                                                         kv.unit_stride, kv.n_ctx, kv.seq_first, kv.anc, layer, d, out);
+  BW_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+template void dec_self_attention<float>(const DecRows&, const float*, const SelfKV&, int, int, int, float*, cudaStream_t);
+template void dec_self_attention<bf16>(const DecRows&, const bf16*, const SelfKV&, int, int, int, bf16*, cudaStream_t);
+
+size_t dec_cross_workspace_floats(int n_rows, int n_head) { return (size_t)n_rows * n_head * kMaxSplit * 66; }
+
+namespace {
+template <typename T, int NQ>
+void launch_cross(const int* gfr, const int* gnr, const int* gx, int n_groups, const T* q, const CrossKV& kv, int layer, int d,
+                  int n_head, int n_split, T* out, float* ws, cudaStream_t stream) {
+  const int chunk = (kv.T_enc + n_split - 1) / n_split;
+  const size_t smem = sizeof(float) * ((size_t)NQ * chunk + (size_t)XW * NQ * 64);
+  auto kern = dec_cross_attention_kernel<T, NQ>;
+  static std::atomic<unsigned long long> attr_set{0};
+  int dev = 0;
+  BW_CUDA(cudaGetDevice(&dev));
+  if (!(attr_set.load() >> dev & 1ull)) {
+    BW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(sizeof(float) * ((size_t)NQ * 1504 + (size_t)XW * NQ * 64))));
+    attr_set.fetch_or(1ull << dev);
+  }
+  dim3 grid(n_head, n_groups, n_split);
+  kern<<<grid, XW * 32, smem, stream>>>(gfr, gnr, gx, q, reinterpret_cast<const T*>(kv.cache), kv.slot_stride, kv.T_enc, layer,
+                                        d, n_split, out, ws);
+  BW_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+}  // namespace
+
+template <typename T>
+void dec_cross_attention(const int* group_first_row, const int* group_n_rows, const int* group_xslot, int n_groups,
+                         int max_group_rows, int n_rows, const T* q, const CrossKV& kv, int layer, int d, int n_head, T* out,
+                         float* workspace, cudaStream_t stream) {
+  if (n_groups <= 0) return;
+  BW_CHECK(max_group_rows <= 8, "at most 8 hypotheses per segment");
+  BW_CHECK(kv.T_enc <= 1504, "n_audio_ctx > 1504 unsupported");
+  // split T so that the grid covers the 148 SMs a few times over; each split re-reads nothing.
+  int n_split = 1;
+  const long long base = (long long)n_head * n_groups;
+  while (n_split < kMaxSplit && base * n_split < 4 * 148) n_split *= 2;
+  if (max_group_rows <= 1) launch_cross<T, 1>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
+  else if (max_group_rows <= 2) launch_cross<T, 2>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
+  else if (max_group_rows <= 4) launch_cross<T, 4>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
+  else launch_cross<T, 8>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
+  if (n_split > 1) {
+    dim3 grid(n_head, n_rows);
+    dec_cross_combine_kernel<T><<<grid, 64, 0, stream>>>(workspace, n_split, d, out);
+    BW_CUDA(cudaGetLastError());
+    ++g_kernel_launches;
+  }
+}
+template void dec_cross_attention<float>(const int*, const int*, const int*, int, int, int, const float*, const CrossKV&, int, int, int, float*, float*, cudaStream_t);
+template void dec_cross_attention<bf16>(const int*, const int*, const int*, int, int, int, const bf16*, const CrossKV&, int, int, int, bf16*, float*, cudaStream_t);
+
+}  // namespace bw

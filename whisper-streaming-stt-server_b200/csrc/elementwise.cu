@@ -1,0 +1,201 @@
+// LayerNorm, conv2 im2col, embedding lookup, KV append and dtype conversion kernels.
+// Upstream counterparts: whisper/model.py LayerNorm (fp32 statistics), Conv1d stem, TextDecoder
+// token/positional embedding (reached from reference torch_whisper.py:55).
+#include "kernels.cuh"
+
+namespace bw {
+namespace {
+
+template <typename TOut, bool GATHER>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const int* __restrict__ rows_idx, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, TOut* __restrict__ out, int rows, int d) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (long long)(GATHER ? rows_idx[warp] : warp) * d;
+  // two-pass (mean, then centred variance) like torch's CPU kernel; d <= 1280 -> <= 40 values per lane
+  float v[40];
+  float s = 0.f;
+  const int per = (d + 31) / 32;
+#pragma unroll
+  for (int i = 0; i < 40; ++i) {
+    if (i < per) {
+      const int c = i * 32 + lane;
+      v[i] = (c < d) ? xr[c] : 0.f;
+      s += v[i];
+    }
+  }
+  const float mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 40; ++i) {
+    if (i < per) {
+      const int c = i * 32 + lane;
+      const float t = (c < d) ? v[i] - mean : 0.f;
+      q += t * t;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
+  TOut* orow = out + (long long)warp * d;
+#pragma unroll
+  for (int i = 0; i < 40; ++i) {
+    if (i < per) {
+      const int c = i * 32 + lane;
+      if (c < d) orow[c] = from_f<TOut>((v[i] - mean) * rstd * gamma[c] + beta[c]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void im2col_conv2_kernel(const T* __restrict__ y1, T* __restrict__ A2, int batch, int d) {
+  // one thread per 8-element (or 4 for float) vector; consecutive threads -> consecutive channels
+  constexpr int VEC = 16 / sizeof(T);
+  const long long dv = d / VEC;
+  const long long total = (long long)batch * 1500 * 3 * dv;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = (int)(i % dv);
+  const int k = (int)((i / dv) % 3);
+  const int t = (int)((i / (3 * dv)) % 1500);
+  const int b = (int)(i / (3 * dv * 1500));
+  const int src_t = 2 * t + k - 1;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (src_t >= 0 && src_t < 3000) v = *reinterpret_cast<const uint4*>(y1 + ((long long)b * 3000 + src_t) * d + cv * VEC);
+  *reinterpret_cast<uint4*>(A2 + ((long long)b * 1500 + t) * 3 * d + (long long)k * d + cv * VEC) = v;
+}
+
+template <typename T>
+__global__ void convert_kernel(const float* __restrict__ src, T* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = from_f<T>(src[i]);
+}
+__global__ void f32_from_bf16_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+template <typename T>
+__global__ void permute_conv_kernel(const float* __restrict__ src, T* __restrict__ dst, int co, int ci) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)co * ci * 3) return;
+  const int c = (int)(i % ci);
+  const int k = (int)((i / ci) % 3);
+  const int o = (int)(i / (3LL * ci));
+  dst[i] = from_f<T>(src[((long long)o * ci + c) * 3 + k]);
+}
+
+template <typename T>
+__global__ void dec_embed_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos,
+                                 const int* __restrict__ row_tok, const int* __restrict__ next_tok,
+                                 const T* __restrict__ tok_emb, const T* __restrict__ pos_emb, float* __restrict__ x, int d) {
+  const int r = blockIdx.x;
+  int tok = row_tok[r];
+  if (tok < 0) tok = next_tok[row_seq[r]];
+  const int pos = row_pos[r];
+  for (int c = threadIdx.x; c < d; c += blockDim.x)
+    x[(long long)r * d + c] = to_f(tok_emb[(long long)tok * d + c]) + to_f(pos_emb[(long long)pos * d + c]);
+}
+
+template <typename T>
+__global__ void dec_kv_append_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const T* __restrict__ qkv,
+                                     T* __restrict__ pool, long long unit_stride, int n_ctx, int layer, int d) {
+  const int r = blockIdx.x;
+  const int s = row_seq[r], pos = row_pos[r];
+  T* kdst = pool + (long long)s * unit_stride + ((long long)(layer * 2 + 0) * n_ctx + pos) * d;
+  T* vdst = pool + (long long)s * unit_stride + ((long long)(layer * 2 + 1) * n_ctx + pos) * d;
+  const T* src = qkv + (long long)r * 3 * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    kdst[c] = src[d + c];
+    vdst[c] = src[2 * d + c];
+  }
+}
+
+inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+template <typename T>
+void layernorm(const float* x, const float* gamma, const float* beta, T* out, int rows, int d, cudaStream_t stream) {
+  BW_CHECK(d <= 1280, "layernorm supports d <= 1280");
+  if (rows <= 0) return;
+  layernorm_kernel<T, false><<<blocks_for((long long)rows * 32, 256), 256, 0, stream>>>(x, nullptr, gamma, beta, out, rows, d);
+  BW_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+template void layernorm<float>(const float*, const float*, const float*, float*, int, int, cudaStream_t);
+template void layernorm<bf16>(const float*, const float*, const float*, bf16*, int, int, cudaStream_t);
+
+void layernorm_f32out(const float* x, const float* gamma, const float* beta, float* out, int rows, int d, cudaStream_t stream) {
+  layernorm<float>(x, gamma, beta, out, rows, d, stream);
+}
+
+template <typename T>
+void layernorm_gather(const float* x, const int* rows_idx, const float* gamma, const float* beta, T* out, int n, int d,
+                      cudaStream_t stream) {
+  BW_CHECK(d <= 1280, "layernorm supports d <= 1280");
+  if (n <= 0) return;
+  layernorm_kernel<T, true><<<blocks_for((long long)n * 32, 256), 256, 0, stream>>>(x, rows_idx, gamma, beta, out, n, d);
+  BW_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+template void layernorm_gather<float>(const float*, const int*, const float*, const float*, float*, int, int, cudaStream_t);
+template void layernorm_gather<bf16>(const float*, const int*, const float*, const float*, bf16*, int, int, cudaStream_t);
+
+template <typename T>
+void im2col_conv2(const T* y1, T* A2, int batch, int d, cudaStream_t stream) {
+  constexpr int VEC = 16 / sizeof(T);
+  BW_CHECK(d % VEC == 0, "d must be a multiple of the vector width");
+  const long long total = (long long)batch * 1500 * 3 * (d / VEC);
+  im2col_conv2_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(y1, A2, batch, d);
+  BW_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+template void im2col_conv2<float>(const float*, float*, int, int, cudaStream_t);
+template void im2col_conv2<bf16>(const bf16*, bf16*, int, int, cudaStream_t);
+
+template <typename T>
+void convert_f32(const float* src, T* dst, long long n, cudaStream_t stream) {
+  if (n <= 0) return;
+  convert_kernel<T><<<blocks_for(n, 256), 256, 0, stream>>>(src, dst, n);
+  BW_CUDA(cudaGetLastError());
+}
+template void convert_f32<float>(const float*, float*, long long, cudaStream_t);
+template void convert_f32<bf16>(const float*, bf16*, long long, cudaStream_t);
+
+void f32_from_bf16(const bf16* src, float* dst, long long n, cudaStream_t stream) {
+  if (n <= 0) return;
+  f32_from_bf16_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(src, dst, n);
+  BW_CUDA(cudaGetLastError());
+}
+
+template <typename T>
+void permute_conv_weight(const float* src, T* dst, int co, int ci, cudaStream_t stream) {
+  permute_conv_kernel<T><<<blocks_for((long long)co * ci * 3, 256), 256, 0, stream>>>(src, dst, co, ci);
+  BW_CUDA(cudaGetLastError());
+}
+template void permute_conv_weight<float>(const float*, float*, int, int, cudaStream_t);
+template void permute_conv_weight<bf16>(const float*, bf16*, int, int, cudaStream_t);
+
+template <typename T>
+void dec_embed(const DecRows& rows, const int* next_tok, const T* tok_emb, const T* pos_emb, float* x, int d,
+               cudaStream_t stream) {
+  if (rows.n_rows <= 0) return;
+  dec_embed_kernel<T><<<rows.n_rows, 128, 0, stream>>>(rows.row_seq, rows.row_pos, rows.row_tok, next_tok, tok_emb, pos_emb, x, d);
+  BW_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+template void dec_embed<float>(const DecRows&, const int*, const float*, const float*, float*, int, cudaStream_t);
+template void dec_embed<bf16>(const DecRows&, const int*, const bf16*, const bf16*, float*, int, cudaStream_t);
+
+template <typename T>
+void dec_kv_append(const DecRows& rows, const T* qkv, const SelfKV& kv, int layer, int d, cudaStream_t stream) {
+  if (rows.n_rows <= 0) return;
+  dec_kv_append_kernel<T><<<rows.n_rows, 128, 0, stream>>>(rows.row_seq, rows.row_pos, qkv, reinterpret_cast<T*>(kv.pool),
+                                                           kv.unit_stride, kv.n_ctx, layer, d);
+  BW_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+template void dec_kv_append<float>(const DecRows&, const float*, const SelfKV&, int, int, cudaStream_t);
+template void dec_kv_append<bf16>(const DecRows&, const bf16*, const SelfKV&, int, int, cudaStream_t);
+
+}  // namespace bw

@@ -1,0 +1,369 @@
+// Engine: weight packing, device pools, encoder forward, batched decoder step, continuous-batching
+// scheduler.  One engine per (GPU, model, compute mode); many host threads block in bw_call_decode and
+// the scheduler thread coalesces them -- the cross-session batching the reference declares
+// (config/server.yaml:48-49 decode_batch_window_ms / max_decode_batch_size) but never implements
+//  has to live here.
+#include "engine.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace bw {
+
+namespace {
+
+__global__ void init_requests_kernel(const int* __restrict__ init, int n, ReqState rs, SeqState ss, int anc_cur, int n_ctx) {
+  // init record: q, G, greedy, sample_begin, cur_len, first_seq, without_ts, suppress_blank, max_initial_ts,
+  //              max_candidates, last_init_tok, pad
+  const int* r = init + blockIdx.x * 12;
+  const int q = r[0], G = r[1], first_seq = r[5];
+  if (threadIdx.x == 0) {
+    rs.n_beam[q] = G; rs.greedy[q] = r[2]; rs.sample_begin[q] = r[3]; rs.cur_len[q] = r[4]; rs.first_seq[q] = first_seq;
+    rs.without_ts[q] = r[6]; rs.suppress_blank[q] = r[7]; rs.max_initial_ts[q] = r[8]; rs.max_candidates[q] = r[9];
+    rs.n_finished[q] = 0; rs.completed[q] = 0; rs.no_speech_prob[q] = nanf("");
+    for (int j = 0; j < G; ++j) {
+      const int s = first_seq + j;
+      ss.sum_logprob[s] = 0.f; ss.next_tok[s] = r[10]; ss.prev_tok[s] = -1; ss.last_ts[s] = -1; ss.seq_first[s] = first_seq;
+    }
+  }
+  unsigned char* a = ss.anc[anc_cur] + (long long)first_seq * n_ctx;
+  for (int i = threadIdx.x; i < G * n_ctx; i += blockDim.x) a[i] = 0;
+}
+
+inline float bf16_bits_to_float(uint16_t b) {
+  uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline float half_bits_to_float(uint16_t h) {
+  const uint32_t sign = (h >> 15) & 1, exp = (h >> 10) & 0x1f, man = h & 0x3ff;
+  uint32_t u;
+  if (exp == 0) {
+    if (man == 0) u = sign << 31;
+    else {
+      int e = -1;
+      uint32_t m = man;
+      do { ++e; m <<= 1; } while (!(m & 0x400));
+      u = (sign << 31) | ((uint32_t)(127 - 15 - e) << 23) | ((m & 0x3ff) << 13);
+    }
+  } else if (exp == 31) u = (sign << 31) | 0x7f800000u | (man << 13);
+  else u = (sign << 31) | ((exp + 112) << 23) | (man << 13);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+}  // namespace
+
+// ================================================================================================
+// Typed implementation (T = bf16 product mode, float validation mode)
+// ================================================================================================
+template <typename T>
+struct Impl {
+  bw_engine* e;
+  explicit Impl(bw_engine* eng) : e(eng) {}
+  const bw_model_dims& D() const { return e->dims; }
+
+  void gemm(const GemmArgs& g) const {
+    if constexpr (std::is_same<T, float>::value) gemm_simt<float>(g, e->stream);
+    else {
+      if (e->force_simt) gemm_simt<bf16>(g, e->stream);
+      else gemm_tc_bf16(g, e->stream);
+    }
+  }
+
+  // out[R, N] = act(X[R, K] . W[N, K]^T + bias) (+ residual[R, N]); decoder-side skinny GEMM
+  void linear_rows(const T* X, int R, int x_rows_alloc, const void* W, int N, int K, const float* bias, const float* residual,
+                   void* out, bool gelu, bool out_fp32) const {
+    GemmArgs g;
+    g.K = K; g.lda = K; g.ldb = K; g.ldc = N; g.ldres = N; g.bias = bias; g.residual = residual; g.C = out;
+    g.gelu = gelu; g.out_fp32 = out_fp32;
+    const bool swap = !std::is_same<T, float>::value && !e->force_simt;
+    if (swap) {  // weight rows fill the 128-row MMA, live sequences are the N operand
+      g.A = W; g.B = X; g.M = N; g.N = R; g.transposed = true; g.b_rows = x_rows_alloc;
+    } else {
+      g.A = X; g.B = W; g.M = R; g.N = N;
+    }
+    gemm(g);
+  }
+
+  // ---- encoder forward on `nb` windows whose conv1 operand already sits in A1 ----
+  void encoder_forward(int nb) const {
+    const auto& d = D();
+    const int dm = d.n_audio_state, T_enc = d.n_audio_ctx, K1 = 3 * d.n_mels;
+    const int M = nb * T_enc;
+    cudaStream_t st = e->stream;
+    {  // conv1 + GELU
+      GemmArgs g;
+      g.A = e->A1.p; g.B = e->w.conv1_w; g.C = e->y1.p; g.bias = e->w.conv1_b;
+      g.M = nb * 3000; g.N = dm; g.K = K1; g.lda = K1; g.ldb = K1; g.ldc = dm; g.gelu = true;
+      gemm(g);
+    }
+    im2col_conv2<T>(e->y1.as<T>(), e->A2.as<T>(), nb, dm, st);
+    {  // conv2 + GELU + positional embedding -> fp32 residual stream
+      GemmArgs g;
+      g.A = e->A2.p; g.B = e->w.conv2_w; g.C = e->enc_x.p; g.bias = e->w.conv2_b; g.residual = e->w.enc_pos;
+      g.M = T_enc; g.N = dm; g.K = 3 * dm; g.lda = 3 * dm; g.ldb = 3 * dm; g.ldc = dm; g.ldres = dm;
+      g.Z = nb; g.a_zstride = (long long)T_enc * 3 * dm; g.b_zstride = 0; g.c_zstride = (long long)T_enc * dm;
+      g.res_zstride = 0; g.bias_zstride = 0; g.gelu = true; g.out_fp32 = true;
+      gemm(g);
+    }
+    float* x = e->enc_x.as<float>();
+    for (int l = 0; l < d.n_audio_layer; ++l) {
+      const LayerW& w = e->w.enc[l];
+      layernorm<T>(x, w.ln1_g, w.ln1_b, e->enc_xn.as<T>(), M, dm, st);
+      {
+        GemmArgs g;
+        g.A = e->enc_xn.p; g.B = w.wqkv; g.C = e->enc_qkv.p; g.bias = w.bqkv;
+        g.M = M; g.N = 3 * dm; g.K = dm; g.lda = dm; g.ldb = dm; g.ldc = 3 * dm;
+        gemm(g);
+      }
+      if constexpr (std::is_same<T, float>::value) {
+        attn_encoder_simt<float>(e->enc_qkv.as<float>(), e->enc_att.as<float>(), nb, T_enc, d.n_audio_head, st);
+      } else {
+        if (e->force_simt || (e->cfg.flags & 4)) attn_encoder_simt<bf16>(e->enc_qkv.as<bf16>(), e->enc_att.as<bf16>(), nb, T_enc, d.n_audio_head, st);
+        else attn_encoder_tc(e->enc_qkv.as<bf16>(), e->enc_att.as<bf16>(), nb, T_enc, d.n_audio_head, st);
+      }
+      {
+        GemmArgs g;
+        g.A = e->enc_att.p; g.B = w.wo; g.C = x; g.bias = w.bo; g.residual = x;
+        g.M = M; g.N = dm; g.K = dm; g.lda = dm; g.ldb = dm; g.ldc = dm; g.ldres = dm; g.out_fp32 = true;
+        gemm(g);
+      }
+      layernorm<T>(x, w.ln2_g, w.ln2_b, e->enc_xn.as<T>(), M, dm, st);
+      {
+        GemmArgs g;
+        g.A = e->enc_xn.p; g.B = w.w1; g.C = e->enc_h.p; g.bias = w.b1;
+        g.M = M; g.N = 4 * dm; g.K = dm; g.lda = dm; g.ldb = dm; g.ldc = 4 * dm; g.gelu = true;
+        gemm(g);
+      }
+      {
+        GemmArgs g;
+        g.A = e->enc_h.p; g.B = w.w2; g.C = x; g.bias = w.b2; g.residual = x;
+        g.M = M; g.N = dm; g.K = 4 * dm; g.lda = 4 * dm; g.ldb = 4 * dm; g.ldc = dm; g.ldres = dm; g.out_fp32 = true;
+        gemm(g);
+      }
+    }
+    layernorm<T>(x, e->w.ln_post_g, e->w.ln_post_b, e->enc_out.as<T>(), M, dm, st);
+  }
+
+  // cross K/V of every decoder layer for batch element `bi` -> cross-cache slot q (one launch, z = layer)
+  void cross_kv(int bi, int q) const {
+    const auto& d = D();
+    const int dm = d.n_text_state, T_enc = d.n_audio_ctx, L = d.n_text_layer;
+    GemmArgs g;
+    g.A = e->enc_out.as<T>() + (long long)bi * T_enc * dm; g.B = e->w.wkv_x; g.bias = e->w.bkv_x;
+    g.C = e->cross_cache.as<T>() + (long long)q * L * T_enc * 2 * dm;
+    g.M = T_enc; g.N = 2 * dm; g.K = dm; g.lda = dm; g.ldb = dm; g.ldc = 2 * dm;
+    g.Z = L; g.a_zstride = 0; g.b_zstride = (long long)2 * dm * dm; g.c_zstride = (long long)T_enc * 2 * dm; g.bias_zstride = 2 * dm;
+    gemm(g);
+  }
+
+  // ---- one decoder step over `R` rows; control arrays already on the device ----
+  struct StepCtl {
+    int R = 0, n_groups = 0, max_group_rows = 1, n_lrows = 0;
+    const int *row_seq, *row_pos, *row_tok, *grp_first, *grp_n, *grp_x, *lrow_src;
+  };
+  void decoder_layers(const StepCtl& c) const {
+    const auto& d = D();
+    const int dm = d.n_text_state, L = d.n_text_layer, H = d.n_text_head;
+    cudaStream_t st = e->stream;
+    DecRows rows;
+    rows.n_rows = c.R; rows.row_seq = c.row_seq; rows.row_pos = c.row_pos; rows.row_tok = c.row_tok;
+    float* x = e->d_x.as<float>();
+    dec_embed<T>(rows, e->ss.next_tok, reinterpret_cast<const T*>(e->w.tok_emb), reinterpret_cast<const T*>(e->w.dec_pos), x, dm, st);
+    SelfKV skv;
+    skv.pool = e->self_pool.p; skv.unit_stride = (long long)L * 2 * d.n_text_ctx * dm; skv.n_ctx = d.n_text_ctx;
+    skv.seq_first = e->ss.seq_first; skv.anc = e->ss.anc[e->anc_cur];
+    CrossKV xkv;
+    xkv.cache = e->cross_cache.p; xkv.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; xkv.T_enc = d.n_audio_ctx;
+    const int Ra = e->R_max;
+    for (int l = 0; l < L; ++l) {
+      const LayerW& w = e->w.dec[l];
+      layernorm<T>(x, w.ln1_g, w.ln1_b, e->d_xn.as<T>(), c.R, dm, st);
+      linear_rows(e->d_xn.as<T>(), c.R, Ra, w.wqkv, 3 * dm, dm, w.bqkv, nullptr, e->d_qkv.p, false, false);
+      dec_kv_append<T>(rows, e->d_qkv.as<T>(), skv, l, dm, st);
+      dec_self_attention<T>(rows, e->d_qkv.as<T>(), skv, l, dm, H, e->d_att.as<T>(), st);
+      linear_rows(e->d_att.as<T>(), c.R, Ra, w.wo, dm, dm, w.bo, x, x, false, true);
+      layernorm<T>(x, w.lnx_g, w.lnx_b, e->d_xn.as<T>(), c.R, dm, st);
+      linear_rows(e->d_xn.as<T>(), c.R, Ra, w.wq_x, dm, dm, w.bq_x, nullptr, e->d_q.p, false, false);
+      dec_cross_attention<T>(c.grp_first, c.grp_n, c.grp_x, c.n_groups, c.max_group_rows, c.R, e->d_q.as<T>(), xkv, l, dm, H,
+                             e->d_att.as<T>(), e->d_ws.as<float>(), st);
+      linear_rows(e->d_att.as<T>(), c.R, Ra, w.wo_x, dm, dm, w.bo_x, x, x, false, true);
+      layernorm<T>(x, w.ln2_g, w.ln2_b, e->d_xn.as<T>(), c.R, dm, st);
+      linear_rows(e->d_xn.as<T>(), c.R, Ra, w.w1, 4 * dm, dm, w.b1, nullptr, e->d_h.p, true, false);
+      linear_rows(e->d_h.as<T>(), c.R, Ra, w.w2, dm, 4 * dm, w.b2, x, x, false, true);
+    }
+    // final LayerNorm only on the rows whose logits are needed, then the tied-embedding projection
+    layernorm_gather<T>(x, c.lrow_src, e->w.ln_g, e->w.ln_b, e->d_lnrows.as<T>(), c.n_lrows, dm, st);
+    linear_rows(e->d_lnrows.as<T>(), c.n_lrows, e->LR_max, e->w.tok_emb, d.n_vocab, dm, nullptr, nullptr, e->d_logits.p, false, true);
+  }
+
+  void window_to_A1(const float* logmel, int ld, int n_real, const int* gmax, int seek, int seg, int bi) const {
+    T* dst = e->A1.as<T>() + (long long)bi * 3000 * 3 * D().n_mels;
+    mel_window<T>(logmel, ld, n_real, gmax, D().n_mels, seek, seg, dst, e->stream);
+  }
+};
+
+// ================================================================================================
+// engine-level helpers used by api.cu
+// ================================================================================================
+static void* alloc_weight(bw_engine* e, size_t bytes, bool zero) {
+  auto b = std::make_unique<DevBuf>();
+  b->alloc(bytes);
+  if (zero) BW_CUDA(cudaMemset(b->p, 0, bytes));
+  void* p = b->p;
+  e->weight_bufs.push_back(std::move(b));
+  return p;
+}
+
+void engine_build_weight_table(bw_engine* e) {
+  const auto& d = e->dims;
+  const size_t ts = e->fp32 ? 4 : 2;
+  auto wt = [&](size_t elems) { return alloc_weight(e, elems * ts, false); };
+  auto wf = [&](size_t elems) { return reinterpret_cast<float*>(alloc_weight(e, elems * 4, true)); };
+  auto reg = [&](const std::string& name, void* p, size_t n, bool required = true) {
+    e->named[name] = {p, n};
+    if (required) e->expected_names.push_back(name);
+  };
+  auto off = [&](void* p, size_t elems) { return reinterpret_cast<void*>(reinterpret_cast<char*>(p) + elems * ts); };
+  const size_t dm = d.n_audio_state;
+  ModelW& w = e->w;
+  w.conv1_w = wt(dm * 3 * d.n_mels); w.conv1_b = wf(dm);
+  w.conv2_w = wt(dm * 3 * dm); w.conv2_b = wf(dm);
+  w.enc_pos = wf((size_t)d.n_audio_ctx * dm);
+  reg("encoder.conv1.weight", w.conv1_w, dm * 3 * d.n_mels); reg("encoder.conv1.bias", w.conv1_b, dm);
+  reg("encoder.conv2.weight", w.conv2_w, dm * 3 * dm); reg("encoder.conv2.bias", w.conv2_b, dm);
+  reg("encoder.positional_embedding", w.enc_pos, (size_t)d.n_audio_ctx * dm, false);
+  auto block = [&](const std::string& p, LayerW& lw, size_t dd, bool cross) {
+    lw.ln1_g = wf(dd); lw.ln1_b = wf(dd);
+    lw.wqkv = wt(3 * dd * dd); lw.bqkv = wf(3 * dd);
+    lw.wo = wt(dd * dd); lw.bo = wf(dd);
+    reg(p + ".attn_ln.weight", lw.ln1_g, dd); reg(p + ".attn_ln.bias", lw.ln1_b, dd);
+    reg(p + ".attn.query.weight", lw.wqkv, dd * dd); reg(p + ".attn.query.bias", lw.bqkv, dd);
+    reg(p + ".attn.key.weight", off(lw.wqkv, dd * dd), dd * dd);
+    reg(p + ".attn.value.weight", off(lw.wqkv, 2 * dd * dd), dd * dd); reg(p + ".attn.value.bias", lw.bqkv + 2 * dd, dd);
+    reg(p + ".attn.out.weight", lw.wo, dd * dd); reg(p + ".attn.out.bias", lw.bo, dd);
+    if (cross) {
+      lw.lnx_g = wf(dd); lw.lnx_b = wf(dd);
+      lw.wq_x = wt(dd * dd); lw.bq_x = wf(dd);
+      lw.wo_x = wt(dd * dd); lw.bo_x = wf(dd);
+      reg(p + ".cross_attn_ln.weight", lw.lnx_g, dd); reg(p + ".cross_attn_ln.bias", lw.lnx_b, dd);
+      reg(p + ".cross_attn.query.weight", lw.wq_x, dd * dd); reg(p + ".cross_attn.query.bias", lw.bq_x, dd);
+      reg(p + ".cross_attn.out.weight", lw.wo_x, dd * dd); reg(p + ".cross_attn.out.bias", lw.bo_x, dd);
+    }
+    lw.ln2_g = wf(dd); lw.ln2_b = wf(dd);
+    lw.w1 = wt(4 * dd * dd); lw.b1 = wf(4 * dd);
+    lw.w2 = wt(4 * dd * dd); lw.b2 = wf(dd);
+    reg(p + ".mlp_ln.weight", lw.ln2_g, dd); reg(p + ".mlp_ln.bias", lw.ln2_b, dd);
+    reg(p + ".mlp.0.weight", lw.w1, 4 * dd * dd); reg(p + ".mlp.0.bias", lw.b1, 4 * dd);
+    reg(p + ".mlp.2.weight", lw.w2, 4 * dd * dd); reg(p + ".mlp.2.bias", lw.b2, dd);
+  };
+  w.enc.resize(d.n_audio_layer);
+  for (int i = 0; i < d.n_audio_layer; ++i) block("encoder.blocks." + std::to_string(i), w.enc[i], dm, false);
+  w.ln_post_g = wf(dm); w.ln_post_b = wf(dm);
+  reg("encoder.ln_post.weight", w.ln_post_g, dm); reg("encoder.ln_post.bias", w.ln_post_b, dm);
+  const size_t dt = d.n_text_state;
+  w.tok_emb = wt((size_t)d.n_vocab * dt);
+  w.dec_pos = wt((size_t)d.n_text_ctx * dt);
+  reg("decoder.token_embedding.weight", w.tok_emb, (size_t)d.n_vocab * dt);
+  reg("decoder.positional_embedding", w.dec_pos, (size_t)d.n_text_ctx * dt);
+  w.wkv_x = wt((size_t)d.n_text_layer * 2 * dt * dt);
+  w.bkv_x = wf((size_t)d.n_text_layer * 2 * dt);
+  w.dec.resize(d.n_text_layer);
+  for (int i = 0; i < d.n_text_layer; ++i) {
+    const std::string p = "decoder.blocks." + std::to_string(i);
+    block(p, w.dec[i], dt, true);
+    reg(p + ".cross_attn.key.weight", off(w.wkv_x, (size_t)i * 2 * dt * dt), dt * dt);
+    reg(p + ".cross_attn.value.weight", off(w.wkv_x, (size_t)i * 2 * dt * dt + dt * dt), dt * dt);
+    reg(p + ".cross_attn.value.bias", w.bkv_x + (size_t)i * 2 * dt + dt, dt);
+  }
+  w.ln_g = wf(dt); w.ln_b = wf(dt);
+  reg("decoder.ln.weight", w.ln_g, dt); reg("decoder.ln.bias", w.ln_b, dt);
+}
+
+static bool is_f32_dest(const std::string& name) {
+  auto ends = [&](const char* s) { const size_t n = strlen(s); return name.size() >= n && name.compare(name.size() - n, n, s) == 0; };
+  if (name == "encoder.positional_embedding") return true;
+  if (ends(".bias")) return true;
+  if (ends("_ln.weight") || ends("ln_post.weight") || name == "decoder.ln.weight") return true;
+  return false;
+}
+
+void engine_load_tensor(bw_engine* e, const bw_tensor_desc& t) {
+  BW_CHECK(t.name && t.data, "tensor name/data null");
+  const std::string name(t.name);
+  auto it = e->named.find(name);
+  if (it == e->named.end()) {
+    if (name == "alignment_heads" || name.find("mask") != std::string::npos) return;  // non-parameter buffers of upstream
+    throw std::invalid_argument("unknown tensor name: " + name);
+  }
+  size_t n = 1;
+  for (int i = 0; i < t.ndim; ++i) n *= (size_t)t.shape[i];
+  BW_CHECK(n == it->second.second, ("element count mismatch for " + name).c_str());
+  // stage as fp32 on the device
+  if (e->staging.bytes < n * 4) e->staging.alloc(std::max(n * 4, (size_t)64 << 20));
+  std::vector<float> tmp;
+  const float* src = nullptr;
+  if (t.dtype == BW_F32) src = reinterpret_cast<const float*>(t.data);
+  else {
+    tmp.resize(n);
+    const uint16_t* h = reinterpret_cast<const uint16_t*>(t.data);
+    if (t.dtype == BW_F16) for (size_t i = 0; i < n; ++i) tmp[i] = half_bits_to_float(h[i]);
+    else if (t.dtype == BW_BF16) for (size_t i = 0; i < n; ++i) tmp[i] = bf16_bits_to_float(h[i]);
+    else throw std::invalid_argument("unsupported dtype for " + name);
+    src = tmp.data();
+  }
+  BW_CUDA(cudaMemcpyAsync(e->staging.p, src, n * 4, cudaMemcpyHostToDevice, e->stream));
+  void* dst = it->second.first;
+  const bool conv = (name == "encoder.conv1.weight" || name == "encoder.conv2.weight");
+  if (conv) {
+    BW_CHECK(t.ndim == 3 && t.shape[2] == 3, "conv weight must be [co, ci, 3]");
+    if (e->fp32) permute_conv_weight<float>(e->staging.as<float>(), reinterpret_cast<float*>(dst), (int)t.shape[0], (int)t.shape[1], e->stream);
+    else permute_conv_weight<bf16>(e->staging.as<float>(), reinterpret_cast<bf16*>(dst), (int)t.shape[0], (int)t.shape[1], e->stream);
+  } else if (is_f32_dest(name) || e->fp32) {
+    BW_CUDA(cudaMemcpyAsync(dst, e->staging.p, n * 4, cudaMemcpyDeviceToDevice, e->stream));
+  } else {
+    convert_f32<bf16>(e->staging.as<float>(), reinterpret_cast<bf16*>(dst), (long long)n, e->stream);
+  }
+  BW_CUDA(cudaStreamSynchronize(e->stream));  // `tmp` / caller memory may go away
+  for (size_t i = 0; i < e->expected_names.size(); ++i)
+    if (e->expected_names[i] == name) e->loaded[i] = 1;
+  if (name == "encoder.positional_embedding") e->loaded.back() = 1;
+}
+
+template <typename T> static void encoder_forward_t(bw_engine* e, int nb) { Impl<T>(e).encoder_forward(nb); }
+void engine_encoder_forward(bw_engine* e, int nb) {
+  if (e->fp32) encoder_forward_t<float>(e, nb); else encoder_forward_t<bf16>(e, nb);
+}
+void engine_cross_kv(bw_engine* e, int bi, int q) {
+  if (e->fp32) Impl<float>(e).cross_kv(bi, q); else Impl<bf16>(e).cross_kv(bi, q);
+}
+void engine_window_to_A1(bw_engine* e, const float* logmel, int ld, int n_real, const int* gmax, int seek, int seg, int bi) {
+  if (e->fp32) Impl<float>(e).window_to_A1(logmel, ld, n_real, gmax, seek, seg, bi);
+  else Impl<bf16>(e).window_to_A1(logmel, ld, n_real, gmax, seek, seg, bi);
+}
+void engine_decoder_layers(bw_engine* e, int R, int n_groups, int max_group_rows, int n_lrows, const int* row_seq,
+                           const int* row_pos, const int* row_tok, const int* grp_first, const int* grp_n, const int* grp_x,
+                           const int* lrow_src) {
+  if (e->fp32) {
+    Impl<float>::StepCtl c; c.R = R; c.n_groups = n_groups; c.max_group_rows = max_group_rows; c.n_lrows = n_lrows;
+    c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
+    Impl<float>(e).decoder_layers(c);
+  } else {
+    Impl<bf16>::StepCtl c; c.R = R; c.n_groups = n_groups; c.max_group_rows = max_group_rows; c.n_lrows = n_lrows;
+    c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
+    Impl<bf16>(e).decoder_layers(c);
+  }
+}
+void engine_init_requests(bw_engine* e, const int* init_dev, int n) {
+  if (n <= 0) return;
+  init_requests_kernel<<<n, 128, 0, e->stream>>>(init_dev, n, e->rs, e->ss, e->anc_cur, e->dims.n_text_ctx);
+  BW_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+
+}  // namespace bw

@@ -1,0 +1,39 @@
+// GEMM interface shared by the tcgen05 kernel (gemm_tc.cu) and the SIMT kernel (gemm_simt.cu).
+//
+//   D[z][i][j] = act( sum_k A[z][i][k] * B[z][j][k] + bias ) (+ residual)       i < M, j < N
+//
+// A and B are K-major ("row-major [rows, K]", leading dimension lda/ldb elements); the weight
+// matrices of torch Linear layers ([out, in]) are K-major B operands as they are.  `transposed`
+// stores D^T (out[j*ldc + i], bias[i], residual[j*ldres + i]): the decoder's skinny GEMMs run
+// "swap-AB" -- the weight is the 128-row M operand, the few live sequences are the N operand.
+#pragma once
+#include <atomic>
+
+#include "common.cuh"
+
+namespace bw {
+
+struct GemmArgs {
+  const void* A = nullptr;  // [Z?][M, K]
+  const void* B = nullptr;  // [Z?][N, K]
+  void* C = nullptr;
+  const float* bias = nullptr;      // fp32
+  const float* residual = nullptr;  // fp32
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldb = 0, ldc = 0, ldres = 0;
+  int Z = 1;
+  int a_rows = 0, b_rows = 0;  // allocated rows behind A / B (>= M / N) used for the TMA maps; 0 = M / N
+  long long a_zstride = 0, b_zstride = 0, c_zstride = 0, bias_zstride = 0, res_zstride = 0;  // elements
+  bool gelu = false;
+  bool out_fp32 = false;    // else same storage type as the inputs
+  bool transposed = false;
+};
+
+// bf16 inputs, fp32 accumulate, tcgen05.mma + TMEM + TMA. Throws on CUDA errors.
+void gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream);
+// SIMT tiled GEMM: T = float (validation mode) or bf16 (fallback / cross-check).
+template <typename T> void gemm_simt(const GemmArgs& g, cudaStream_t stream);
+
+extern std::atomic<long long> g_kernel_launches;  // counted by every launcher in this library
+
+}  // namespace bw

@@ -1,0 +1,323 @@
+// tcgen05 GEMM for sm_100a: TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared -> tcgen05.mma
+// (cta_group::1, kind::f16, M=128, N=BN) with the fp32 accumulator in TMEM -> tcgen05.ld ->
+// fused bias / GELU / residual epilogue.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM
+// allocator + single-thread MMA issuer, warps 2..5 = epilogue (one TMEM lane quarter each).
+//
+// Replaces the cuBLAS GEMMs that upstream `whisper.model.Linear` / `Conv1d` dispatch to from
+// `TorchWhisperBackend.transcribe` (reference stt_server/model/backends/torch_whisper.py:55);
+// see SURVEY.md section 2.2 rows K2/K4.
+#include <cuda.h>
+
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm.cuh"
+
+namespace bw {
+
+std::atomic<long long> g_kernel_launches{0};
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+
+struct GemmDev {
+  void* C;
+  const float* bias;
+  const float* residual;
+  int M, N, K;
+  int ldc, ldres;
+  long long c_zstride, bias_zstride, res_zstride;
+  int a_z_bcast, b_z_bcast;
+  int gelu, out_fp32, transposed;
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+};
+
+template <int BN, int STAGES, int MINB>
+__global__ void __launch_bounds__(192, MINB)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int z = blockIdx.z;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int za = p.a_z_bcast ? 0 : z;
+      const int zb = p.b_z_bcast ? 0 : z;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], phase ^ 1);
+        uint8_t* sa = smem + s * L::kStageBytes;
+        uint8_t* sb = sa + L::kABytes;
+        mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
+        tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, m0, za);
+        tma_load_3d(sb, &tmB, &full_bar[s], kb * BK, n0, zb);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
+        const uint32_t sb = sa + L::kABytes;
+        const uint64_t adesc = umma_smem_desc_sw128(sa, 16, 1024);
+        const uint64_t bdesc = umma_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // +32 B per UMMA_K=16 step inside the 128 B swizzle row (descriptor address units of 16 B)
+          umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);    // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: 4 warps, warp (w & 3) owns TMEM lanes [32*(w&3), +32) ----
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const int i = m0 + row;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const float* bias = p.bias ? p.bias + (long long)z * p.bias_zstride : nullptr;
+    const float* res = p.residual ? p.residual + (long long)z * p.res_zstride : nullptr;
+    const bool row_ok = i < p.M;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int j0 = n0 + c * 32;
+      if (j0 >= p.N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      float v[32];
+      if (!p.transposed) {
+        const bool full = (j0 + 32 <= p.N);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          if (bias && (full || j0 + j < p.N)) x += __ldg(bias + j0 + j);
+          if (p.gelu) x = gelu_erf(x);
+          v[j] = x;
+        }
+        if (row_ok) {
+          if (res) {
+            const float* rr = res + (long long)i * p.ldres + j0;
+            if (full && ((p.ldres & 3) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(rr + j);
+                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j0 + j < p.N) v[j] += rr[j];
+            }
+          }
+          if (p.out_fp32) {
+            float* o = reinterpret_cast<float*>(p.C) + (long long)z * p.c_zstride + (long long)i * p.ldc + j0;
+            if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j0 + j < p.N) o[j] = v[j];
+            }
+          } else {
+            bf16* o = reinterpret_cast<bf16*>(p.C) + (long long)z * p.c_zstride + (long long)i * p.ldc + j0;
+            if (full && ((p.ldc & 7) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 t;
+                t.x = pack_bf16x2(v[j], v[j + 1]);
+                t.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                t.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                t.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = t;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j0 + j < p.N) o[j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+      } else {
+        // D^T: out[j*ldc + i]; consecutive lanes = consecutive i -> coalesced per j
+        const float b = (bias && row_ok) ? __ldg(bias + i) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]) + b;
+          if (p.gelu) x = gelu_erf(x);
+          if (row_ok && j0 + j < p.N) {
+            if (res) x += res[(long long)(j0 + j) * p.ldres + i];
+            if (p.out_fp32)
+              (reinterpret_cast<float*>(p.C) + (long long)z * p.c_zstride)[(long long)(j0 + j) * p.ldc + i] = x;
+            else
+              (reinterpret_cast<bf16*>(p.C) + (long long)z * p.c_zstride)[(long long)(j0 + j) * p.ldc + i] = __float2bfloat16(x);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---- host side: tensor maps (driver entry point fetched through the runtime; no -lcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+      throw CudaError("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int rows, K, ld, Z; long long zstride; int box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && K == o.K && ld == o.ld && Z == o.Z && zstride == o.zstride && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&](long long v) { h ^= (size_t)v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
+    mix(k.rows); mix(k.K); mix(k.ld); mix(k.Z); mix(k.zstride); mix(k.box_rows);
+    return h;
+  }
+};
+
+}  // namespace
+
+// bf16 [Z][rows, K] K-major operand -> 3D tiled map {K, rows, Z}, box {64, box_rows, 1}, SWIZZLE_128B.
+CUtensorMap make_operand_map(const void* ptr, int rows, int K, int ld, int Z, long long zstride, int box_rows) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, rows, K, ld, Z, zstride, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  BW_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand must be 16-byte aligned");
+  BW_CHECK((ld % 8) == 0, "TMA operand leading dimension must be a multiple of 8 bf16");
+  CUtensorMap m;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(Z > 0 ? Z : 1)};
+  long long zs = (Z > 1 && zstride > 0) ? zstride : (long long)rows * ld;
+  BW_CHECK((zs % 8) == 0, "TMA operand batch stride must be a multiple of 8 bf16");
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)zs * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 65536) cache.clear();
+  cache.emplace(key, m);
+  return m;
+}
+
+namespace {
+template <int BN, int STAGES, int MINB>
+void launch(const GemmArgs& g, cudaStream_t stream) {
+  using L = SmemLayout<BN, STAGES>;
+  static std::atomic<unsigned long long> attr_set{0};  // per-device bit
+  auto kern = gemm_tc_kernel<BN, STAGES, MINB>;
+  int dev = 0;
+  BW_CUDA(cudaGetDevice(&dev));
+  if (!(attr_set.load() >> dev & 1ull)) {
+    BW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set.fetch_or(1ull << dev);
+  }
+  const bool a_bcast = (g.Z > 1 && g.a_zstride == 0), b_bcast = (g.Z > 1 && g.b_zstride == 0);
+  CUtensorMap tmA = make_operand_map(g.A, g.a_rows > g.M ? g.a_rows : g.M, g.K, g.lda, a_bcast ? 1 : g.Z, g.a_zstride, BM);
+  CUtensorMap tmB = make_operand_map(g.B, g.b_rows > g.N ? g.b_rows : g.N, g.K, g.ldb, b_bcast ? 1 : g.Z, g.b_zstride, BN);
+  GemmDev p;
+  p.C = g.C; p.bias = g.bias; p.residual = g.residual;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = g.ldc; p.ldres = g.ldres;
+  p.c_zstride = g.c_zstride; p.bias_zstride = g.bias_zstride; p.res_zstride = g.res_zstride;
+  p.a_z_bcast = a_bcast; p.b_z_bcast = b_bcast;
+  p.gelu = g.gelu; p.out_fp32 = g.out_fp32; p.transposed = g.transposed;
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.Z);
+  kern<<<grid, 192, L::kTotal, stream>>>(tmA, tmB, p);
+  BW_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+}  // namespace
+
+void gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
+  BW_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.Z > 0, "empty GEMM");
+  // Tile choice: 128x256 (fewer smem bytes per MMA) when it still fills the 148 SMs, else
+  // 128x128 with two CTAs per SM; tiny N (swap-AB decode) uses the narrowest tile that covers it.
+  const long long mt = (g.M + BM - 1) / BM;
+  if (g.N <= 32) return launch<32, 5, 2>(g, stream);
+  if (g.N <= 64) return launch<64, 4, 2>(g, stream);
+  const long long tiles256 = mt * ((g.N + 255) / 256) * g.Z;
+  if (g.N > 128 && tiles256 >= 2 * 148) return launch<256, 4, 1>(g, stream);
+  return launch<128, 3, 2>(g, stream);
+}
+
+}  // namespace bw

@@ -1,0 +1,149 @@
+// Launchers for the non-GEMM kernels of the Whisper hot path.  T is the activation/weight storage
+// type: bf16 (product mode) or float (fp32 validation mode).  The residual stream is always fp32.
+#pragma once
+#include <atomic>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace bw {
+
+// ---- mel.cu ----
+size_t mel_tables_floats();
+void mel_fill_tables(float* host);
+void mel_power(const float* pcm_dev, long long n, long long padding, const float* tables, const float* filters,
+               const int2* ranges, int n_mels, float* logmel, int ld, int n_real, int total_frames, int* gmax_bits,
+               cudaStream_t stream);
+void mel_normalize_f32(const float* logmel, int ld, int n_real, const int* gmax_bits, int n_mels, int total_frames,
+                       float* out, cudaStream_t stream);
+template <typename T>
+void mel_window(const float* logmel, int ld, int n_real, const int* gmax_bits, int n_mels, int seek, int segment_size,
+                T* A1, cudaStream_t stream);
+
+// ---- elementwise.cu ----
+// out[r][:] = LayerNorm(x[r][:]) * gamma + beta   (fp32 statistics, eps 1e-5)
+template <typename T>
+void layernorm(const float* x, const float* gamma, const float* beta, T* out, int rows, int d, cudaStream_t stream);
+void layernorm_f32out(const float* x, const float* gamma, const float* beta, float* out, int rows, int d, cudaStream_t stream);
+// gathered variant for the decoder's final LN: out[i] = LN(x[rows_idx[i]])
+template <typename T>
+void layernorm_gather(const float* x, const int* rows_idx, const float* gamma, const float* beta, T* out, int n, int d,
+                      cudaStream_t stream);
+// conv2 operand: A2[b*1500+t][k*d + c] = y1[b][2t+k-1][c] (zero outside [0,3000))
+template <typename T>
+void im2col_conv2(const T* y1, T* A2, int batch, int d, cudaStream_t stream);
+// fp32 -> T conversion (weight packing), optional [co][ci][k] -> [co][k][ci] conv-weight permute
+template <typename T>
+void convert_f32(const float* src, T* dst, long long n, cudaStream_t stream);
+template <typename T>
+void permute_conv_weight(const float* src, T* dst, int co, int ci, cudaStream_t stream);
+void f32_from_bf16(const bf16* src, float* dst, long long n, cudaStream_t stream);
+
+// ---- attention.cu ----
+// Encoder self-attention, non-causal, head dim 64: qkv [B*T, 3*d] (q | k | v), out [B*T, d].
+template <typename T>
+void attn_encoder_simt(const T* qkv, T* out, int batch, int T_len, int n_head, cudaStream_t stream);
+void attn_encoder_tc(const bf16* qkv, bf16* out, int batch, int T_len, int n_head, cudaStream_t stream);
+
+// Decoder row descriptors (one row = one (sequence, position) token fed through the decoder step)
+struct DecRows {
+  int n_rows = 0;
+  const int* row_seq = nullptr;   // [R] sequence slot (state arrays are indexed by it)
+  const int* row_pos = nullptr;   // [R] position of the row's token in its sequence
+  const int* row_tok = nullptr;   // [R] token id, or -1: take next_tok[row_seq]
+};
+
+// x[r] = E[tok] + pos_emb[pos]  (fp32 residual stream)
+template <typename T>
+void dec_embed(const DecRows& rows, const int* next_tok, const T* tok_emb, const T* pos_emb, float* x, int d,
+               cudaStream_t stream);
+
+// Self-attention KV pool: unit u (= sequence slot) holds [L][2][n_ctx][d] of one hypothesis slot.
+// Beams of one request occupy adjacent units starting at seq_first[s]; the key/value of sequence s at
+// position t lives in unit seq_first[s] + anc[s][t] (beam reordering never copies K/V, it rewrites anc).
+struct SelfKV {
+  void* pool = nullptr;                // T*
+  long long unit_stride = 0;           // elements per unit = L*2*n_ctx*d
+  int n_ctx = 448;
+  const int* seq_first = nullptr;      // [S] first sequence slot of the owning request
+  const unsigned char* anc = nullptr;  // [S][n_ctx] beam slot holding position t (current ping-pong buffer)
+};
+// scatter this step's k/v (from qkv rows [R, 3d]) into the pool for `layer`
+template <typename T>
+void dec_kv_append(const DecRows& rows, const T* qkv, const SelfKV& kv, int layer, int d, cudaStream_t stream);
+// out[r] = softmax(q_r . K[0..pos_r]) V   (head dim 64)
+template <typename T>
+void dec_self_attention(const DecRows& rows, const T* qkv, const SelfKV& kv, int layer, int d, int n_head, T* out,
+                        cudaStream_t stream);
+// Cross attention over the cached encoder K/V of each row's segment:
+// cross cache slot layout [L][T_enc][2*d] (k | v). Group g = rows [first_row, first_row + n_rows) that share
+// segment slot group_xslot[g] (the beams of one request); groups tile [0, n_rows) in order.
+struct CrossKV {
+  const void* cache = nullptr;   // T*
+  long long slot_stride = 0;     // elements per slot = L*T_enc*2*d
+  int T_enc = 1500;
+};
+template <typename T>
+void dec_cross_attention(const int* group_first_row, const int* group_n_rows, const int* group_xslot, int n_groups,
+                         int max_group_rows, int n_rows, const T* q, const CrossKV& kv, int layer, int d, int n_head, T* out,
+                         float* workspace, cudaStream_t stream);
+size_t dec_cross_workspace_floats(int n_rows, int n_head);
+
+// ---- sampling.cu ----
+struct TokenTables {
+  int eot, sot, sot_prev, sot_lm, no_speech, no_timestamps, timestamp_begin, translate, transcribe;
+  int first_language_token, num_languages;
+  int n_blank;
+  int blank[4];                           // SuppressBlank ids: encode(" ") + eot
+  const unsigned int* suppress_bits = nullptr;  // [ceil(V/32)] bit set = SuppressTokens id
+};
+
+constexpr int kMaxBeam = 8;           // beams per request (n_group)
+constexpr int kMaxCand = kMaxBeam + 1;
+constexpr int kMaxFinished = 16;
+
+// Per-request decoding state (device, struct of arrays indexed by request slot q)
+struct ReqState {
+  int* n_beam;          // G
+  int* greedy;          // GreedyDecoder semantics (G = 1)
+  int* sample_begin;    // index of the first sampled position
+  int* cur_len;         // tokens so far (positions [0, cur_len))
+  int* first_seq;       // sequence slot of beam 0 (beams are adjacent)
+  int* without_ts;      // ApplyTimestampRules off
+  int* suppress_blank;
+  int* max_initial_ts;  // index or -1
+  int* max_candidates;  // round(beam * patience)
+  int* n_finished;      // finished pool fill
+  float* fin_score;     // [Q][kMaxFinished]
+  int* fin_pos;         // [Q][kMaxFinished] position of last token before EOT
+  int* fin_slot;        // [Q][kMaxFinished] beam slot holding that token
+  int* completed;       // out: all candidates collected
+  float* no_speech_prob;
+  int* tok;             // [Q][n_ctx][kMaxBeam] token written at (position, slot)
+  unsigned char* parent;  // [Q][n_ctx][kMaxBeam] slot of the predecessor token
+};
+struct SeqState {
+  float* sum_logprob;   // [S]
+  int* next_tok;        // [S] most recent token of the hypothesis (fed at the next step)
+  int* prev_tok;        // [S] the token before it
+  int* last_ts;         // [S] most recent sampled timestamp token, or -1
+  int* seq_first;       // [S] first sequence slot of the owning request
+  unsigned char* anc[2];  // ping-pong [S][n_ctx]
+};
+
+// Fused logit filters + log-softmax statistics + top-(G+1) per logits row (warp-level reductions).
+// Sample row i reads logits row srow_lrow[i]; cand_tok/cand_lp: [n_sample_rows][kMaxCand]
+void sample_topk(const float* logits, int ld, int V, const int* srow_lrow, const int* lrow_req, const int* lrow_seq, int n_lrows,
+                 const TokenTables& tt, const ReqState& rs, const SeqState& ss, int anc_cur, int* cand_tok, float* cand_lp,
+                 cudaStream_t stream);
+// Beam bookkeeping (BeamSearchDecoder.update / GreedyDecoder.update) for each active request.
+void beam_update(const int* active_req, const int* req_first_lrow, int n_active, const TokenTables& tt, const ReqState& rs,
+                 const SeqState& ss, int anc_cur, int n_ctx, const int* cand_tok, const float* cand_lp, cudaStream_t stream);
+// probs_at_sot.softmax()[no_speech] for requests in their first step
+void no_speech_prob(const float* logits, int ld, int V, const int* lrows, const int* reqs, int n, int no_speech_id,
+                    float* out_prob, cudaStream_t stream);
+// detect_language: softmax over the language tokens of one logits row
+void language_probs(const float* logits, int V, int first_lang, int n_lang, float* probs_out, int* argmax_out,
+                    cudaStream_t stream);
+
+}  // namespace bw

@@ -1,0 +1,201 @@
+"""Python face of one GPU engine (thin ctypes layer over the C ABI; no torch in the call path)."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from .melfilters import mel_filterbank
+from .synth import ModelDims
+from .vocab import Vocab, vocab_for
+
+
+def _as_f32(a) -> np.ndarray:
+    if hasattr(a, "detach"):  # torch tensor hand-off
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Call:
+    """One `transcribe()` call: PCM resident on the device + its whole-call log-mel."""
+
+    def __init__(self, engine: "Engine", audio: np.ndarray):
+        self.engine = engine
+        self._h = C.c_void_p()
+        audio = _as_f32(audio)
+        L.check(engine.lib.bw_call_open(engine.handle, audio.ctypes.data_as(L.c_f32_p), audio.size, C.byref(self._h)),
+                "bw_call_open")
+        n = C.c_int32()
+        L.check(engine.lib.bw_call_content_frames(self._h, C.byref(n)), "bw_call_content_frames")
+        self.content_frames = n.value
+
+    def decode(self, seek: int, initial: Sequence[int], sot_index: int, beam_size: Optional[int], patience: Optional[float],
+               length_penalty: Optional[float], sample_len: int = 0, without_timestamps: bool = False,
+               suppress_blank: bool = True, max_initial_timestamp_index: Optional[int] = 50) -> dict:
+        init = (C.c_int32 * len(initial))(*initial)
+        o = L.DecodeOptsC(init, len(initial), sot_index, int(beam_size or 0), float(patience or 0.0),
+                          -1.0 if length_penalty is None else float(length_penalty), int(sample_len),
+                          int(bool(without_timestamps)), int(bool(suppress_blank)),
+                          -1 if max_initial_timestamp_index is None else int(max_initial_timestamp_index))
+        r = L.ResultC()
+        L.check(self.engine.lib.bw_call_decode(self._h, int(seek), C.byref(o), C.byref(r)), "bw_call_decode")
+        return {"tokens": list(r.tokens[: r.n_tokens]), "sum_logprob": r.sum_logprob, "avg_logprob": r.avg_logprob,
+                "no_speech_prob": r.no_speech_prob, "n_steps": r.n_steps, "t_queue": r.t_queue, "t_encode": r.t_encode,
+                "t_decode": r.t_decode}
+
+    def detect_language(self, seek: int = 0):
+        r = L.LangResultC()
+        L.check(self.engine.lib.bw_call_detect_language(self._h, int(seek), C.byref(r)), "bw_call_detect_language")
+        return r.language_token, np.array(r.probs[: r.n_languages], dtype=np.float32)
+
+    def close(self) -> None:
+        if self._h:
+            self.engine.lib.bw_call_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One weight copy + KV pools + scheduler thread on one GPU."""
+
+    def __init__(self, dims: ModelDims, state: Dict[str, object], device_index: int = 0, compute: str = "bf16",
+                 max_segments: int = 0, max_sequences: int = 0, max_encoder_batch: int = 0, flags: int = 0):
+        self.lib = L.load()
+        if self.lib.bw_device_count() <= 0:
+            raise L.B200WhisperError("no CUDA device visible: the b200_whisper backend has no CPU fallback")
+        self.dims = dims
+        self.vocab: Vocab = vocab_for(dims.n_vocab)
+        self.compute = compute
+        self.device_index = device_index
+        self.handle = C.c_void_p()
+        self._lock = threading.Lock()
+        cd = L.ModelDimsC(*[getattr(dims, f) for f, _ in L.ModelDimsC._fields_])
+        cfg = L.EngineConfigC(device_index, L.BW_COMPUTE_FP32 if compute == "fp32" else L.BW_COMPUTE_BF16, max_segments,
+                              max_sequences, max_encoder_batch, flags)
+        L.check(self.lib.bw_engine_create(C.byref(cd), C.byref(cfg), C.byref(self.handle)), "bw_engine_create")
+        try:
+            self._load(state)
+            v = self.vocab
+            sup = v.suppress_tokens()
+            sup_c = (C.c_int32 * len(sup))(*sup)
+            blank = list(v.blank) + [v.eot]
+            blank_c = (C.c_int32 * len(blank))(*blank)
+            tt = L.TokenTablesC(v.eot, v.sot, v.sot_prev, v.sot_lm, v.no_speech, v.no_timestamps, v.timestamp_begin, v.translate,
+                                v.transcribe, v.first_language_token, v.num_languages, sup_c, len(sup), blank_c, len(blank))
+            L.check(self.lib.bw_engine_set_tables(self.handle, C.byref(tt)), "bw_engine_set_tables")
+            filt = np.ascontiguousarray(mel_filterbank(dims.n_mels), dtype=np.float32)
+            L.check(self.lib.bw_engine_set_mel_filters(self.handle, filt.ctypes.data_as(L.c_f32_p)), "bw_engine_set_mel_filters")
+            L.check(self.lib.bw_engine_finalize(self.handle), "bw_engine_finalize")
+        except Exception:
+            self.lib.bw_engine_destroy(self.handle)
+            self.handle = C.c_void_p()
+            raise
+
+    def _load(self, state: Dict[str, object]) -> None:
+        for name, t in state.items():
+            if hasattr(t, "detach"):
+                import torch
+
+                t = t.detach()
+                if t.dtype == torch.bfloat16:
+                    arr = t.contiguous().cpu().view(torch.int16).numpy()
+                    dtype = L.BW_BF16
+                elif t.dtype == torch.float16:
+                    arr = t.contiguous().cpu().view(torch.int16).numpy()
+                    dtype = L.BW_F16
+                else:
+                    arr = t.to(torch.float32).contiguous().cpu().numpy()
+                    dtype = L.BW_F32
+            else:
+                arr = np.ascontiguousarray(t, dtype=np.float32)
+                dtype = L.BW_F32
+            if arr.ndim > 4:
+                raise ValueError(f"{name}: rank {arr.ndim} tensor")
+            shape = (C.c_int64 * 4)(*(list(arr.shape) + [1] * (4 - arr.ndim)))
+            desc = L.TensorDescC(name.encode(), arr.ctypes.data_as(C.c_void_p), dtype, arr.ndim, shape)
+            L.check(self.lib.bw_engine_load_weights(self.handle, C.byref(desc), 1), f"bw_engine_load_weights({name})")
+
+    # ---- stage-level ----
+    def mel(self, audio, padding: int = 0) -> np.ndarray:
+        audio = _as_f32(audio)
+        frames = (audio.size + padding) // 160
+        out = np.empty((self.dims.n_mels, frames), dtype=np.float32)
+        n = C.c_int32()
+        L.check(self.lib.bw_mel(self.handle, audio.ctypes.data_as(L.c_f32_p), audio.size, padding, out.ctypes.data_as(L.c_f32_p),
+                                C.byref(n)), "bw_mel")
+        assert n.value == frames
+        return out
+
+    def encode(self, mel) -> np.ndarray:
+        mel = _as_f32(mel)
+        if mel.ndim == 2:
+            mel = mel[None]
+        b = mel.shape[0]
+        assert mel.shape[1:] == (self.dims.n_mels, 3000), mel.shape
+        out = np.empty((b, 1500, self.dims.n_audio_state), dtype=np.float32)
+        L.check(self.lib.bw_encode(self.handle, mel.ctypes.data_as(L.c_f32_p), b, out.ctypes.data_as(L.c_f32_p)), "bw_encode")
+        return out
+
+    def decode_logits(self, mel_window, tokens: Sequence[int]) -> np.ndarray:
+        mel = _as_f32(mel_window)
+        assert mel.shape == (self.dims.n_mels, 3000)
+        toks = (C.c_int32 * len(tokens))(*tokens)
+        out = np.empty((len(tokens), self.dims.n_vocab), dtype=np.float32)
+        L.check(self.lib.bw_decode_logits(self.handle, mel.ctypes.data_as(L.c_f32_p), toks, len(tokens), out.ctypes.data_as(L.c_f32_p)),
+                "bw_decode_logits")
+        return out
+
+    def open_call(self, audio) -> Call:
+        return Call(self, audio)
+
+    def stats(self) -> Dict[str, int]:
+        buf = (C.c_int64 * len(L.STAT_NAMES))()
+        L.check(self.lib.bw_engine_stats(self.handle, buf, len(L.STAT_NAMES)), "bw_engine_stats")
+        return dict(zip(L.STAT_NAMES, list(buf)))
+
+    # ---- timing helpers used by bench.py (CUDA events inside the library) ----
+    def _bench(self, fn, *args):
+        ms, q = C.c_float(), C.c_double()
+        L.check(fn(self.handle, *args, C.byref(ms), C.byref(q)), fn.__name__)
+        return ms.value, q.value
+
+    def bench_mel(self, n_samples: int, iters: int):
+        return self._bench(self.lib.bw_bench_mel, C.c_int64(n_samples), iters)
+
+    def bench_encoder(self, batch: int, iters: int):
+        return self._bench(self.lib.bw_bench_encoder, batch, iters)
+
+    def bench_cross_attention(self, n_segments: int, n_group: int, iters: int):
+        return self._bench(self.lib.bw_bench_cross_attention, n_segments, n_group, iters)
+
+    def bench_decoder_step(self, n_segments: int, n_group: int, context_len: int, iters: int):
+        return self._bench(self.lib.bw_bench_decoder_step, n_segments, n_group, context_len, iters)
+
+    def retain(self) -> None:
+        self.lib.bw_engine_retain(self.handle)
+
+    def close(self) -> None:
+        with self._lock:
+            if self.handle:
+                self.lib.bw_engine_destroy(self.handle)
+                self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
