@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- RTFx (audio-seconds transcribed per wall-second) of the Whisper hot path on B200.
+
+Workload (BASELINE.json configs[4], the per-GPU shard of the config the metric is quoted on):
+large-v3 (128 mel bins), realtime decode profile (beam_size=1), 128 concurrent streaming sessions
+per GPU, each submitting one partial-decode window of its last 2-10 s of audio per step (seeded
+lengths; every window is a full 30 s encoder pass, as in the reference).  Random-init weights of the
+named architecture and synthetic audio (no network) -> hypotheses never reach EOT and every window
+runs the full 224 decoder steps: the worst case.  One "step" = one such batch of 128 windows.
+
+  value : whole-job RTFx with the PCM already resident in HBM, timed with CUDA events on the engine
+          stream around mel -> encoder -> cross-KV -> 224 batched decoder steps (max over ranks)
+  e2e   : the same metric through the public backend (`B200WhisperBackend.transcribe`, the call
+          ModelWorker makes, reference worker.py:125) from 128 host threads with host numpy buffers;
+          host->device PCM copies and device->host results are inside the timed region
+  --impl reference : the reference's CPU path (fp32 torch restatement of torch_whisper, `oracle/`)
+          on all host cores, one window per step (bounded sample), same metric/config
+
+Weak scaling: sessions per GPU are fixed; ranks never exchange data (sessions shard), torch.distributed
+is used only for the barrier and the max-over-ranks reduction.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+REALTIME = {"beam_size": 1, "best_of": 1, "patience": 1.0, "temperature": 0.0, "length_penalty": 1.0,
+            "without_timestamps": True, "compression_ratio_threshold": 2.4, "no_speech_threshold": 0.6,
+            "log_prob_threshold": -1.0, "language": "en", "task": "transcribe"}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="large-v3")
+    ap.add_argument("--sessions", type=int, default=128, help="concurrent sessions per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def window_lengths(rank: int, sessions: int):
+    rng = np.random.default_rng(4242 + rank)
+    return [float(np.round(rng.uniform(2.0, 10.0), 2)) for _ in range(sessions)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def barrier_max(dist, local, value: float) -> float:
+    if dist is None:
+        return value
+    import torch
+
+    t = torch.tensor([value], device=f"cuda:{local}", dtype=torch.float64)
+    dist.barrier()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def cpu_oracle_window(state, model_name: str, seconds: float, sample_len=None, threads: int = 0):
+    """One window through the CPU oracle (reference torch_whisper path restated); returns (elapsed s, cores)."""
+    import torch
+
+    from b200_whisper.synth import MODEL_DIMS, synth_audio
+    from oracle import whisper_oracle as wo
+
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dims = MODEL_DIMS[model_name]
+    model = wo.Whisper(wo.ModelDimensions(**dims.__dict__), state)
+    audio = synth_audio(999, seconds)
+    opts = dict(REALTIME)
+    if sample_len:
+        opts["sample_len"] = sample_len
+    t0 = time.perf_counter()
+    wo.backend_transcribe(model, audio, opts)
+    return time.perf_counter() - t0, cores
+
+
+def run_reference(args):
+    rank, world, local, dist = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    from b200_whisper.synth import MODEL_DIMS, random_state_dict
+
+    state = random_state_dict(MODEL_DIMS[args.model], 0, emb_std=0.1)
+    seconds = 6.0
+    for _ in range(args.warmup):  # nothing to warm on the CPU but threads/allocator: short decodes
+        cpu_oracle_window(state, args.model, seconds, sample_len=4, threads=args.cpu_threads)
+    times = []
+    cores = 1
+    for _ in range(args.steps):
+        dt, cores = cpu_oracle_window(state, args.model, seconds, threads=args.cpu_threads)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = seconds / (ms / 1e3)
+    sample = f"1 session x 1 partial window ({seconds:.0f} s audio -> full 30 s encoder pass + 224 decoder steps) per step"
+    print(json.dumps({
+        "impl": "reference", "metric": "RTFx (audio-seconds transcribed per second)", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic audio, random-init weights",
+        "config": {"workload": f"{args.model} realtime profile (beam_size=1), partial windows 2-10 s, one window per step on host cores",
+                   "note": "warm-up steps decode 4 tokens only; timed steps are full windows"},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_b200(args):
+    rank, world, local, dist = dist_setup(args.gpus)
+    import torch  # device plumbing only (set_device / barrier)
+
+    torch.cuda.set_device(local)
+    from b200_whisper.backend import B200WhisperBackend, _ENGINES
+    from b200_whisper.synth import MODEL_DIMS, random_state_dict, synth_audio
+
+    pk = peaks()
+    S = args.sessions
+    dims = MODEL_DIMS[args.model]
+    spec = f"random:{args.model}:0:0.1"
+    state = random_state_dict(dims, 0, emb_std=0.1)
+    # hand the already-generated weights to the registry so the CPU baseline can reuse them
+    from b200_whisper import backend as bk
+
+    orig_loader = bk.load_checkpoint
+    bk.load_checkpoint = lambda name: (dims, state, name) if name == spec else orig_loader(name)
+    handles = [B200WhisperBackend(spec, f"cuda:{local}", "bfloat16", max_segments=S, max_sequences=max(2 * S, 8),
+                                  max_encoder_batch=min(16, S)) for _ in range(S)]
+    bk.load_checkpoint = orig_loader
+    eng = handles[0].engine
+    lengths = window_lengths(rank, S)
+    audios = [synth_audio(rank * 100000 + i, lengths[i]) for i in range(S)]
+    audio_sec = float(sum(a.size for a in audios)) / 16000.0
+    n_steps = dims.n_text_ctx // 2  # 224: random weights never emit EOT (worst case)
+
+    # ---- value: device-timed pipeline on resident PCM ----
+    for _ in range(args.warmup):
+        eng.bench_pipeline(audios, 1, n_steps)
+    barrier_max(dist, local, 0.0)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = eng.stats()["kernel_launches"]
+    total_ms = 0.0
+    for _ in range(args.steps):
+        total_ms += eng.bench_pipeline(audios, 1, n_steps)
+    torch.cuda.synchronize()
+    launches = eng.stats()["kernel_launches"] - l0
+    total_ms = barrier_max(dist, local, total_ms)
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = total_ms / args.steps
+    value = world * audio_sec / (ms_per_step / 1e3)
+
+    # ---- e2e: public backend call from S host threads, host buffers ----
+    lat = []
+
+    def e2e_step(record: bool):
+        def work(i):
+            t0 = time.perf_counter()
+            handles[i].transcribe(audios[i], REALTIME)
+            if record:
+                lat.append(time.perf_counter() - t0)
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(S)]
+        t0 = time.perf_counter()
+        [t.start() for t in th]
+        [t.join() for t in th]
+        return time.perf_counter() - t0
+
+    for _ in range(max(1, args.warmup - 1)):
+        e2e_step(False)
+    barrier_max(dist, local, 0.0)
+    s0 = eng.stats()
+    e2e_total = 0.0
+    for _ in range(args.steps):
+        e2e_total += e2e_step(True)
+    s1 = eng.stats()
+    e2e_total = barrier_max(dist, local, e2e_total)
+    e2e_value = world * audio_sec / (e2e_total / args.steps)
+    lat_sorted = sorted(lat)
+    p95 = lat_sorted[max(0, int(np.ceil(0.95 * len(lat_sorted))) - 1)] if lat_sorted else None  # nearest rank
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (decoder cross-attention, HBM-bound), timed live ----
+    xa_ms, xa_bytes = eng.bench_cross_attention(S, 1, 64)
+    achieved = xa_bytes / (xa_ms * 1e-3) / 1e9
+    stages = {}
+    enc_b = min(16, S)
+    ems, eflops = eng.bench_encoder(enc_b, 3)
+    stages["encoder"] = {"batch": enc_b, "ms": ems, "tflops": eflops / (ems * 1e-3) / 1e12,
+                         "frac_of_bf16_sustained": eflops / (ems * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]}
+    dms, dbytes = eng.bench_decoder_step(S, 1, 100, 20)
+    stages["decoder_step"] = {"segments": S, "context": 100, "ms": dms, "gbs": dbytes / (dms * 1e-3) / 1e9,
+                              "frac_of_hbm": dbytes / (dms * 1e-3) / 1e9 / pk["hbm_gbs"]}
+    mms, mbytes = eng.bench_mel(96000, 20)
+    stages["mel"] = {"audio_s": 6.0, "ms": mms, "gbs": mbytes / (mms * 1e-3) / 1e9}
+
+    out = {
+        "metric": "RTFx (audio-seconds transcribed per second)", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic audio, random-init weights (no EOT: 224 decoder steps per window)",
+        "config": {"workload": f"{args.model} realtime profile (beam_size=1), {S} concurrent sessions per GPU, one 2-10 s "
+                               f"partial window per session per step (configs[4] per-GPU shard)",
+                   "sessions_per_gpu": S, "audio_s_per_step_per_gpu": audio_sec, "decoder_steps_per_window": n_steps,
+                   "l2": "inputs larger than L2 (cross-KV cache %.1f GB per step)" % (S * dims.n_text_layer * 1500 * 2 * dims.n_text_state * 2 / 1e9),
+                   "timing": "CUDA events on the engine stream inside libb200whisper.so, max over ranks", "peaks": pk["source"]},
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // args.steps,
+                "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // args.steps,
+                "ms_per_step": 1e3 * e2e_total / args.steps, "p95_partial_latency_s": p95, "host_threads": S},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "dec_cross_attention_kernel<bf16,1>", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None, "ms_per_launch": xa_ms,
+                     "algorithmic_bytes_per_launch": xa_bytes},
+        "stages": stages,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        dt, cores = cpu_oracle_window(state, args.model, 6.0, threads=args.cpu_threads)
+        out["cpu_baseline"] = {"value": 6.0 / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                               "sample": "1 session x 1 partial window (6 s audio, full 30 s encoder pass + 224 decoder steps), "
+                                         f"fp32 torch on {cores} threads, {dt:.1f} s"}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -167,6 +167,11 @@ int bw_bench_mel(bw_engine*, int64_t n_samples, int32_t iters, float* ms_out, do
 int bw_bench_decoder_step(bw_engine*, int32_t n_segments, int32_t n_group, int32_t context_len, int32_t iters,
                           float* ms_out, double* bytes_out);
 
+/* Whole hot path on device-resident PCM (mel -> encoder -> cross-KV -> n_steps batched decoder steps), one
+ * CUDA-event pair on the engine stream; returns total ms. */
+int bw_bench_pipeline(bw_engine*, const float* pcm_host, const int64_t* offsets, const int64_t* lengths,
+                      int32_t n_segments, int32_t n_group, int32_t n_steps, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

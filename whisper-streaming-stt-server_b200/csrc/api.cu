@@ -957,6 +957,47 @@ int bw_bench_encoder(bw_engine* e, int32_t batch, int32_t iters, float* ms_out, 
   BW_API_END
 }
 
+namespace {
+// Synthetic resident decode: `n_segments` windows x `n_group` hypotheses, positions [start_len, start_len + n_steps).
+// Same launches, control upload and per-step completion read-back as the scheduler's decode_step().
+void synthetic_init(bw_engine* e, Ctl& ctl, int n_segments, int n_group, int start_len) {
+  for (int i = 0; i < n_segments; ++i) {
+    int* rec = ctl.init + i * 12;
+    rec[0] = i; rec[1] = n_group; rec[2] = 0; rec[3] = 3; rec[4] = start_len; rec[5] = i * n_group; rec[6] = 0; rec[7] = 1;
+    rec[8] = 50; rec[9] = kMaxFinished; rec[10] = e->tt.timestamp_begin - 1000; rec[11] = 0;
+  }
+  int* init_dev = e->d_ctrl.as<int>() + (ctl.init - e->h_ctrl);
+  BW_CUDA(cudaMemcpyAsync(init_dev, ctl.init, (size_t)n_segments * 48, cudaMemcpyHostToDevice, e->stream));
+  engine_init_requests(e, init_dev, n_segments);
+  BW_CUDA(cudaStreamSynchronize(e->stream));
+}
+void synthetic_step(bw_engine* e, Ctl& ctl, int n_segments, int n_group, int cur) {
+  int R = 0, SR = 0;
+  for (int i = 0; i < n_segments; ++i) {
+    ctl.grp_first[i] = R; ctl.grp_n[i] = n_group; ctl.grp_x[i] = i;
+    ctl.act_req[i] = i; ctl.act_first[i] = SR;
+    for (int j = 0; j < n_group; ++j) {
+      ctl.row_seq[R] = i * n_group + j; ctl.row_pos[R] = cur - 1; ctl.row_tok[R] = -1;
+      ctl.lrow_src[R] = R; ctl.srow_lrow[SR] = R; ctl.srow_req[SR] = i; ctl.srow_seq[SR] = i * n_group + j;
+      ++R; ++SR;
+    }
+  }
+  int* dbase = e->d_ctrl.as<int>();
+  auto dev = [&](int* h) { return dbase + (h - e->h_ctrl); };
+  BW_CUDA(cudaMemcpyAsync(dbase, e->h_ctrl, (size_t)(ctl.init - e->h_ctrl) * 4, cudaMemcpyHostToDevice, e->stream));
+  engine_decoder_layers(e, R, n_segments, n_group, R, dev(ctl.row_seq), dev(ctl.row_pos), dev(ctl.row_tok), dev(ctl.grp_first),
+                        dev(ctl.grp_n), dev(ctl.grp_x), dev(ctl.lrow_src));
+  const int V = e->dims.n_vocab;
+  sample_topk(e->d_logits.as<float>(), V, V, dev(ctl.srow_lrow), dev(ctl.srow_req), dev(ctl.srow_seq), SR, e->tt, e->rs, e->ss,
+              e->anc_cur, e->d_cand_tok.as<int>(), e->d_cand_lp.as<float>(), e->stream);
+  beam_update(dev(ctl.act_req), dev(ctl.act_first), n_segments, e->tt, e->rs, e->ss, e->anc_cur, e->dims.n_text_ctx,
+              e->d_cand_tok.as<int>(), e->d_cand_lp.as<float>(), e->stream);
+  BW_CUDA(cudaMemcpyAsync(e->h_flags, e->rs.completed, (size_t)e->Q * 4, cudaMemcpyDeviceToHost, e->stream));
+  BW_CUDA(cudaStreamSynchronize(e->stream));
+  e->anc_cur ^= 1;
+}
+}  // namespace
+
 // One full decoder step (all layers + logits + sampling + beam update) over `n_segments` resident
 // windows with `n_group` hypotheses each at context length `context_len`, timed with CUDA events.
 int bw_bench_decoder_step(bw_engine* e, int32_t n_segments, int32_t n_group, int32_t context_len, int32_t iters, float* ms_out,
@@ -972,50 +1013,74 @@ int bw_bench_decoder_step(bw_engine* e, int32_t n_segments, int32_t n_group, int
   Ctl ctl;
   ctl.layout(e->h_ctrl, e->R_max, e->LR_max, e->Q);
   BW_CUDA(cudaMemsetAsync(e->cross_cache.p, 0, (size_t)n_segments * (e->cross_cache.bytes / e->Q), e->stream));
-  for (int i = 0; i < n_segments; ++i) {
-    int* rec = ctl.init + i * 12;
-    rec[0] = i; rec[1] = n_group; rec[2] = 0; rec[3] = 3; rec[4] = context_len; rec[5] = i * n_group; rec[6] = 0; rec[7] = 1;
-    rec[8] = 50; rec[9] = kMaxFinished; rec[10] = e->tt.timestamp_begin - 1000; rec[11] = 0;
-  }
-  int* init_dev = e->d_ctrl.as<int>() + (ctl.init - e->h_ctrl);
-  BW_CUDA(cudaMemcpyAsync(init_dev, ctl.init, (size_t)n_segments * 48, cudaMemcpyHostToDevice, e->stream));
-  engine_init_requests(e, init_dev, n_segments);
-  BW_CUDA(cudaStreamSynchronize(e->stream));
+  synthetic_init(e, ctl, n_segments, n_group, context_len);
   int cur = context_len;
-  auto step = [&] {
-    int R = 0, SR = 0;
-    for (int i = 0; i < n_segments; ++i) {
-      ctl.grp_first[i] = R; ctl.grp_n[i] = n_group; ctl.grp_x[i] = i;
-      ctl.act_req[i] = i; ctl.act_first[i] = SR;
-      for (int j = 0; j < n_group; ++j) {
-        ctl.row_seq[R] = i * n_group + j; ctl.row_pos[R] = cur - 1; ctl.row_tok[R] = -1;
-        ctl.lrow_src[R] = R; ctl.srow_lrow[SR] = R; ctl.srow_req[SR] = i; ctl.srow_seq[SR] = i * n_group + j;
-        ++R; ++SR;
-      }
-    }
-    int* dbase = e->d_ctrl.as<int>();
-    auto dev = [&](int* h) { return dbase + (h - e->h_ctrl); };
-    BW_CUDA(cudaMemcpyAsync(dbase, e->h_ctrl, (size_t)(ctl.init - e->h_ctrl) * 4, cudaMemcpyHostToDevice, e->stream));
-    engine_decoder_layers(e, R, n_segments, n_group, R, dev(ctl.row_seq), dev(ctl.row_pos), dev(ctl.row_tok), dev(ctl.grp_first),
-                          dev(ctl.grp_n), dev(ctl.grp_x), dev(ctl.lrow_src));
-    const int V = e->dims.n_vocab;
-    sample_topk(e->d_logits.as<float>(), V, V, dev(ctl.srow_lrow), dev(ctl.srow_req), dev(ctl.srow_seq), SR, e->tt, e->rs, e->ss,
-                e->anc_cur, e->d_cand_tok.as<int>(), e->d_cand_lp.as<float>(), e->stream);
-    beam_update(dev(ctl.act_req), dev(ctl.act_first), n_segments, e->tt, e->rs, e->ss, e->anc_cur, e->dims.n_text_ctx,
-                e->d_cand_tok.as<int>(), e->d_cand_lp.as<float>(), e->stream);
-    BW_CUDA(cudaMemcpyAsync(e->h_flags, e->rs.completed, (size_t)e->Q * 4, cudaMemcpyDeviceToHost, e->stream));
-    BW_CUDA(cudaStreamSynchronize(e->stream));
-    e->anc_cur ^= 1;
-    ++cur;
-  };
-  step();
+  synthetic_step(e, ctl, n_segments, n_group, cur++);
   EvTimer t(e->stream);
   t.start();
-  for (int i = 0; i < iters; ++i) step();
+  for (int i = 0; i < iters; ++i) synthetic_step(e, ctl, n_segments, n_group, cur++);
   *ms_out = t.stop_ms() / iters;
   const double ts = e->fp32 ? 4 : 2, d = e->dims.n_text_state, L = e->dims.n_text_layer, V = e->dims.n_vocab;
   const double S = (double)n_segments * n_group;
   *bytes_out = ts * (L * 14 * d * d + V * d) + n_segments * ts * L * 2 * 1500 * d + S * ts * L * 2 * (context_len + iters / 2.0) * d + 4 * S * V;
+  BW_API_END
+}
+
+// The whole hot path on device-resident PCM: log-mel -> encoder (batches of max_encoder_batch) -> cross-KV ->
+// `n_steps` batched decoder steps for `n_segments` windows of `n_samples` samples each.  One CUDA-event pair
+// on the engine stream brackets everything (bench.py `value`: inputs resident in HBM when timing starts).
+int bw_bench_pipeline(bw_engine* e, const float* pcm_host, const int64_t* offsets, const int64_t* lengths, int32_t n_segments,
+                      int32_t n_group, int32_t n_steps, float* ms_out) {
+  BW_API_BEGIN
+  BW_CHECK(e && pcm_host && offsets && lengths && ms_out, "bad argument");
+  BW_CHECK(e->state == 1, "engine not finalized");
+  BW_CHECK(n_segments >= 1 && n_segments <= e->Q && n_group >= 1 && n_group <= kMaxBeam && n_segments * n_group <= e->S, "exceeds pools");
+  BW_CHECK(n_steps >= 1 && 3 + n_steps < e->dims.n_text_ctx, "n_steps out of range");
+  for (int i = 0; i < n_segments; ++i) BW_CHECK(lengths[i] > 400 && lengths[i] <= e->call_pcm_cap, "segment length out of range");
+  DeviceGuard dg(e->device);
+  std::lock_guard<std::mutex> g(e->gpu_mu);
+  BW_CHECK(e->live.empty(), "engine busy");
+  std::vector<CallBuf> bufs;
+  {
+    std::lock_guard<std::mutex> cg(e->call_mu);
+    BW_CHECK((int)e->call_pool.size() >= n_segments, "not enough call buffers");
+    for (int i = 0; i < n_segments; ++i) { bufs.push_back(e->call_pool.back()); e->call_pool.pop_back(); }
+  }
+  for (int i = 0; i < n_segments; ++i)
+    BW_CUDA(cudaMemcpyAsync(bufs[i].pcm, pcm_host + offsets[i], (size_t)lengths[i] * 4, cudaMemcpyHostToDevice, e->stream));
+  BW_CUDA(cudaStreamSynchronize(e->stream));
+  Ctl ctl;
+  ctl.layout(e->h_ctrl, e->R_max, e->LR_max, e->Q);
+  auto frames = [&](int i, int& total, int& n_real, int& seg) {
+    total = (int)((lengths[i] + 480000) / 160);
+    n_real = (int)std::min<long long>(total, (lengths[i] + 200 + 159) / 160);
+    seg = std::min(3000, total - 3000);
+  };
+  EvTimer t(e->stream);
+  t.start();
+  for (int i = 0; i < n_segments; ++i) {
+    int total, n_real, seg;
+    frames(i, total, n_real, seg);
+    mel_power(bufs[i].pcm, lengths[i], 480000, e->mel_tables.as<float>(), e->mel_filters.as<float>(), e->mel_ranges.as<int2>(),
+              e->dims.n_mels, bufs[i].logmel, bufs[i].ld, n_real, total, bufs[i].gmax, e->stream);
+  }
+  for (int s0 = 0; s0 < n_segments; s0 += e->Be) {
+    const int nb = std::min(e->Be, n_segments - s0);
+    for (int i = 0; i < nb; ++i) {
+      int total, n_real, seg;
+      frames(s0 + i, total, n_real, seg);
+      engine_window_to_A1(e, bufs[s0 + i].logmel, bufs[s0 + i].ld, n_real, bufs[s0 + i].gmax, 0, seg, i);
+    }
+    engine_encoder_forward(e, nb);
+    for (int i = 0; i < nb; ++i) engine_cross_kv(e, i, s0 + i);
+  }
+  synthetic_init(e, ctl, n_segments, n_group, 3);
+  for (int i = 0; i < n_steps; ++i) synthetic_step(e, ctl, n_segments, n_group, 3 + i);
+  *ms_out = t.stop_ms();
+  {
+    std::lock_guard<std::mutex> cg(e->call_mu);
+    for (auto& b : bufs) e->call_pool.push_back(b);
+  }
   BW_API_END
 }
 

@@ -185,6 +185,18 @@ class Engine:
     def bench_decoder_step(self, n_segments: int, n_group: int, context_len: int, iters: int):
         return self._bench(self.lib.bw_bench_decoder_step, n_segments, n_group, context_len, iters)
 
+    def bench_pipeline(self, audios, n_group: int, n_steps: int) -> float:
+        """Device-timed ms for mel -> encoder -> cross-KV -> n_steps decoder steps over `audios` (resident PCM)."""
+        audios = [_as_f32(a) for a in audios]
+        flat = np.ascontiguousarray(np.concatenate(audios))
+        lengths = (C.c_int64 * len(audios))(*[a.size for a in audios])
+        offs = np.cumsum([0] + [a.size for a in audios[:-1]])
+        offsets = (C.c_int64 * len(audios))(*[int(o) for o in offs])
+        ms = C.c_float()
+        L.check(self.lib.bw_bench_pipeline(self.handle, flat.ctypes.data_as(L.c_f32_p), offsets, lengths, len(audios), n_group,
+                                           n_steps, C.byref(ms)), "bw_bench_pipeline")
+        return ms.value
+
     def retain(self) -> None:
         self.lib.bw_engine_retain(self.handle)
 

@@ -126,6 +126,9 @@ def normalize_language(language: Optional[str]) -> Optional[str]:
     return language
 
 
+_WARNED: set = set()
+
+
 class Detokenizer:
     """tiktoken-backed text codec when the rank file is available, `<id>` placeholders otherwise."""
 
@@ -153,7 +156,8 @@ class Detokenizer:
                 name=os.path.basename(path), explicit_n_vocab=n,
                 pat_str=r"""'s|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+""",
                 mergeable_ranks=ranks, special_tokens=special_tokens)
-        else:
+        elif name not in _WARNED:
+            _WARNED.add(name)
             LOGGER.warning("b200_whisper: no %s.tiktoken under B200_WHISPER_VOCAB_DIR; text is rendered as <id> placeholders", name)
 
     @property
