@@ -598,7 +598,7 @@ int bw_engine_finalize(bw_engine* e) {
   // decoder activations
   const size_t R = e->R_max, LR = e->LR_max;
   e->d_x.alloc(R * dm * 4);
-  e->d_xn.alloc(R * dm * ts); e->d_qkv.alloc(R * 3 * dm * ts); e->d_att.alloc(R * dm * ts); e->d_q.alloc(R * dm * ts);
+  e->d_xn.alloc(R * dm * ts); e->d_qkv.alloc(R * 3 * dm * 4); e->d_att.alloc(R * dm * ts); e->d_q.alloc(R * dm * 4);
   e->d_h.alloc(R * 4 * dm * ts); e->d_lnrows.alloc(LR * dm * ts);
   e->d_logits.alloc(LR * (size_t)d.n_vocab * 4);
   e->d_ws.alloc(dec_cross_workspace_floats((int)R, d.n_text_head) * 4);
@@ -1109,7 +1109,7 @@ int bw_bench_cross_attention(bw_engine* e, int32_t n_segments, int32_t n_group, 
                                  d.n_text_head, e->d_att.as<float>(), e->d_ws.as<float>(), e->stream);
     } else {
       CrossKV x; x.cache = e->cross_cache.p; x.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; x.T_enc = d.n_audio_ctx;
-      dec_cross_attention<bf16>(dev(ctl.grp_first), dev(ctl.grp_n), dev(ctl.grp_x), n_segments, n_group, R, e->d_q.as<bf16>(), x, layer, dm,
+      dec_cross_attention<bf16>(dev(ctl.grp_first), dev(ctl.grp_n), dev(ctl.grp_x), n_segments, n_group, R, e->d_q.as<float>(), x, layer, dm,
                                 d.n_text_head, e->d_att.as<bf16>(), e->d_ws.as<float>(), e->stream);
     }
   };

@@ -120,7 +120,7 @@ template <> struct Vec16<float> {
 
 template <typename T>
 __global__ void __launch_bounds__(128)
-dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const T* __restrict__ qkv,
+dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const float* __restrict__ qkv,
                           const T* __restrict__ pool, long long unit_stride, int n_ctx, const int* __restrict__ seq_first,
                           const unsigned char* __restrict__ anc, int layer, int d, T* __restrict__ out) {
   constexpr int VEC = Vec16<T>::N, LPR = 64 / VEC, RPW = 32 / LPR;
@@ -134,9 +134,8 @@ dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane % LPR, rg = lane / LPR;
   float qf[VEC];
-  Vec16<T>::load(qkv + (long long)r * 3 * d + h * 64 + sub * VEC, qf);
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) qf[i] *= 0.125f;
+  for (int i = 0; i < VEC; ++i) qf[i] = qkv[(long long)r * 3 * d + h * 64 + sub * VEC + i] * 0.125f;
   const long long koff = ((long long)(layer * 2 + 0) * n_ctx) * d + h * 64 + sub * VEC;
   const long long voff = ((long long)(layer * 2 + 1) * n_ctx) * d + h * 64 + sub * VEC;
   const int n = pos + 1;
@@ -206,7 +205,7 @@ constexpr int kMaxSplit = 8;
 template <typename T, int NQ>
 __global__ void __launch_bounds__(XW * 32)
 dec_cross_attention_kernel(const int* __restrict__ group_first_row, const int* __restrict__ group_n_rows,
-                           const int* __restrict__ group_xslot, const T* __restrict__ q, const T* __restrict__ cache,
+                           const int* __restrict__ group_xslot, const float* __restrict__ q, const T* __restrict__ cache,
                            long long slot_stride, int T_enc, int layer, int d, int n_split, T* __restrict__ out,
                            float* __restrict__ ws) {
   constexpr int VEC = Vec16<T>::N, LPR = 64 / VEC, RPW = 32 / LPR;
@@ -231,9 +230,8 @@ dec_cross_attention_kernel(const int* __restrict__ group_first_row, const int* _
 #pragma unroll
   for (int qi = 0; qi < NQ; ++qi) {
     if (qi < nq) {
-      Vec16<T>::load(q + (long long)(row0 + qi) * d + h * 64 + sub * VEC, qf[qi]);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) qf[qi][i] *= 0.125f;
+      for (int i = 0; i < VEC; ++i) qf[qi][i] = q[(long long)(row0 + qi) * d + h * 64 + sub * VEC + i] * 0.125f;
     } else {
 #pragma unroll
       for (int i = 0; i < VEC; ++i) qf[qi][i] = 0.f;
@@ -390,7 +388,7 @@ template void attn_encoder_simt<float>(const float*, float*, int, int, int, cuda
 template void attn_encoder_simt<bf16>(const bf16*, bf16*, int, int, int, cudaStream_t);
 
 template <typename T>
-void dec_self_attention(const DecRows& rows, const T* qkv, const SelfKV& kv, int layer, int d, int n_head, T* out,
+void dec_self_attention(const DecRows& rows, const float* qkv, const SelfKV& kv, int layer, int d, int n_head, T* out,
                         cudaStream_t stream) {
   if (rows.n_rows <= 0) return;
   BW_CHECK(kv.n_ctx <= 448, "n_text_ctx > 448 unsupported");
@@ -401,13 +399,13 @@ void dec_self_attention(const DecRows& rows, const T* qkv, const SelfKV& kv, int
   ++g_kernel_launches;
 }
 template void dec_self_attention<float>(const DecRows&, const float*, const SelfKV&, int, int, int, float*, cudaStream_t);
-template void dec_self_attention<bf16>(const DecRows&, const bf16*, const SelfKV&, int, int, int, bf16*, cudaStream_t);
+template void dec_self_attention<bf16>(const DecRows&, const float*, const SelfKV&, int, int, int, bf16*, cudaStream_t);
 
 size_t dec_cross_workspace_floats(int n_rows, int n_head) { return (size_t)n_rows * n_head * kMaxSplit * 66; }
 
 namespace {
 template <typename T, int NQ>
-void launch_cross(const int* gfr, const int* gnr, const int* gx, int n_groups, const T* q, const CrossKV& kv, int layer, int d,
+void launch_cross(const int* gfr, const int* gnr, const int* gx, int n_groups, const float* q, const CrossKV& kv, int layer, int d,
                   int n_head, int n_split, T* out, float* ws, cudaStream_t stream) {
   const int chunk = (kv.T_enc + n_split - 1) / n_split;
   const size_t smem = sizeof(float) * ((size_t)NQ * chunk + (size_t)XW * NQ * 64);
@@ -430,7 +428,7 @@ void launch_cross(const int* gfr, const int* gnr, const int* gx, int n_groups, c
 
 template <typename T>
 void dec_cross_attention(const int* group_first_row, const int* group_n_rows, const int* group_xslot, int n_groups,
-                         int max_group_rows, int n_rows, const T* q, const CrossKV& kv, int layer, int d, int n_head, T* out,
+                         int max_group_rows, int n_rows, const float* q, const CrossKV& kv, int layer, int d, int n_head, T* out,
                          float* workspace, cudaStream_t stream) {
   if (n_groups <= 0) return;
   BW_CHECK(max_group_rows <= 8, "at most 8 hypotheses per segment");
@@ -451,6 +449,6 @@ void dec_cross_attention(const int* group_first_row, const int* group_n_rows, co
   }
 }
 template void dec_cross_attention<float>(const int*, const int*, const int*, int, int, int, const float*, const CrossKV&, int, int, int, float*, float*, cudaStream_t);
-template void dec_cross_attention<bf16>(const int*, const int*, const int*, int, int, int, const bf16*, const CrossKV&, int, int, int, bf16*, float*, cudaStream_t);
+template void dec_cross_attention<bf16>(const int*, const int*, const int*, int, int, int, const float*, const CrossKV&, int, int, int, bf16*, float*, cudaStream_t);
 
 }  // namespace bw

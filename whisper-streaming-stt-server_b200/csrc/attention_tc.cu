@@ -7,7 +7,9 @@
 //     O_j = P_j V_j        tcgen05.mma M128 N64 K128, V consumed straight from the TMA tile as an
 //                          MN-major B operand (no transposed copy of V) -> TMEM (double buffered)
 //     softmax warps fold O_j into fp32 registers: o = o * alpha + O_j
-// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..5 = softmax / epilogue.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = softmax / epilogue: two warps per
+// TMEM lane quarter (= per SM sub-partition), each owning 64 of the 128 key columns of its 32 query rows and
+// 32 of the 64 output columns, so every scheduler has two warps to hide tcgen05.ld / MUFU latency.
 // Replaces F.scaled_dot_product_attention in upstream MultiHeadAttention.qkv_attention
 // (reached from reference torch_whisper.py:55); SURVEY.md section 2.2 row K5.
 #include <cuda.h>
@@ -26,9 +28,11 @@ constexpr int SM_K = 16384;                 // 2 stages x 16 KB
 constexpr int SM_V = SM_K + 2 * 16384;      // 2 stages x 16 KB
 constexpr int SM_P = SM_V + 2 * 16384;      // 2 buffers x 32 KB (two 64-column panels each)
 constexpr int SM_BAR = SM_P + 2 * 32768;
-constexpr int SM_TOTAL = SM_BAR + 256 + 1024;
+constexpr int SM_MX = SM_BAR + 256;             // row-max exchange: [2 parity][2 halves][128] floats
+constexpr int SM_TOTAL = SM_MX + 2 * 2 * 128 * 4 + 1024;
+constexpr int kThreads = 320;
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 attn_encoder_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ out, int T_len, int d) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -37,7 +41,7 @@ attn_encoder_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict_
   uint64_t* kv_full = bars + 1;     // 2
   uint64_t* kv_empty = bars + 3;    // 2
   uint64_t* s_full = bars + 5;      // 2
-  uint64_t* p_full = bars + 7;      // 2 (128 arrivals)
+  uint64_t* p_full = bars + 7;      // 2 (256 arrivals)
   uint64_t* o_full = bars + 9;      // 2
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
 
@@ -51,7 +55,7 @@ attn_encoder_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict_
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1);
+      mbar_init(&p_full[i], 256); mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
   }
@@ -116,57 +120,57 @@ attn_encoder_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict_
     }
     __syncwarp();
   } else {
-    const int wq = warp & 3;
+    const int wq = warp & 3;             // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;    // which 64 key columns / 32 output columns
     const int row = wq * 32 + lane;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const float sl2 = 0.125f * 1.4426950408889634f;
+    float* mxbuf = reinterpret_cast<float*>(smem + SM_MX);
     float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    float o[HD];
+    float o[32];
 #pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
     for (int j = 0; j < n_kt; ++j) {
       const int s = j & 1;
       mbar_wait(&s_full[s], (j >> 1) & 1);
       tc_fence_after();
-      const int kvalid = T_len - j * TK;  // columns >= kvalid are padding / the next window
+      uint32_t sv[64];
+      tmem_ld_32x32b_x32(tm_S + s * 128 + lane_off + half * 64, sv);
+      tmem_ld_32x32b_x32(tm_S + s * 128 + lane_off + half * 64 + 32, sv + 32);
+      tmem_ld_wait();
+      const int kvalid = T_len - j * TK - half * 64;  // my columns >= kvalid are padding / the next window
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tm_S + s * 128 + lane_off + c * 32, r);
-        tmem_ld_wait();
+      if (kvalid >= 64) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = (c * 32 + i < kvalid) ? __uint_as_float(r[i]) * sl2 : -INFINITY;
-          mx = fmaxf(mx, v);
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          if (i >= kvalid) sv[i] = 0xff800000u;  // -inf
+          mx = fmaxf(mx, __uint_as_float(sv[i]));
         }
       }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = exp2f(m - m_new);  // m = -inf on the first tile -> 0
+      mxbuf[(s * 2 + half) * 128 + row] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, mxbuf[(s * 2 + (half ^ 1)) * 128 + row]);
+      const float m_new = fmaxf(m, mx * sl2);
+      const float alpha = fast_exp2(m - m_new);  // m = -inf on the first tile -> 0
       float lsum = 0.f;
-      uint8_t* prow = smem + SM_P + s * 32768 + row * 128;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tm_S + s * 128 + lane_off + c * 32, r);
-        tmem_ld_wait();
-        float p[32];
+      uint8_t* prow = smem + SM_P + s * 32768 + half * 16384 + row * 128;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          p[i] = (c * 32 + i < kvalid) ? exp2f(__uint_as_float(r[i]) * sl2 - m_new) : 0.f;
+      for (int g = 0; g < 8; ++g) {
+        float p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          p[i] = fast_exp2(fmaf(__uint_as_float(sv[g * 8 + i]), sl2, -m_new));
           lsum += p[i];
         }
-        uint8_t* panel = prow + (c >> 1) * 16384;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = (c & 1) * 4 + g;  // 16-byte chunk inside the 128-byte row of this panel
-          uint4 t;
-          t.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);
-          t.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
-          t.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);
-          t.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(panel + ((chunk ^ (row & 7)) << 4)) = t;
-        }
+        uint4 t;
+        t.x = pack_bf16x2(p[0], p[1]);
+        t.y = pack_bf16x2(p[2], p[3]);
+        t.z = pack_bf16x2(p[4], p[5]);
+        t.w = pack_bf16x2(p[6], p[7]);
+        *reinterpret_cast<uint4*>(prow + ((g ^ (row & 7)) << 4)) = t;
       }
       l = l * alpha + lsum;
       m = m_new;
@@ -177,14 +181,11 @@ attn_encoder_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict_
         const int so = (j - 1) & 1;
         mbar_wait(&o_full[so], ((j - 1) >> 1) & 1);
         tc_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tm_O + so * 64 + lane_off + half * 32, r);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(tm_O + so * 64 + lane_off + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
-        }
+        for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(r[i]));
       }
       alpha_prev = alpha;
     }
@@ -192,20 +193,22 @@ attn_encoder_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict_
       const int so = (n_kt - 1) & 1;
       mbar_wait(&o_full[so], ((n_kt - 1) >> 1) & 1);
       tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tm_O + so * 64 + lane_off + half * 32, r);
+      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tm_O + so * 64 + lane_off + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
-      }
+      for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(r[i]));
     }
+    // total row sum = this half + the other half (both track the same running max)
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mxbuf[half * 128 + row] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += mxbuf[(half ^ 1) * 128 + row];
     if (q0 + row < T_len) {
       const float inv = 1.f / l;
-      bf16* orow = out + (long long)(row_base + q0 + row) * d + h * HD;
+      bf16* orow = out + (long long)(row_base + q0 + row) * d + h * HD + half * 32;
 #pragma unroll
-      for (int i = 0; i < HD; i += 8) {
+      for (int i = 0; i < 32; i += 8) {
         uint4 t;
         t.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv);
         t.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
@@ -236,7 +239,7 @@ void attn_encoder_tc(const bf16* qkv, bf16* out, int batch, int T_len, int n_hea
   }
   CUtensorMap tm = make_operand_map(qkv, batch * T_len, 3 * d, 3 * d, 1, 0, 128);
   dim3 grid((T_len + TQ - 1) / TQ, n_head, batch);
-  attn_encoder_tc_kernel<<<grid, 192, SM_TOTAL, stream>>>(tm, out, T_len, d);
+  attn_encoder_tc_kernel<<<grid, kThreads, SM_TOTAL, stream>>>(tm, out, T_len, d);
   BW_CUDA(cudaGetLastError());
   ++g_kernel_launches;
 }

@@ -6,43 +6,60 @@
 namespace bw {
 namespace {
 
+// One 128-thread block per row, float4 loads (d % 4 == 0, d <= 1536), two-pass mean / centred variance
+// in registers like torch's kernel.  Many small blocks keep enough loads in flight both for the encoder
+// (tens of thousands of rows) and for the decoder step (a few hundred rows).
 template <typename TOut, bool GATHER>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 layernorm_kernel(const float* __restrict__ x, const int* __restrict__ rows_idx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, TOut* __restrict__ out, int rows, int d) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const float* xr = x + (long long)(GATHER ? rows_idx[warp] : warp) * d;
-  // two-pass (mean, then centred variance) like torch's CPU kernel; d <= 1280 -> <= 40 values per lane
-  float v[40];
+  __shared__ float red[4];
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)(GATHER ? rows_idx[row] : row) * d);
+  const int nv = d >> 2;
+  float4 v[3];
   float s = 0.f;
-  const int per = (d + 31) / 32;
 #pragma unroll
-  for (int i = 0; i < 40; ++i) {
-    if (i < per) {
-      const int c = i * 32 + lane;
-      v[i] = (c < d) ? xr[c] : 0.f;
-      s += v[i];
-    }
+  for (int i = 0; i < 3; ++i) {
+    const int c = tid + i * 128;
+    v[i] = (c < nv) ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
-  const float mean = warp_sum(s) / d;
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  const float mean = (red[0] + red[1] + red[2] + red[3]) / d;
+  __syncthreads();
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 40; ++i) {
-    if (i < per) {
-      const int c = i * 32 + lane;
-      const float t = (c < d) ? v[i] - mean : 0.f;
-      q += t * t;
+  for (int i = 0; i < 3; ++i) {
+    const int c = tid + i * 128;
+    if (c < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + dd * dd);
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
-  TOut* orow = out + (long long)warp * d;
+  q = warp_sum(q);
+  if (lane == 0) red[warp] = q;
+  __syncthreads();
+  const float rstd = rsqrtf((red[0] + red[1] + red[2] + red[3]) / d + 1e-5f);
+  TOut* orow = out + (long long)row * d;
 #pragma unroll
-  for (int i = 0; i < 40; ++i) {
-    if (i < per) {
-      const int c = i * 32 + lane;
-      if (c < d) orow[c] = from_f<TOut>((v[i] - mean) * rstd * gamma[c] + beta[c]);
+  for (int i = 0; i < 3; ++i) {
+    const int c = tid + i * 128;
+    if (c < nv) {
+      const float4 g = reinterpret_cast<const float4*>(gamma)[c], b = reinterpret_cast<const float4*>(beta)[c];
+      const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
+      const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
+      if constexpr (sizeof(TOut) == 4) {
+        reinterpret_cast<float4*>(orow)[c] = make_float4(o0, o1, o2, o3);
+      } else {
+        uint2 t;
+        t.x = pack_bf16x2(o0, o1);
+        t.y = pack_bf16x2(o2, o3);
+        reinterpret_cast<uint2*>(orow)[c] = t;
+      }
     }
   }
 }
@@ -97,16 +114,16 @@ __global__ void dec_embed_kernel(const int* __restrict__ row_seq, const int* __r
 }
 
 template <typename T>
-__global__ void dec_kv_append_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const T* __restrict__ qkv,
+__global__ void dec_kv_append_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const float* __restrict__ qkv,
                                      T* __restrict__ pool, long long unit_stride, int n_ctx, int layer, int d) {
   const int r = blockIdx.x;
   const int s = row_seq[r], pos = row_pos[r];
   T* kdst = pool + (long long)s * unit_stride + ((long long)(layer * 2 + 0) * n_ctx + pos) * d;
   T* vdst = pool + (long long)s * unit_stride + ((long long)(layer * 2 + 1) * n_ctx + pos) * d;
-  const T* src = qkv + (long long)r * 3 * d;
+  const float* src = qkv + (long long)r * 3 * d;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    kdst[c] = src[d + c];
-    vdst[c] = src[2 * d + c];
+    kdst[c] = from_f<T>(src[d + c]);
+    vdst[c] = from_f<T>(src[2 * d + c]);
   }
 }
 
@@ -116,9 +133,9 @@ inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) /
 
 template <typename T>
 void layernorm(const float* x, const float* gamma, const float* beta, T* out, int rows, int d, cudaStream_t stream) {
-  BW_CHECK(d <= 1280, "layernorm supports d <= 1280");
+  BW_CHECK(d <= 1536 && d % 4 == 0, "layernorm supports d <= 1536, d % 4 == 0");
   if (rows <= 0) return;
-  layernorm_kernel<T, false><<<blocks_for((long long)rows * 32, 256), 256, 0, stream>>>(x, nullptr, gamma, beta, out, rows, d);
+  layernorm_kernel<T, false><<<rows, 128, 0, stream>>>(x, nullptr, gamma, beta, out, rows, d);
   BW_CUDA(cudaGetLastError());
   ++g_kernel_launches;
 }
@@ -132,9 +149,9 @@ void layernorm_f32out(const float* x, const float* gamma, const float* beta, flo
 template <typename T>
 void layernorm_gather(const float* x, const int* rows_idx, const float* gamma, const float* beta, T* out, int n, int d,
                       cudaStream_t stream) {
-  BW_CHECK(d <= 1280, "layernorm supports d <= 1280");
+  BW_CHECK(d <= 1536 && d % 4 == 0, "layernorm supports d <= 1536, d % 4 == 0");
   if (n <= 0) return;
-  layernorm_kernel<T, true><<<blocks_for((long long)n * 32, 256), 256, 0, stream>>>(x, rows_idx, gamma, beta, out, n, d);
+  layernorm_kernel<T, true><<<n, 128, 0, stream>>>(x, rows_idx, gamma, beta, out, n, d);
   BW_CUDA(cudaGetLastError());
   ++g_kernel_launches;
 }
@@ -188,7 +205,7 @@ template void dec_embed<float>(const DecRows&, const int*, const float*, const f
 template void dec_embed<bf16>(const DecRows&, const int*, const bf16*, const bf16*, float*, int, cudaStream_t);
 
 template <typename T>
-void dec_kv_append(const DecRows& rows, const T* qkv, const SelfKV& kv, int layer, int d, cudaStream_t stream) {
+void dec_kv_append(const DecRows& rows, const float* qkv, const SelfKV& kv, int layer, int d, cudaStream_t stream) {
   if (rows.n_rows <= 0) return;
   dec_kv_append_kernel<T><<<rows.n_rows, 128, 0, stream>>>(rows.row_seq, rows.row_pos, qkv, reinterpret_cast<T*>(kv.pool),
                                                            kv.unit_stride, kv.n_ctx, layer, d);
@@ -196,6 +213,6 @@ void dec_kv_append(const DecRows& rows, const T* qkv, const SelfKV& kv, int laye
   ++g_kernel_launches;
 }
 template void dec_kv_append<float>(const DecRows&, const float*, const SelfKV&, int, int, cudaStream_t);
-template void dec_kv_append<bf16>(const DecRows&, const bf16*, const SelfKV&, int, int, cudaStream_t);
+template void dec_kv_append<bf16>(const DecRows&, const float*, const SelfKV&, int, int, cudaStream_t);
 
 }  // namespace bw

@@ -75,15 +75,23 @@ struct Impl {
     }
   }
 
-  // out[R, N] = act(X[R, K] . W[N, K]^T + bias) (+ residual[R, N]); decoder-side skinny GEMM
+  // out[R, N] = act(X[R, K] . W[N, K]^T + bias) (+ residual[R, N]); decoder-side skinny GEMM.
+  // tcgen05 path: swap-AB (weight rows fill the 128-row MMA, live sequences are the N operand).  fp32 outputs
+  // use split-K CTAs that reduce with red.global.add.f32 -- straight into the residual stream when
+  // `residual == out`, else into `out` zeroed first -- so that ~300 CTAs stream the weight instead of N/128.
   void linear_rows(const T* X, int R, int x_rows_alloc, const void* W, int N, int K, const float* bias, const float* residual,
                    void* out, bool gelu, bool out_fp32) const {
     GemmArgs g;
     g.K = K; g.lda = K; g.ldb = K; g.ldc = N; g.ldres = N; g.bias = bias; g.residual = residual; g.C = out;
     g.gelu = gelu; g.out_fp32 = out_fp32;
     const bool swap = !std::is_same<T, float>::value && !e->force_simt;
-    if (swap) {  // weight rows fill the 128-row MMA, live sequences are the N operand
+    if (swap) {
       g.A = W; g.B = X; g.M = N; g.N = R; g.transposed = true; g.b_rows = x_rows_alloc;
+      if (out_fp32 && !gelu && N <= 8192 && (residual == nullptr || residual == out)) {
+        if (residual == nullptr) BW_CUDA(cudaMemsetAsync(out, 0, (size_t)R * N * 4, e->stream));
+        g.residual = nullptr;
+        g.accumulate = true;
+      }
     } else {
       g.A = X; g.B = W; g.M = R; g.N = N;
     }
@@ -184,13 +192,13 @@ struct Impl {
     for (int l = 0; l < L; ++l) {
       const LayerW& w = e->w.dec[l];
       layernorm<T>(x, w.ln1_g, w.ln1_b, e->d_xn.as<T>(), c.R, dm, st);
-      linear_rows(e->d_xn.as<T>(), c.R, Ra, w.wqkv, 3 * dm, dm, w.bqkv, nullptr, e->d_qkv.p, false, false);
-      dec_kv_append<T>(rows, e->d_qkv.as<T>(), skv, l, dm, st);
-      dec_self_attention<T>(rows, e->d_qkv.as<T>(), skv, l, dm, H, e->d_att.as<T>(), st);
+      linear_rows(e->d_xn.as<T>(), c.R, Ra, w.wqkv, 3 * dm, dm, w.bqkv, nullptr, e->d_qkv.p, false, true);
+      dec_kv_append<T>(rows, e->d_qkv.as<float>(), skv, l, dm, st);
+      dec_self_attention<T>(rows, e->d_qkv.as<float>(), skv, l, dm, H, e->d_att.as<T>(), st);
       linear_rows(e->d_att.as<T>(), c.R, Ra, w.wo, dm, dm, w.bo, x, x, false, true);
       layernorm<T>(x, w.lnx_g, w.lnx_b, e->d_xn.as<T>(), c.R, dm, st);
-      linear_rows(e->d_xn.as<T>(), c.R, Ra, w.wq_x, dm, dm, w.bq_x, nullptr, e->d_q.p, false, false);
-      dec_cross_attention<T>(c.grp_first, c.grp_n, c.grp_x, c.n_groups, c.max_group_rows, c.R, e->d_q.as<T>(), xkv, l, dm, H,
+      linear_rows(e->d_xn.as<T>(), c.R, Ra, w.wq_x, dm, dm, w.bq_x, nullptr, e->d_q.p, false, true);
+      dec_cross_attention<T>(c.grp_first, c.grp_n, c.grp_x, c.n_groups, c.max_group_rows, c.R, e->d_q.as<float>(), xkv, l, dm, H,
                              e->d_att.as<T>(), e->d_ws.as<float>(), st);
       linear_rows(e->d_att.as<T>(), c.R, Ra, w.wo_x, dm, dm, w.bo_x, x, x, false, true);
       layernorm<T>(x, w.ln2_g, w.ln2_b, e->d_xn.as<T>(), c.R, dm, st);

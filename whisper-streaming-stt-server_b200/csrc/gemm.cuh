@@ -27,6 +27,10 @@ struct GemmArgs {
   bool gelu = false;
   bool out_fp32 = false;    // else same storage type as the inputs
   bool transposed = false;
+  // C (fp32) += A.B^T (+ bias): split-K CTAs reduce with red.global.add.f32 straight into the fp32 residual
+  // stream (or a zeroed buffer); `residual` must be null.  tcgen05 path only.
+  bool accumulate = false;
+  int ksplit = 0;  // 0 = choose
 };
 
 // bf16 inputs, fp32 accumulate, tcgen05.mma + TMEM + TMA. Throws on CUDA errors.

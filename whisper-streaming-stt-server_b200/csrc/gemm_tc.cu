@@ -8,6 +8,9 @@
 // see SURVEY.md section 2.2 rows K2/K4.
 #include <cuda.h>
 
+#include <stdlib.h>
+
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <unordered_map>
@@ -32,6 +35,7 @@ struct GemmDev {
   long long c_zstride, bias_zstride, res_zstride;
   int a_z_bcast, b_z_bcast;
   int gelu, out_fp32, transposed;
+  int accumulate, ksplit;
 };
 
 template <int BN, int STAGES>
@@ -58,8 +62,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * BM;
-  const int z = blockIdx.z;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int z = blockIdx.z / p.ksplit;
+  const int ks = blockIdx.z - z * p.ksplit;
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int kb0 = (int)((long long)ks * total_kb / p.ksplit);           // balanced split: every CTA gets >= 1 block
+  const int num_kb = (int)((long long)(ks + 1) * total_kb / p.ksplit) - kb0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -91,8 +98,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* sa = smem + s * L::kStageBytes;
         uint8_t* sb = sa + L::kABytes;
         mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
-        tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, m0, za);
-        tma_load_3d(sb, &tmB, &full_bar[s], kb * BK, n0, zb);
+        tma_load_3d(sa, &tmA, &full_bar[s], (kb0 + kb) * BK, m0, za);
+        tma_load_3d(sb, &tmB, &full_bar[s], (kb0 + kb) * BK, n0, zb);
       }
     }
     __syncwarp();
@@ -125,7 +132,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int i = m0 + row;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const float* bias = p.bias ? p.bias + (long long)z * p.bias_zstride : nullptr;
+    const float* bias = (p.bias && ks == 0) ? p.bias + (long long)z * p.bias_zstride : nullptr;
     const float* res = p.residual ? p.residual + (long long)z * p.res_zstride : nullptr;
     const bool row_ok = i < p.M;
 #pragma unroll 1
@@ -142,7 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(r[j]);
           if (bias && (full || j0 + j < p.N)) x += __ldg(bias + j0 + j);
-          if (p.gelu) x = gelu_erf(x);
+          if (p.gelu) x = gelu_erf_fast(x);
           v[j] = x;
         }
         if (row_ok) {
@@ -160,7 +167,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (j0 + j < p.N) v[j] += rr[j];
             }
           }
-          if (p.out_fp32) {
+          if (p.accumulate) {
+            float* o = reinterpret_cast<float*>(p.C) + (long long)z * p.c_zstride + (long long)i * p.ldc + j0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j0 + j < p.N) atomicAdd(o + j, v[j]);
+          } else if (p.out_fp32) {
             float* o = reinterpret_cast<float*>(p.C) + (long long)z * p.c_zstride + (long long)i * p.ldc + j0;
             if (full && ((p.ldc & 3) == 0)) {
 #pragma unroll
@@ -195,10 +207,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(r[j]) + b;
-          if (p.gelu) x = gelu_erf(x);
+          if (p.gelu) x = gelu_erf_fast(x);
           if (row_ok && j0 + j < p.N) {
             if (res) x += res[(long long)(j0 + j) * p.ldres + i];
-            if (p.out_fp32)
+            if (p.accumulate)
+              atomicAdd((reinterpret_cast<float*>(p.C) + (long long)z * p.c_zstride) + (long long)(j0 + j) * p.ldc + i, x);
+            else if (p.out_fp32)
               (reinterpret_cast<float*>(p.C) + (long long)z * p.c_zstride)[(long long)(j0 + j) * p.ldc + i] = x;
             else
               (reinterpret_cast<bf16*>(p.C) + (long long)z * p.c_zstride)[(long long)(j0 + j) * p.ldc + i] = __float2bfloat16(x);
@@ -301,7 +315,17 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
   p.c_zstride = g.c_zstride; p.bias_zstride = g.bias_zstride; p.res_zstride = g.res_zstride;
   p.a_z_bcast = a_bcast; p.b_z_bcast = b_bcast;
   p.gelu = g.gelu; p.out_fp32 = g.out_fp32; p.transposed = g.transposed;
-  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.Z);
+  p.accumulate = g.accumulate;
+  const int total_kb = (g.K + BK - 1) / BK;
+  int ksplit = 1;
+  if (g.accumulate) {
+    BW_CHECK(!g.residual && !g.gelu, "accumulate GEMM takes no residual / activation");
+    const long long tiles = (long long)((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM) * g.Z;
+    ksplit = g.ksplit > 0 ? g.ksplit : (int)std::max<long long>(1, std::min<long long>(total_kb / 2, (2 * 148 + tiles - 1) / tiles));
+    ksplit = std::max(1, std::min(ksplit, total_kb));
+  }
+  p.ksplit = ksplit;
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.Z * ksplit);
   kern<<<grid, 192, L::kTotal, stream>>>(tmA, tmB, p);
   BW_CUDA(cudaGetLastError());
   ++g_kernel_launches;
@@ -315,8 +339,11 @@ void gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   const long long mt = (g.M + BM - 1) / BM;
   if (g.N <= 32) return launch<32, 5, 2>(g, stream);
   if (g.N <= 64) return launch<64, 4, 2>(g, stream);
-  const long long tiles256 = mt * ((g.N + 255) / 256) * g.Z;
-  if (g.N > 128 && tiles256 >= 2 * 148) return launch<256, 4, 1>(g, stream);
+  (void)mt;
+  // 128x128 with two CTAs per SM: one CTA's epilogue overlaps the other's main loop.  (The 128x256 / 1 CTA
+  // variant measured slower here -- profiles/r1a_summary.txt -- until the kernel is persistent.)
+  static const bool wide = getenv("B200W_GEMM_WIDE") != nullptr;
+  if (wide && g.N > 128 && mt * ((g.N + 255) / 256) * g.Z >= 2 * 148) return launch<256, 4, 1>(g, stream);
   return launch<128, 3, 2>(g, stream);
 }
 

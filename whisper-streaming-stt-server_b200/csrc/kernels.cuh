@@ -68,12 +68,12 @@ struct SelfKV {
   const int* seq_first = nullptr;      // [S] first sequence slot of the owning request
   const unsigned char* anc = nullptr;  // [S][n_ctx] beam slot holding position t (current ping-pong buffer)
 };
-// scatter this step's k/v (from qkv rows [R, 3d]) into the pool for `layer`
+// scatter this step's k/v (from the fp32 qkv rows [R, 3d]) into the pool for `layer`
 template <typename T>
-void dec_kv_append(const DecRows& rows, const T* qkv, const SelfKV& kv, int layer, int d, cudaStream_t stream);
-// out[r] = softmax(q_r . K[0..pos_r]) V   (head dim 64)
+void dec_kv_append(const DecRows& rows, const float* qkv, const SelfKV& kv, int layer, int d, cudaStream_t stream);
+// out[r] = softmax(q_r . K[0..pos_r]) V   (head dim 64); q = first d columns of the fp32 qkv rows
 template <typename T>
-void dec_self_attention(const DecRows& rows, const T* qkv, const SelfKV& kv, int layer, int d, int n_head, T* out,
+void dec_self_attention(const DecRows& rows, const float* qkv, const SelfKV& kv, int layer, int d, int n_head, T* out,
                         cudaStream_t stream);
 // Cross attention over the cached encoder K/V of each row's segment:
 // cross cache slot layout [L][T_enc][2*d] (k | v). Group g = rows [first_row, first_row + n_rows) that share
@@ -85,7 +85,7 @@ struct CrossKV {
 };
 template <typename T>
 void dec_cross_attention(const int* group_first_row, const int* group_n_rows, const int* group_xslot, int n_groups,
-                         int max_group_rows, int n_rows, const T* q, const CrossKV& kv, int layer, int d, int n_head, T* out,
+                         int max_group_rows, int n_rows, const float* q, const CrossKV& kv, int layer, int d, int n_head, T* out,
                          float* workspace, cudaStream_t stream);
 size_t dec_cross_workspace_floats(int n_rows, int n_head);
 
