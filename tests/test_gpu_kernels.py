@@ -105,3 +105,26 @@ def test_encoder_attention(impl, cfg):
     ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(batch * T, d)
     rel = ((out.float() - ref).norm() / ref.norm()).item()
     assert rel < 2e-2, f"impl {impl} cfg {cfg}: rel-L2 {rel}"
+
+
+@pytest.mark.parametrize("shape", [(128, 1280, 1280), (100, 5120, 1280), (128, 1280, 5120), (300, 1280, 512), (7, 384, 1536), (1, 3840, 1280)])
+def test_gemm_cluster_splitk(shape):
+    """few output tiles -> K is split over a thread-block cluster and reduced through DSMEM (decoder GEMMs)"""
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = (torch.randn((M, K), device="cuda", generator=g) * 0.3).bfloat16()
+    B = (torch.randn((N, K), device="cuda", generator=g) * 0.3).bfloat16()
+    bias = torch.randn((N,), device="cuda", generator=g)
+    res = torch.randn((M, N), device="cuda", generator=g)
+    for gelu, use_res, out_fp32 in ((False, False, True), (True, False, False), (False, True, True), (False, True, False)):
+        out = _gemm(0, A, B, bias, res if use_res else None, gelu, out_fp32).float()
+        ref = _ref(A, B, bias, res if use_res else None, gelu)
+        rel = ((out - ref).norm() / ref.norm()).item()
+        assert rel < (5e-3 if out_fp32 else 3e-2), f"{shape} gelu={gelu} res={use_res} fp32={out_fp32}: rel-L2 {rel}"
+    # in-place residual (C == residual), as the decoder uses it
+    x = res.clone()
+    L, lib = _lib()
+    L.check(lib.bw_gemm_bf16(0, A.data_ptr(), B.data_ptr(), x.data_ptr(), bias.data_ptr(), x.data_ptr(), M, N, K, 0, 1, None), "gemm")
+    torch.cuda.synchronize()
+    ref = _ref(A, B, bias, res, False)
+    assert ((x - ref).norm() / ref.norm()).item() < 5e-3

@@ -76,24 +76,20 @@ struct Impl {
   }
 
   // out[R, N] = act(X[R, K] . W[N, K]^T + bias) (+ residual[R, N]); decoder-side skinny GEMM.
-  // tcgen05 path: swap-AB (weight rows fill the 128-row MMA, live sequences are the N operand).  fp32 outputs
-  // use split-K CTAs that reduce with red.global.add.f32 -- straight into the residual stream when
-  // `residual == out`, else into `out` zeroed first -- so that ~300 CTAs stream the weight instead of N/128.
+  // tcgen05 path: the live sequences are the (zero-padded) 128-row M operand and the weight streams through
+  // as the N operand; gemm_tc_bf16 splits K over a thread-block cluster so that hundreds of CTAs, not N/128,
+  // pull the weight from HBM (DSMEM reduction, no atomics).  The vocabulary projection (406 N tiles) runs
+  // swap-AB instead: weight rows fill the MMA's M, the few logit rows are a narrow N tile.
   void linear_rows(const T* X, int R, int x_rows_alloc, const void* W, int N, int K, const float* bias, const float* residual,
                    void* out, bool gelu, bool out_fp32) const {
     GemmArgs g;
     g.K = K; g.lda = K; g.ldb = K; g.ldc = N; g.ldres = N; g.bias = bias; g.residual = residual; g.C = out;
     g.gelu = gelu; g.out_fp32 = out_fp32;
-    const bool swap = !std::is_same<T, float>::value && !e->force_simt;
-    if (swap) {
+    const bool tc = !std::is_same<T, float>::value && !e->force_simt;
+    if (tc && N > 8192) {
       g.A = W; g.B = X; g.M = N; g.N = R; g.transposed = true; g.b_rows = x_rows_alloc;
-      if (out_fp32 && !gelu && N <= 8192 && (residual == nullptr || residual == out)) {
-        if (residual == nullptr) BW_CUDA(cudaMemsetAsync(out, 0, (size_t)R * N * 4, e->stream));
-        g.residual = nullptr;
-        g.accumulate = true;
-      }
     } else {
-      g.A = X; g.B = W; g.M = R; g.N = N;
+      g.A = X; g.B = W; g.M = R; g.N = N; g.a_rows = x_rows_alloc;
     }
     gemm(g);
   }

@@ -229,6 +229,196 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Split-K over a thread-block cluster (KS CTAs along K per 128x128 output tile), for GEMMs whose M x N
+// tile count cannot fill the 148 SMs -- the decoder step's skinny GEMMs (M = live sequences) above all.
+// Each CTA accumulates its K range in TMEM, parks the fp32 tile in its own shared memory (re-using the
+// pipeline stages), the cluster synchronises, and CTA rank r reduces tile rows [r*128/KS, (r+1)*128/KS)
+// across all peers through distributed shared memory and runs the normal bias / GELU / residual epilogue.
+// No atomics, deterministic summation order, every weight byte still streamed from HBM exactly once.
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+  return v;
+}
+
+template <int KS>
+__global__ void __launch_bounds__(192, 2)
+gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+  constexpr int BN = 128, STAGES = 3;
+  using L = SmemLayout<BN, STAGES>;
+  static_assert(STAGES * L::kStageBytes >= BM * BN * 4, "reduction tile must fit in the pipeline stages");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int z = blockIdx.z / KS;
+  const int ks = (int)cluster_ctarank();  // == blockIdx.z % KS for cluster dims (1, 1, KS)
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int kb0 = (int)((long long)ks * total_kb / KS);
+  const int num_kb = (int)((long long)(ks + 1) * total_kb / KS) - kb0;  // >= 1: host guarantees KS <= total_kb
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int za = p.a_z_bcast ? 0 : z;
+      const int zb = p.b_z_bcast ? 0 : z;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], phase ^ 1);
+        uint8_t* sa = smem + s * L::kStageBytes;
+        uint8_t* sb = sa + L::kABytes;
+        mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
+        tma_load_3d(sa, &tmA, &full_bar[s], (kb0 + kb) * BK, m0, za);
+        tma_load_3d(sb, &tmB, &full_bar[s], (kb0 + kb) * BK, n0, zb);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
+        const uint32_t sb = sa + L::kABytes;
+        const uint64_t adesc = umma_smem_desc_sw128(sa, 16, 1024);
+        const uint64_t bdesc = umma_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    // park the partial tile: red[row][f4 ^ (row & 31)] (float4 granules; conflict-free for a warp of rows)
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);  // all MMAs retired -> the stage buffers are free to be overwritten
+    tc_fence_after();
+    float4* red = reinterpret_cast<float4*>(smem);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int f4 = c * 8 + g;
+        red[row * 32 + (f4 ^ (row & 31))] = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
+                                                        __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+      }
+    }
+    tc_fence_before();
+  }
+  cluster_sync_all();  // every thread of every CTA in the cluster
+  if (warp >= 2) {
+    constexpr int RPC = BM / KS;  // tile rows reduced by this CTA
+    const int t = threadIdx.x - 64;
+    const float* bias = p.bias ? p.bias + (long long)z * p.bias_zstride : nullptr;
+    const float* res = p.residual ? p.residual + (long long)z * p.res_zstride : nullptr;
+    const uint32_t red_base = smem_u32(smem);
+    for (int e = t; e < RPC * 32; e += 128) {
+      const int row = ks * RPC + (e >> 5);
+      const int f4 = e & 31;
+      const uint32_t off = red_base + (uint32_t)((row * 32 + (f4 ^ (row & 31))) * 16);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int pr = 0; pr < KS; ++pr) {
+        const float4 v = ld_dsmem_f4(off, (uint32_t)pr);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      const int i = m0 + row;
+      const int j0 = n0 + f4 * 4;
+      if (i >= p.M || j0 >= p.N) continue;
+      float v[4] = {acc.x, acc.y, acc.z, acc.w};
+      const bool full = (j0 + 4 <= p.N);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!full && j0 + q >= p.N) continue;
+        float x = v[q];
+        if (bias) x += __ldg(bias + (p.transposed ? i : j0 + q));
+        if (p.gelu) x = gelu_erf_fast(x);
+        if (res) x += p.transposed ? res[(long long)(j0 + q) * p.ldres + i] : res[(long long)i * p.ldres + j0 + q];
+        v[q] = x;
+      }
+      if (p.transposed) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (j0 + q >= p.N) continue;
+          const long long oi = (long long)z * p.c_zstride + (long long)(j0 + q) * p.ldc + i;
+          if (p.out_fp32) reinterpret_cast<float*>(p.C)[oi] = v[q];
+          else reinterpret_cast<bf16*>(p.C)[oi] = __float2bfloat16(v[q]);
+        }
+      } else {
+        const long long oi = (long long)z * p.c_zstride + (long long)i * p.ldc + j0;
+        if (p.out_fp32) {
+          float* o = reinterpret_cast<float*>(p.C) + oi;
+          if (full && ((p.ldc & 3) == 0)) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          else
+            for (int q = 0; q < 4; ++q) if (j0 + q < p.N) o[q] = v[q];
+        } else {
+          bf16* o = reinterpret_cast<bf16*>(p.C) + oi;
+          if (full && ((p.ldc & 3) == 0)) {
+            uint2 w;
+            w.x = pack_bf16x2(v[0], v[1]);
+            w.y = pack_bf16x2(v[2], v[3]);
+            *reinterpret_cast<uint2*>(o) = w;
+          } else
+            for (int q = 0; q < 4; ++q) if (j0 + q < p.N) o[q] = __float2bfloat16(v[q]);
+        }
+      }
+    }
+  }
+  cluster_sync_all();  // peers may still be reading this CTA's shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
 // ---- host side: tensor maps (driver entry point fetched through the runtime; no -lcuda) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -330,6 +520,42 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
   BW_CUDA(cudaGetLastError());
   ++g_kernel_launches;
 }
+
+template <int KS>
+void launch_splitk(const GemmArgs& g, cudaStream_t stream) {
+  constexpr int BN = 128, STAGES = 3;
+  using L = SmemLayout<BN, STAGES>;
+  static std::atomic<unsigned long long> attr_set{0};
+  auto kern = gemm_tc_splitk_kernel<KS>;
+  int dev = 0;
+  BW_CUDA(cudaGetDevice(&dev));
+  if (!(attr_set.load() >> dev & 1ull)) {
+    BW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set.fetch_or(1ull << dev);
+  }
+  const bool a_bcast = (g.Z > 1 && g.a_zstride == 0), b_bcast = (g.Z > 1 && g.b_zstride == 0);
+  CUtensorMap tmA = make_operand_map(g.A, g.a_rows > g.M ? g.a_rows : g.M, g.K, g.lda, a_bcast ? 1 : g.Z, g.a_zstride, BM);
+  CUtensorMap tmB = make_operand_map(g.B, g.b_rows > g.N ? g.b_rows : g.N, g.K, g.ldb, b_bcast ? 1 : g.Z, g.b_zstride, BN);
+  GemmDev p;
+  p.C = g.C; p.bias = g.bias; p.residual = g.residual;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = g.ldc; p.ldres = g.ldres;
+  p.c_zstride = g.c_zstride; p.bias_zstride = g.bias_zstride; p.res_zstride = g.res_zstride;
+  p.a_z_bcast = a_bcast; p.b_z_bcast = b_bcast;
+  p.gelu = g.gelu; p.out_fp32 = g.out_fp32; p.transposed = g.transposed;
+  p.accumulate = 0; p.ksplit = KS;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.Z * KS);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = KS;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BW_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  ++g_kernel_launches;
+}
 }  // namespace
 
 void gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
@@ -337,6 +563,19 @@ void gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   // Tile choice: 128x256 (fewer smem bytes per MMA) when it still fills the 148 SMs, else
   // 128x128 with two CTAs per SM; tiny N (swap-AB decode) uses the narrowest tile that covers it.
   const long long mt = (g.M + BM - 1) / BM;
+  if (!g.accumulate && g.N > 64 && g.ksplit >= 0) {
+    // too few 128x128 tiles for 148 SMs -> split K over a cluster (DSMEM reduction, full epilogue)
+    const long long tiles = mt * ((g.N + 127) / 128) * g.Z;
+    const int total_kb = (g.K + BK - 1) / BK;
+    static const bool no_splitk = getenv("B200W_NO_SPLITK") != nullptr;
+    if (tiles < 120 && total_kb >= 4 && !no_splitk) {
+      int ks = 8;
+      while (ks > 2 && (tiles * ks > 640 || total_kb < 2 * ks)) ks >>= 1;
+      if (ks == 8) return launch_splitk<8>(g, stream);
+      if (ks == 4) return launch_splitk<4>(g, stream);
+      return launch_splitk<2>(g, stream);
+    }
+  }
   if (g.N <= 32) return launch<32, 5, 2>(g, stream);
   if (g.N <= 64) return launch<64, 4, 2>(g, stream);
   (void)mt;
