@@ -1,0 +1,87 @@
+"""Independent second opinion on the oracle: HF transformers' port of the same published model
+(feature extractor + WhisperModel with the oracle's weights remapped).  Not the reference, but different code."""
+import numpy as np
+import pytest
+import torch
+
+from b200_whisper.synth import MODEL_DIMS, random_state_dict, synth_audio
+from oracle import whisper_oracle as wo
+from oracle.tables import layout_for_vocab
+
+transformers = pytest.importorskip("transformers")
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_mel_matches_hf_feature_extractor(n_mels):
+    from transformers import WhisperFeatureExtractor
+    from transformers.audio_utils import mel_filter_bank
+
+    ours = wo.mel_filters(n_mels)
+    hf = mel_filter_bank(201, n_mels, 0.0, 8000.0, 16000, norm="slaney", mel_scale="slaney").T.astype(np.float32)
+    assert np.abs(ours - hf).max() < 1e-7
+    audio = synth_audio(4, 7.3)
+    fe = WhisperFeatureExtractor(feature_size=n_mels)
+    ref = np.asarray(fe._torch_extract_fbank_features(np.concatenate([audio, np.zeros(480000, np.float32)])[None]))[0]
+    got = wo.log_mel_spectrogram(audio, n_mels, padding=480000).numpy()
+    assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-5
+
+
+def _to_hf(state, dims):
+    from transformers import WhisperConfig, WhisperModel
+
+    cfg = WhisperConfig(vocab_size=dims.n_vocab, num_mel_bins=dims.n_mels, d_model=dims.n_audio_state,
+                        encoder_layers=dims.n_audio_layer, decoder_layers=dims.n_text_layer,
+                        encoder_attention_heads=dims.n_audio_head, decoder_attention_heads=dims.n_text_head,
+                        encoder_ffn_dim=4 * dims.n_audio_state, decoder_ffn_dim=4 * dims.n_text_state,
+                        max_source_positions=1500, max_target_positions=448, activation_function="gelu")
+    cfg._attn_implementation = "eager"
+    m = WhisperModel(cfg).eval()
+    sd = {}
+    rn = {"attn.query": "self_attn.q_proj", "attn.key": "self_attn.k_proj", "attn.value": "self_attn.v_proj",
+          "attn.out": "self_attn.out_proj", "attn_ln": "self_attn_layer_norm", "cross_attn.query": "encoder_attn.q_proj",
+          "cross_attn.key": "encoder_attn.k_proj", "cross_attn.value": "encoder_attn.v_proj", "cross_attn.out": "encoder_attn.out_proj",
+          "cross_attn_ln": "encoder_attn_layer_norm", "mlp.0": "fc1", "mlp.2": "fc2", "mlp_ln": "final_layer_norm"}
+    for k, v in state.items():
+        side, rest = k.split(".", 1)
+        if rest.startswith("blocks."):
+            _, i, tail = rest.split(".", 2)
+            for a, b in sorted(rn.items(), key=lambda kv: -len(kv[0])):
+                if tail.startswith(a + "."):
+                    tail = b + tail[len(a):]
+                    break
+            sd[f"{side}.layers.{i}.{tail}"] = v
+        elif rest.startswith("conv"):
+            sd[f"{side}.{rest}"] = v
+        elif rest == "ln_post.weight" or rest == "ln_post.bias" or rest.startswith("ln."):
+            sd[f"{side}.layer_norm.{rest.split('.')[-1]}"] = v
+        elif rest == "token_embedding.weight":
+            sd["decoder.embed_tokens.weight"] = v
+        elif rest == "positional_embedding":
+            sd[f"{side}.embed_positions.weight"] = v
+    sd["encoder.embed_positions.weight"] = wo.sinusoids(1500, dims.n_audio_state)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("k_proj.bias" in k for k in missing), (missing, unexpected)
+    for k, p in m.named_parameters():  # HF key projections carry a bias openai's do not
+        if "k_proj.bias" in k:
+            torch.nn.init.zeros_(p)
+    return m
+
+
+def test_encoder_decoder_match_hf_whisper():
+    dims = MODEL_DIMS["test-tiny"]
+    state = random_state_dict(dims, 0, emb_std=0.1)
+    model = wo.Whisper(wo.ModelDimensions(**dims.__dict__), state)
+    hf = _to_hf(state, dims)
+    audio = synth_audio(6, 5.0)
+    mel = wo.pad_or_trim(wo.log_mel_spectrogram(audio, 80, padding=480000), 3000)[None]
+    lay = layout_for_vocab(dims.n_vocab)
+    tokens = torch.tensor([[lay.sot, lay.language_token("en"), lay.transcribe, lay.timestamp_begin, 100, 2000, 31000]])
+    with torch.no_grad():
+        xa = model.encode(mel)
+        logits = model.decode(tokens, xa)
+        enc_hf = hf.encoder(mel).last_hidden_state
+        dec_hf = hf.decoder(input_ids=tokens, encoder_hidden_states=enc_hf).last_hidden_state
+        logits_hf = dec_hf @ hf.decoder.embed_tokens.weight.t()
+    assert (xa - enc_hf).abs().max() < 2e-4
+    assert (logits - logits_hf).abs().max() < 2e-3
+    assert logits.argmax(-1).tolist() == logits_hf.argmax(-1).tolist()
