@@ -75,6 +75,24 @@ def test_decoder_logits_fp32():
     assert err <= 2e-3, f"decoder logits max-abs error {err} (scale {np.abs(ref).max()})"
 
 
+@pytest.mark.parametrize("name", ["test-tiny", "test-v3"])
+def test_decoder_logits_bf16(name):
+    """bf16 product path (tcgen05 GEMMs, mma.sync cross-attention, split-K clusters) against the fp32 oracle"""
+    b = backend(name, "bfloat16")
+    model = oracle_model(name)
+    audio = synth_audio(3, 5.0)
+    mel = wo.pad_or_trim(wo.log_mel_spectrogram(audio, model.dims.n_mels, padding=480000), 3000)
+    lay = model.layout
+    tokens = [lay.sot, lay.language_token("en"), lay.transcribe, lay.timestamp_begin, 1000, 2000, 3000, 400, 50, 7, 11]
+    got = b.engine.decode_logits(mel.numpy(), tokens)
+    xa = model.encode(mel[None])
+    ref = model.decode(torch.tensor([tokens]), xa)[0].numpy()
+    r = rel_l2(got, ref)
+    assert r <= 3e-2, f"{name}: bf16 decoder logits rel-L2 {r}"
+    agree = float((got.argmax(-1) == ref.argmax(-1)).mean())
+    print(f"{name}: bf16 logits rel-L2 {r:.4f}, argmax agreement {agree:.2f}")
+
+
 def _oracle_segments(name, audio, opts, **kw):
     segs, info, raw = wo.backend_transcribe(oracle_model(name, **kw), audio, opts)
     return segs, info, raw

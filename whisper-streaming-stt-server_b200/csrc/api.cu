@@ -1105,10 +1105,12 @@ int bw_bench_cross_attention(bw_engine* e, int32_t n_segments, int32_t n_group, 
   auto run = [&](int layer) {
     if (e->fp32) {
       CrossKV x; x.cache = e->cross_cache.p; x.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; x.T_enc = d.n_audio_ctx;
+      x.n_slots = e->Q; x.n_layer = L;
       dec_cross_attention<float>(dev(ctl.grp_first), dev(ctl.grp_n), dev(ctl.grp_x), n_segments, n_group, R, e->d_q.as<float>(), x, layer, dm,
                                  d.n_text_head, e->d_att.as<float>(), e->d_ws.as<float>(), e->stream);
     } else {
       CrossKV x; x.cache = e->cross_cache.p; x.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; x.T_enc = d.n_audio_ctx;
+      x.n_slots = e->Q; x.n_layer = L;
       dec_cross_attention<bf16>(dev(ctl.grp_first), dev(ctl.grp_n), dev(ctl.grp_x), n_segments, n_group, R, e->d_q.as<float>(), x, layer, dm,
                                 d.n_text_head, e->d_att.as<bf16>(), e->d_ws.as<float>(), e->stream);
     }

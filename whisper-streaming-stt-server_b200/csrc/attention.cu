@@ -6,9 +6,18 @@
 //  * dec_cross_attention: the decoder step's HBM-bound kernel -- streams the cached encoder K/V of a
 //    segment ONCE for all beams of that segment (NQ queries share each 16-byte load), split along T.
 // Upstream: whisper/model.py MultiHeadAttention.qkv_attention (SDPA, scale 1/sqrt(64)).
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace bw {
+
+void dec_cross_attention_mma(const int* group_first_row, const int* group_n_rows, const int* group_xslot, int n_groups,
+                             const float* q, const CrossKV& kv, int n_layer, int layer, int d, int n_head, int n_split,
+                             bf16* out, float* ws, cudaStream_t stream);
+
 namespace {
 
 // fp32 validation mode uses the accurate expf; bf16 mode the fast intrinsic
@@ -437,6 +446,20 @@ void dec_cross_attention(const int* group_first_row, const int* group_n_rows, co
   int n_split = 1;
   const long long base = (long long)n_head * n_groups;
   while (n_split < kMaxSplit && base * n_split < 4 * 148) n_split *= 2;
+  if constexpr (std::is_same<T, bf16>::value) {
+    static const bool simt = getenv("B200W_XATTN_SIMT") != nullptr;
+    if (!simt && kv.n_slots > 0) {
+      dec_cross_attention_mma(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, kv.n_layer, layer, d, n_head, n_split,
+                              out, workspace, stream);
+      if (n_split > 1) {
+        dim3 grid(n_head, n_rows);
+        dec_cross_combine_kernel<T><<<grid, 64, 0, stream>>>(workspace, n_split, d, out);
+        BW_CUDA(cudaGetLastError());
+        ++g_kernel_launches;
+      }
+      return;
+    }
+  }
   if (max_group_rows <= 1) launch_cross<T, 1>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
   else if (max_group_rows <= 2) launch_cross<T, 2>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
   else if (max_group_rows <= 4) launch_cross<T, 4>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);

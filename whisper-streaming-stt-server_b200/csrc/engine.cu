@@ -184,6 +184,7 @@ struct Impl {
     skv.seq_first = e->ss.seq_first; skv.anc = e->ss.anc[e->anc_cur];
     CrossKV xkv;
     xkv.cache = e->cross_cache.p; xkv.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; xkv.T_enc = d.n_audio_ctx;
+    xkv.n_slots = e->Q; xkv.n_layer = L;
     const int Ra = e->R_max;
     for (int l = 0; l < L; ++l) {
       const LayerW& w = e->w.dec[l];

@@ -484,6 +484,23 @@ CUtensorMap make_operand_map(const void* ptr, int rows, int K, int ld, int Z, lo
   return m;
 }
 
+// Generic bf16 3D tiled map {inner, rows, outer} with a {box_inner, box_rows, 1} SWIZZLE_128B box (box_inner * 2 B = 128 B).
+CUtensorMap make_box_map(const void* ptr, int inner, int rows, int outer, long long row_stride, long long outer_stride,
+                         int box_inner, int box_rows) {
+  BW_CHECK(box_inner == 64, "SWIZZLE_128B box must be 64 bf16 wide");
+  BW_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (row_stride % 8) == 0 && (outer_stride % 8) == 0, "TMA alignment");
+  CUtensorMap m;
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)outer};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)outer_stride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return m;
+}
+
 namespace {
 template <int BN, int STAGES, int MINB>
 void launch(const GemmArgs& g, cudaStream_t stream) {

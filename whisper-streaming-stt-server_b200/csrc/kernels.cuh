@@ -82,6 +82,8 @@ struct CrossKV {
   const void* cache = nullptr;   // T*
   long long slot_stride = 0;     // elements per slot = L*T_enc*2*d
   int T_enc = 1500;
+  int n_slots = 0;               // slots behind `cache` (TMA map extent)
+  int n_layer = 0;
 };
 template <typename T>
 void dec_cross_attention(const int* group_first_row, const int* group_n_rows, const int* group_xslot, int n_groups,
