@@ -1,0 +1,233 @@
+"""Host-side logic of the backend without a GPU: option normalisation and result mapping (the template is the
+reference's tests/test_mlx_whisper_backend.py), token tables, device parsing, registration, and the seek loop /
+segment assembly driven by a fake engine and compared with the oracle's restatement of upstream transcribe()."""
+import sys
+import types
+
+import numpy as np
+import pytest
+
+import b200_whisper.backend as bk
+from b200_whisper.backend import B200WhisperBackend
+from b200_whisper.melfilters import mel_filterbank
+from b200_whisper.synth import MODEL_DIMS, synth_audio
+from b200_whisper.vocab import Detokenizer, normalize_language, vocab_for
+from oracle import whisper_oracle as wo
+from oracle.tables import layout_for_vocab
+
+
+class FakeCall:
+    def __init__(self, engine, audio):
+        self.engine = engine
+        self.content_frames = (len(audio) + 480000) // 160 - 3000
+        self.decodes = []
+
+    def decode(self, seek, initial, sot_index, beam, patience, length_penalty, **kw):
+        self.decodes.append({"seek": seek, "initial": list(initial), "sot_index": sot_index, "beam": beam, **kw})
+        self.engine.all_decodes.append(self.decodes[-1])
+        return dict(self.engine.script[min(len(self.engine.all_decodes) - 1, len(self.engine.script) - 1)])
+
+    def detect_language(self, seek=0):
+        v = self.engine.vocab
+        probs = np.full(v.num_languages, 0.001, np.float32)
+        probs[5] = 0.9
+        return v.first_language_token + 5, probs
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        pass
+
+
+class FakeEngine:
+    def __init__(self, n_vocab=51865, script=None):
+        self.dims = MODEL_DIMS["test-tiny"] if n_vocab == 51865 else MODEL_DIMS["test-tiny.en"]
+        self.vocab = vocab_for(n_vocab)
+        self.script = script or []
+        self.all_decodes = []
+
+    def open_call(self, audio):
+        return FakeCall(self, audio)
+
+
+@pytest.fixture
+def fake_backend(monkeypatch):
+    def make(script, n_vocab=51865):
+        eng = FakeEngine(n_vocab, script)
+        monkeypatch.setattr(bk, "get_engine", lambda *a, **k: eng)
+        return B200WhisperBackend("random:test-tiny", "cuda:0", "bfloat16"), eng
+
+    return make
+
+
+def res(tokens, avg=-0.5, nsp=0.01):
+    return {"tokens": tokens, "sum_logprob": avg * (len(tokens) + 1), "avg_logprob": avg, "no_speech_prob": nsp, "n_steps": len(tokens)}
+
+
+def test_tables_match_oracle_layout():
+    for n in (51864, 51865, 51866):
+        v, o = vocab_for(n), layout_for_vocab(n)
+        assert v.suppress_tokens() == list(o.suppress_tokens())
+        for f in ("eot", "sot", "translate", "transcribe", "sot_lm", "sot_prev", "no_speech", "no_timestamps", "timestamp_begin",
+                  "num_languages", "multilingual"):
+            assert getattr(v, f) == getattr(o, f), (n, f)
+        assert v.sot_sequence("ko", "translate") == list(o.sot_sequence("ko", "translate"))
+    assert vocab_for(51866).language_token("yue") == 50358
+    with pytest.raises(ValueError):
+        vocab_for(51865).language_token("yue")
+    assert normalize_language("Korean") == "ko" and normalize_language("EN") == "en"
+    with pytest.raises(ValueError):
+        normalize_language("klingon")
+
+
+def test_mel_filterbank_matches_oracle():
+    for n in (80, 128):
+        assert np.abs(mel_filterbank(n) - wo.mel_filters(n)).max() < 1e-7
+
+
+def test_option_normalisation_mirrors_torch_whisper(fake_backend):
+    b, eng = fake_backend([res([])])
+    opts = {"log_prob_threshold": -0.7, "without_timestamps": True, "vad_filter": True, "hotwords": "x", "beam_size": 5,
+            "best_of": 5, "patience": 1.0, "temperature": 0.0}
+    frozen = dict(opts)
+    n = b._normalize_options(opts)
+    assert opts == frozen
+    assert n == {"logprob_threshold": -0.7, "word_timestamps": False, "beam_size": 5, "best_of": 5, "patience": 1.0, "temperature": 0.0}
+    assert n == {k: v for k, v in wo.normalize_options(opts).items()}
+
+
+def test_result_mapping_and_language(fake_backend):
+    v = vocab_for(51865)
+    tb = v.timestamp_begin
+    b, eng = fake_backend([res([tb, 100, 200, tb + 50, tb + 50, 300, tb + 120])])
+    segs, info = b.transcribe(synth_audio(1, 3.0), {"language": "en", "beam_size": 1})
+    assert [(s.start, s.end) for s in segs] == [(0.0, 1.0), (1.0, 2.4)]
+    assert segs[0].text == "<100><200>" and info.language == "en" and info.language_probability == -1.0
+    # language unset -> detection; torch_whisper parity keeps the reported probability at -1.0
+    segs, info = b.transcribe(synth_audio(1, 3.0), {"beam_size": 1})
+    assert info.language == "ko" and info.language_probability == -1.0 and abs(b.last_language_probability - 0.9) < 1e-6
+    assert eng.all_decodes[-1]["initial"][:3] == [v.sot, v.language_token("ko"), v.transcribe]
+    # .en vocabulary: language forced to en, sot sequence is a single token
+    b2, eng2 = fake_backend([res([])], n_vocab=51864)
+    segs, info = b2.transcribe(synth_audio(1, 1.0), {})
+    assert info.language == "en" and eng2.all_decodes[-1]["initial"] == [vocab_for(51864).sot]
+    assert eng2.all_decodes[-1]["beam"] is None  # no beam_size -> greedy
+    # empty audio short-circuit and beam range
+    assert b.transcribe(np.zeros(0, np.float32), {"language": "en"})[0] == []
+    with pytest.raises(ValueError):
+        b.transcribe(synth_audio(1, 1.0), {"language": "en", "beam_size": 9})
+
+
+def _oracle_with_script(script, audio, n_vocab=51865, **opts):
+    """Run the oracle's restatement of upstream transcribe() with decode_window replaced by the same script."""
+    dims = MODEL_DIMS["test-tiny"]
+    model = types.SimpleNamespace(dims=wo.ModelDimensions(**dims.__dict__), layout=layout_for_vocab(n_vocab), is_multilingual=True)
+    calls = []
+
+    def fake_decode_window(m, mel_segment, o, audio_features=None):
+        r = script[min(len(calls), len(script) - 1)]
+        calls.append(list(o.prompt or []))
+        return wo.DecodingResult(language="en", tokens=list(r["tokens"]), text=wo.render_text(r["tokens"], model.layout.eot).strip(),
+                                 avg_logprob=r["avg_logprob"], no_speech_prob=r["no_speech_prob"], temperature=0.0,
+                                 compression_ratio=1.0, sum_logprob=r["sum_logprob"])
+
+    orig = wo.decode_window
+    wo.decode_window = fake_decode_window
+    try:
+        out = wo.transcribe(model, audio, **opts)
+    finally:
+        wo.decode_window = orig
+    return out, calls
+
+
+@pytest.mark.parametrize("case", ["pairs_then_open", "single_ts_ending", "no_timestamps", "no_speech_skip", "empty"])
+def test_seek_loop_matches_oracle(fake_backend, case):
+    v = vocab_for(51865)
+    tb = v.timestamp_begin
+    audio = synth_audio(2, 70.0)  # three 30 s windows worth of content
+    scripts = {
+        "pairs_then_open": [res([tb, 11, 12, tb + 400, tb + 400, 13, tb + 900, tb + 900, 14]), res([tb + 10, 21, tb + 700, tb + 700]),
+                            res([tb, 31, 32, tb + 1500])],
+        "single_ts_ending": [res([tb, 11, tb + 200, tb + 200, 12, tb + 1400]), res([tb, 21, tb + 1500])],
+        "no_timestamps": [res([11, 12, 13]), res([21, tb + 600]), res([31])],
+        "no_speech_skip": [res([tb, 11, tb + 100], avg=-1.5, nsp=0.9), res([tb, 21, tb + 800]), res([tb, 31, tb + 300])],
+        "empty": [res([])],
+    }
+    script = scripts[case]
+    b, eng = fake_backend(script)
+    for cond in (True, False):
+        eng.all_decodes.clear()
+        opts = {"language": "en", "beam_size": 1, "condition_on_previous_text": cond}
+        got = b.transcribe_raw(audio, **b._normalize_options(opts))
+        want, prompts = _oracle_with_script(script, audio, language="en", beam_size=1, condition_on_previous_text=cond)
+        assert [(s["seek"], s["start"], s["end"], s["tokens"]) for s in got["segments"]] == \
+               [(s["seek"], s["start"], s["end"], s["tokens"]) for s in want["segments"]]
+        assert got["text"] == want["text"]
+        # prompt carry-over: [sot_prev] + previous tokens precede the sot sequence, sot_index follows
+        assert len(eng.all_decodes) == len(prompts)
+        for dec, prompt in zip(eng.all_decodes, prompts):
+            exp = ([v.sot_prev] + prompt[-223:] if prompt else []) + v.sot_sequence("en", None)
+            assert dec["initial"] == exp and dec["initial"][dec["sot_index"]] == v.sot
+
+
+def test_device_parsing_and_compute_types(monkeypatch):
+    assert bk.parse_device("cuda", 3) == 0 and bk.parse_device("cuda:5", 0) == 5
+    monkeypatch.setattr(bk, "get_engine", lambda *a, **k: FakeEngine())
+    for ct, want in (("float32", "fp32"), ("fp32", "fp32"), ("bfloat16", "bf16"), ("float16", "bf16"), ("int8", "bf16"), ("weird", "bf16")):
+        assert B200WhisperBackend("random:test-tiny", "cuda:0", ct).compute == want
+    for dev in ("cpu", "mps", "mlx"):
+        with pytest.raises(ValueError):
+            B200WhisperBackend("random:test-tiny", dev, "bfloat16")
+
+
+def test_checkpoint_resolution(tmp_path, monkeypatch):
+    import torch
+
+    from b200_whisper.synth import random_state_dict
+
+    dims = MODEL_DIMS["test-tiny"]
+    path = tmp_path / "tiny-test.pt"
+    torch.save({"dims": dims.__dict__, "model_state_dict": random_state_dict(dims, 1)}, path)
+    d, sd, name = bk.load_checkpoint(str(path))
+    assert d == dims and "decoder.token_embedding.weight" in sd
+    monkeypatch.setenv("B200_WHISPER_MODEL_DIR", str(tmp_path))
+    d2, _, _ = bk.load_checkpoint("tiny-test")
+    assert d2 == dims
+    with pytest.raises(RuntimeError):
+        bk.load_checkpoint("definitely-not-a-model")
+    d3, sd3, _ = bk.load_checkpoint("random:test-v3:3")
+    assert d3.n_mels == 128 and sd3["decoder.token_embedding.weight"].shape == (51866, 128)
+
+
+def test_registration_wraps_reference_get_backend(monkeypatch):
+    """register.install() against a stand-in for stt_server.model.{backends,worker} (the real package needs
+    grpc stubs that are not generated here)."""
+    pkg = types.ModuleType("stt_server"); model = types.ModuleType("stt_server.model")
+    backends = types.ModuleType("stt_server.model.backends"); worker = types.ModuleType("stt_server.model.worker")
+
+    def get_backend(name):
+        if name in ("torch_whisper", "faster_whisper"):
+            return "REF:" + name
+        raise ValueError(f"Unknown model backend: {name}")
+
+    backends.get_backend = get_backend
+    worker.get_backend = get_backend
+    for n, m in (("stt_server", pkg), ("stt_server.model", model), ("stt_server.model.backends", backends), ("stt_server.model.worker", worker)):
+        monkeypatch.setitem(sys.modules, n, m)
+    from b200_whisper import register
+
+    register.install()
+    register.install()  # idempotent
+    for alias in ("b200_whisper", "B200", "blackwell", "b200-whisper"):
+        assert backends.get_backend(alias) is B200WhisperBackend and worker.get_backend(alias) is B200WhisperBackend
+    assert backends.get_backend("torch_whisper") == "REF:torch_whisper"
+    with pytest.raises(ValueError):
+        backends.get_backend("nope")
+    assert "faster_whisper" in sys.modules  # stubbed when absent so the registry's eager import works
+
+
+def test_detokenizer_placeholder():
+    d = Detokenizer(vocab_for(51865))
+    v = vocab_for(51865)
+    assert d.decode([5, v.timestamp_begin + 3, 7]) == "<5><7>" and d.encode("hi") is None
