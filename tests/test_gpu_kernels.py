@@ -128,3 +128,47 @@ def test_gemm_cluster_splitk(shape):
     torch.cuda.synchronize()
     ref = _ref(A, B, bias, res, False)
     assert ((x - ref).norm() / ref.norm()).item() < 5e-3
+
+
+@pytest.mark.parametrize("shape", [(3000, 1280, 1280), (6000, 3840, 1280), (2999, 1000, 200), (24000, 1280, 384), (4500, 5120, 1280)])
+def test_gemm_cta_pair_persistent(shape):
+    """>= 60 pair tiles -> persistent cta_group::2 kernel (256x256 per CTA pair, double-buffered TMEM)"""
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = (torch.randn((M, K), device="cuda", generator=g) * 0.3).bfloat16()
+    B = (torch.randn((N, K), device="cuda", generator=g) * 0.3).bfloat16()
+    bias = torch.randn((N,), device="cuda", generator=g)
+    res = torch.randn((M, N), device="cuda", generator=g)
+    for gelu, use_res, out_fp32 in ((False, False, True), (True, False, False), (False, True, True)):
+        out = _gemm(0, A, B, bias, res if use_res else None, gelu, out_fp32).float()
+        ref = _ref(A, B, bias, res if use_res else None, gelu)
+        rel = ((out - ref).norm() / ref.norm()).item()
+        assert rel < (5e-3 if out_fp32 else 3e-2), f"{shape} gelu={gelu} res={use_res} fp32={out_fp32}: rel-L2 {rel}"
+        assert torch.isfinite(out).all()
+
+
+def test_gemm_throughput_report():
+    """not a pass/fail perf gate: prints TFLOP/s of the encoder GEMM shapes (CUDA events)"""
+    L, lib = _lib()
+    for M, N, K in ((24000, 5120, 1280), (24000, 1280, 5120), (24000, 3840, 1280), (24000, 1280, 1280), (6000, 5120, 1280)):
+        A = torch.randn((M, K), device="cuda").bfloat16()
+        B = torch.randn((N, K), device="cuda").bfloat16()
+        Cout = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+        for _ in range(3):
+            lib.bw_gemm_bf16(0, A.data_ptr(), B.data_ptr(), Cout.data_ptr(), None, None, M, N, K, 0, 0, None)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            lib.bw_gemm_bf16(0, A.data_ptr(), B.data_ptr(), Cout.data_ptr(), None, None, M, N, K, 0, 0, None)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(10):
+            torch.matmul(A, B.t(), out=Cout)
+        t1.record()
+        torch.cuda.synchronize()
+        ms_ref = t0.elapsed_time(t1) / 10
+        print(f"GEMM {M}x{N}x{K}: ours {2 * M * N * K / ms / 1e9:.0f} TFLOP/s ({ms:.3f} ms), cuBLAS {2 * M * N * K / ms_ref / 1e9:.0f} TFLOP/s")

@@ -237,15 +237,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // pipeline stages), the cluster synchronises, and CTA rank r reduces tile rows [r*128/KS, (r+1)*128/KS)
 // across all peers through distributed shared memory and runs the normal bias / GELU / residual epilogue.
 // No atomics, deterministic summation order, every weight byte still streamed from HBM exactly once.
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
 __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
@@ -419,6 +410,191 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Persistent CTA-pair GEMM (the encoder / cross-KV workhorse): cluster (2,1,1), tcgen05.mma.cta_group::2 with
+// M=256 N=256 per pair, so each SM stages 128 rows of A and 128 rows of B per k-block (32 KB for 128x256x64
+// MACs = 64 B/clk/SM, half of what 128x128 single-CTA tiles pull through L2 and shared memory).
+// 6-stage TMA ring, two 256-column TMEM accumulators per SM: the epilogue of tile i overlaps the main
+// loop of tile i+1.  warp 0 = TMA producer (both CTAs; bytes are credited to the leader's barrier),
+// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..7 = epilogue.
+constexpr int P_STAGES = 6;
+constexpr int P_STAGE_BYTES = 2 * BM * BK * 2;  // A half + B half
+constexpr int P_BAR_OFF = P_STAGES * P_STAGE_BYTES;
+constexpr int P_SMEM_TOTAL = P_BAR_OFF + 256 + 1024;
+
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p,
+                    int m_pairs, int n_tiles, int n_pair_tiles_total) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P_BAR_OFF);
+  uint64_t* empty_bar = full_bar + P_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + P_STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2] (used on the leader)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 2); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_ptr_smem, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto tile_coords = [&](int t, int& m0, int& n0, int& z) {
+    const int per_z = m_pairs * n_tiles;
+    z = t / per_z;
+    const int r = t - z * per_z;
+    n0 = (r / m_pairs) * 256;  // m fastest: pairs running together share the weight tile in L2
+    m0 = (r % m_pairs) * 256;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = pair; t < n_pair_tiles_total; t += n_pairs) {
+        int m0, n0, z;
+        tile_coords(t, m0, n0, z);
+        const int za = p.a_z_bcast ? 0 : z, zb = p.b_z_bcast ? 0 : z;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % P_STAGES;
+          mbar_wait(&empty_bar[s], ((it / P_STAGES) & 1) ^ 1);
+          uint8_t* sa = smem + s * P_STAGE_BYTES;
+          uint8_t* sb = sa + BM * BK * 2;
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * P_STAGE_BYTES);  // both CTAs' bytes land here
+          tma_load_3d_2sm(sa, &tmA, &full_bar[s], kb * BK, m0 + (int)rank * BM, za);
+          tma_load_3d_2sm(sb, &tmB, &full_bar[s], kb * BK, n0 + (int)rank * BM, zb);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, 256, 0, 0);
+      int it = 0, ti = 0;
+      for (int t = pair; t < n_pair_tiles_total; t += n_pairs, ++ti) {
+        const int a = ti & 1;
+        mbar_wait(&tmem_empty_bar[a], ((ti >> 1) & 1) ^ 1);  // both CTAs' epilogues drained this accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % P_STAGES;
+          mbar_wait(&full_bar[s], (it / P_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * P_STAGE_BYTES);
+          const uint32_t sb = sa + BM * BK * 2;
+          const uint64_t adesc = umma_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = umma_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_2sm(tmem_base + a * 256, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit_2sm(&empty_bar[s]);
+        }
+        umma_commit_2sm(&tmem_full_bar[a]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    int ti = 0;
+    for (int t = pair; t < n_pair_tiles_total; t += n_pairs, ++ti) {
+      int m0, n0, z;
+      tile_coords(t, m0, n0, z);
+      const int a = ti & 1;
+      const int i = m0 + (int)rank * BM + row;
+      const bool row_ok = i < p.M;
+      const float* bias = p.bias ? p.bias + (long long)z * p.bias_zstride : nullptr;
+      const float* res = p.residual ? p.residual + (long long)z * p.res_zstride : nullptr;
+      mbar_wait(&tmem_full_bar[a], (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        const int j0 = n0 + c * 32;
+        if (j0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * 256 + c * 32), r);
+        tmem_ld_wait();
+        const bool full = (j0 + 32 <= p.N);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          if (bias && (full || j0 + j < p.N)) x += __ldg(bias + j0 + j);
+          if (p.gelu) x = gelu_erf_fast(x);
+          v[j] = x;
+        }
+        if (row_ok) {
+        if (res) {
+          const float* rr = res + (long long)i * p.ldres + j0;
+          if (full && ((p.ldres & 3) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 q = *reinterpret_cast<const float4*>(rr + j);
+              v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j0 + j < p.N) v[j] += rr[j];
+          }
+        }
+        if (p.out_fp32) {
+          float* o = reinterpret_cast<float*>(p.C) + (long long)z * p.c_zstride + (long long)i * p.ldc + j0;
+          if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j0 + j < p.N) o[j] = v[j];
+          }
+        } else {
+          bf16* o = reinterpret_cast<bf16*>(p.C) + (long long)z * p.c_zstride + (long long)i * p.ldc + j0;
+          if (full && ((p.ldc & 7) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 q;
+              q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = q;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j0 + j < p.N) o[j] = __float2bfloat16(v[j]);
+          }
+        }
+        }
+      }
+      // this CTA's 128 epilogue threads are done with accumulator `a` -> one arrival on the leader's barrier
+      tc_fence_before();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (threadIdx.x == 128) mbar_arrive_cluster(&tmem_empty_bar[a], 0);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 // ---- host side: tensor maps (driver entry point fetched through the runtime; no -lcuda) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -573,6 +749,42 @@ void launch_splitk(const GemmArgs& g, cudaStream_t stream) {
   BW_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   ++g_kernel_launches;
 }
+
+void launch_pair(const GemmArgs& g, cudaStream_t stream) {
+  static std::atomic<unsigned long long> attr_set{0};
+  int dev = 0;
+  BW_CUDA(cudaGetDevice(&dev));
+  if (!(attr_set.load() >> dev & 1ull)) {
+    BW_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_TOTAL));
+    attr_set.fetch_or(1ull << dev);
+  }
+  const bool a_bcast = (g.Z > 1 && g.a_zstride == 0), b_bcast = (g.Z > 1 && g.b_zstride == 0);
+  CUtensorMap tmA = make_operand_map(g.A, g.a_rows > g.M ? g.a_rows : g.M, g.K, g.lda, a_bcast ? 1 : g.Z, g.a_zstride, BM);
+  CUtensorMap tmB = make_operand_map(g.B, g.b_rows > g.N ? g.b_rows : g.N, g.K, g.ldb, b_bcast ? 1 : g.Z, g.b_zstride, BM);
+  GemmDev p;
+  p.C = g.C; p.bias = g.bias; p.residual = g.residual;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = g.ldc; p.ldres = g.ldres;
+  p.c_zstride = g.c_zstride; p.bias_zstride = g.bias_zstride; p.res_zstride = g.res_zstride;
+  p.a_z_bcast = a_bcast; p.b_z_bcast = b_bcast;
+  p.gelu = g.gelu; p.out_fp32 = g.out_fp32; p.transposed = 0; p.accumulate = 0; p.ksplit = 1;
+  const int m_pairs = (g.M + 255) / 256, n_tiles = (g.N + 255) / 256;
+  const int total = m_pairs * n_tiles * g.Z;
+  static int sm_count = 0;
+  if (!sm_count) BW_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  const int n_pairs = std::min(total, sm_count / 2);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * n_pairs);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = P_SMEM_TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BW_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel, tmA, tmB, p, m_pairs, n_tiles, total));
+  ++g_kernel_launches;
+}
 }  // namespace
 
 void gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
@@ -580,6 +792,12 @@ void gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   // Tile choice: 128x256 (fewer smem bytes per MMA) when it still fills the 148 SMs, else
   // 128x128 with two CTAs per SM; tiny N (swap-AB decode) uses the narrowest tile that covers it.
   const long long mt = (g.M + BM - 1) / BM;
+  {
+    // enough 256x256 pair tiles to fill the 74 SM pairs -> persistent cta_group::2 kernel
+    static const bool no_pair = getenv("B200W_NO_PAIR") != nullptr;
+    const long long pair_tiles = (long long)((g.M + 255) / 256) * ((g.N + 255) / 256) * g.Z;
+    if (!no_pair && !g.transposed && !g.accumulate && pair_tiles >= 60 && g.N >= 256) return launch_pair(g, stream);
+  }
   if (!g.accumulate && g.N > 64 && g.ksplit >= 0) {
     // too few 128x128 tiles for 148 SMs -> split K over a cluster (DSMEM reduction, full epilogue)
     const long long tiles = mt * ((g.N + 127) / 128) * g.Z;
