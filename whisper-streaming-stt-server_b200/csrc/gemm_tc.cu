@@ -417,13 +417,13 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // MACs = 64 B/clk/SM, half of what 128x128 single-CTA tiles pull through L2 and shared memory).
 // 6-stage TMA ring, two 256-column TMEM accumulators per SM: the epilogue of tile i overlaps the main
 // loop of tile i+1.  warp 0 = TMA producer (both CTAs; bytes are credited to the leader's barrier),
-// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..7 = epilogue.
+// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..11 = epilogue.
 constexpr int P_STAGES = 6;
 constexpr int P_STAGE_BYTES = 2 * BM * BK * 2;  // A half + B half
 constexpr int P_BAR_OFF = P_STAGES * P_STAGE_BYTES;
 constexpr int P_SMEM_TOTAL = P_BAR_OFF + 256 + 1024;
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p,
                     int m_pairs, int n_tiles, int n_pair_tiles_total) {
   extern __shared__ uint8_t smem_raw[];
@@ -509,7 +509,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     __syncwarp();
   } else if (warp >= 4) {
+    // 8 epilogue warps: two per TMEM lane quarter, each draining 128 of the accumulator's 256 columns
     const int wq = warp & 3;
+    const int chalf = (warp - 4) >> 2;
     const int row = wq * 32 + lane;
     int ti = 0;
     for (int t = pair; t < n_pair_tiles_total; t += n_pairs, ++ti) {
@@ -523,7 +525,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tmem_full_bar[a], (ti >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = chalf * 4; c < chalf * 4 + 4; ++c) {
         const int j0 = n0 + c * 32;
         if (j0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
@@ -532,11 +534,23 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool full = (j0 + 32 <= p.N);
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
-          if (bias && (full || j0 + j < p.N)) x += __ldg(bias + j0 + j);
-          if (p.gelu) x = gelu_erf_fast(x);
-          v[j] = x;
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (bias) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {  // same address in every lane: one broadcast transaction per float4
+              const float4 q = __ldg(reinterpret_cast<const float4*>(bias + j0 + j));
+              v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j0 + j < p.N) v[j] += __ldg(bias + j0 + j);
+          }
+        }
+        if (p.gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
         }
         if (row_ok) {
         if (res) {
@@ -581,9 +595,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         }
       }
-      // this CTA's 128 epilogue threads are done with accumulator `a` -> one arrival on the leader's barrier
+      // this CTA's 256 epilogue threads are done with accumulator `a` -> one arrival on the leader's barrier
       tc_fence_before();
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync 2, 256;" ::: "memory");
       if (threadIdx.x == 128) mbar_arrive_cluster(&tmem_empty_bar[a], 0);
     }
   }
@@ -774,7 +788,7 @@ void launch_pair(const GemmArgs& g, cudaStream_t stream) {
   const int n_pairs = std::min(total, sm_count / 2);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * n_pairs);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(384);
   cfg.dynamicSmemBytes = P_SMEM_TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
