@@ -277,6 +277,8 @@ void decode_step(bw_engine* e, Ctl& ctl) {
                         dev(ctl.grp_n), dev(ctl.grp_x), dev(ctl.lrow_src));
   const float* logits = e->d_logits.as<float>();
   const int V = d.n_vocab;
+  static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;
+  PdlScope pdl(use_pdl && !e->fp32);
   no_speech_prob(logits, V, V, dev(ctl.ns_lrow), dev(ctl.ns_req), NNS, e->tt.no_speech, e->rs.no_speech_prob, e->stream);
   sample_topk(logits, V, V, dev(ctl.srow_lrow), dev(ctl.srow_req), dev(ctl.srow_seq), SR, e->tt, e->rs, e->ss, e->anc_cur,
               e->d_cand_tok.as<int>(), e->d_cand_lp.as<float>(), e->stream);
@@ -988,6 +990,8 @@ void synthetic_step(bw_engine* e, Ctl& ctl, int n_segments, int n_group, int cur
   engine_decoder_layers(e, R, n_segments, n_group, R, dev(ctl.row_seq), dev(ctl.row_pos), dev(ctl.row_tok), dev(ctl.grp_first),
                         dev(ctl.grp_n), dev(ctl.grp_x), dev(ctl.lrow_src));
   const int V = e->dims.n_vocab;
+  static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;
+  PdlScope pdl(use_pdl && !e->fp32);
   sample_topk(e->d_logits.as<float>(), V, V, dev(ctl.srow_lrow), dev(ctl.srow_req), dev(ctl.srow_seq), SR, e->tt, e->rs, e->ss,
               e->anc_cur, e->d_cand_tok.as<int>(), e->d_cand_lp.as<float>(), e->stream);
   beam_update(dev(ctl.act_req), dev(ctl.act_first), n_segments, e->tt, e->rs, e->ss, e->anc_cur, e->dims.n_text_ctx,

@@ -136,6 +136,8 @@ dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict
   __shared__ float sc[448];
   __shared__ float red[4];
   __shared__ float osm[4][64];
+  pdl_trigger();
+  pdl_wait();
   const int h = blockIdx.x, r = blockIdx.y;
   const int s = row_seq[r], pos = row_pos[r];
   const int first = seq_first[s];
@@ -371,6 +373,8 @@ dec_cross_attention_kernel(const int* __restrict__ group_first_row, const int* _
 
 template <typename T>
 __global__ void dec_cross_combine_kernel(const float* __restrict__ ws, int n_split, int d, T* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int h = blockIdx.x, row = blockIdx.y, n_head = gridDim.x, c = threadIdx.x;
   const float* w = ws + ((long long)row * n_head + h) * kMaxSplit * 66;
   float M = -INFINITY;
@@ -402,9 +406,8 @@ void dec_self_attention(const DecRows& rows, const float* qkv, const SelfKV& kv,
   if (rows.n_rows <= 0) return;
   BW_CHECK(kv.n_ctx <= 448, "n_text_ctx > 448 unsupported");
   dim3 grid(n_head, rows.n_rows);
-  dec_self_attention_kernel<T><<<grid, 128, 0, stream>>>(rows.row_seq, rows.row_pos, qkv, reinterpret_cast<const T*>(kv.pool),
-                                                         kv.unit_stride, kv.n_ctx, kv.seq_first, kv.anc, layer, d, out);
-  BW_CUDA(cudaGetLastError());
+  launch_kernel(dec_self_attention_kernel<T>, grid, dim3(128), 0, stream, rows.row_seq, rows.row_pos, qkv,
+                reinterpret_cast<const T*>(kv.pool), kv.unit_stride, kv.n_ctx, kv.seq_first, kv.anc, layer, d, out);
   ++g_kernel_launches;
 }
 template void dec_self_attention<float>(const DecRows&, const float*, const SelfKV&, int, int, int, float*, cudaStream_t);
@@ -453,8 +456,7 @@ void dec_cross_attention(const int* group_first_row, const int* group_n_rows, co
                               out, workspace, stream);
       if (n_split > 1) {
         dim3 grid(n_head, n_rows);
-        dec_cross_combine_kernel<T><<<grid, 64, 0, stream>>>(workspace, n_split, d, out);
-        BW_CUDA(cudaGetLastError());
+        launch_kernel(dec_cross_combine_kernel<T>, grid, dim3(64), 0, stream, (const float*)workspace, n_split, d, out);
         ++g_kernel_launches;
       }
       return;

@@ -64,6 +64,9 @@ dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int
     fence_barrier_init();
   }
   __syncthreads();
+  // PDL: the cached encoder K/V is never written during a decoder step, so the producer starts streaming it
+  // right away; only the consumers (which read q and write out / ws) wait for the preceding kernels.
+  pdl_trigger();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -79,6 +82,7 @@ dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int
     }
     __syncwarp();
   } else {
+    pdl_wait();
     const int gid = lane >> 2, tig = lane & 3;  // query row (hypothesis) and column pair inside an n-tile
     // A fragments of q (rows 8..15 are zero): 4 k-steps of 16 dims; 1/sqrt(64) folded in (exact in bf16)
     uint32_t qa[4][2];
@@ -220,9 +224,8 @@ void dec_cross_attention_mma(const int* group_first_row, const int* group_n_rows
   }
   const CUtensorMap tm = cached_tm;
   dim3 grid(n_head, n_groups, n_split);
-  dec_cross_attention_mma_kernel<<<grid, 160, XSM_TOTAL, stream>>>(tm, group_first_row, group_n_rows, group_xslot, q, kv.T_enc,
-                                                                   n_layer, layer, d, n_split, out, ws);
-  BW_CUDA(cudaGetLastError());
+  launch_kernel(dec_cross_attention_mma_kernel, grid, dim3(160), XSM_TOTAL, stream, tm, group_first_row, group_n_rows, group_xslot, q,
+                kv.T_enc, n_layer, layer, d, n_split, out, ws);
   ++g_kernel_launches;
 }
 

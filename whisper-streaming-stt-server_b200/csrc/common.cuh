@@ -7,6 +7,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 namespace bw {
 
@@ -29,6 +30,30 @@ struct CudaError : std::runtime_error {
   } while (0)
 
 typedef __nv_bfloat16 bf16;
+
+// ---- Programmatic Dependent Launch (decoder step: ~390 short kernels back to back) ----
+// Kernels call pdl_trigger() as early as possible and pdl_wait() before they touch anything a preceding kernel
+// wrote (or write anything it may still read); launched without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+extern thread_local bool tl_pdl;  // set by the engine around the decoder step (see PdlScope)
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool on) : prev(tl_pdl) { tl_pdl = on; }
+  ~PdlScope() { tl_pdl = prev; }
+};
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tl_pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+  if (e != cudaSuccess) throw CudaError(std::string("kernel launch -> ") + cudaGetErrorString(e));
+}
 
 // ---- scalar conversion helpers (templated kernels run in float or bf16 storage) ----
 __device__ __forceinline__ float to_f(float x) { return x; }
@@ -109,6 +134,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---- TMA (cp.async.bulk.tensor) ----
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(desc) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* desc, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(desc), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1) {
   asm volatile(

@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(128)
 layernorm_kernel(const float* __restrict__ x, const int* __restrict__ rows_idx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, TOut* __restrict__ out, int rows, int d) {
   __shared__ float red[4];
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)(GATHER ? rows_idx[row] : row) * d);
@@ -105,6 +107,8 @@ template <typename T>
 __global__ void dec_embed_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos,
                                  const int* __restrict__ row_tok, const int* __restrict__ next_tok,
                                  const T* __restrict__ tok_emb, const T* __restrict__ pos_emb, float* __restrict__ x, int d) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x;
   int tok = row_tok[r];
   if (tok < 0) tok = next_tok[row_seq[r]];
@@ -116,6 +120,8 @@ __global__ void dec_embed_kernel(const int* __restrict__ row_seq, const int* __r
 template <typename T>
 __global__ void dec_kv_append_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const float* __restrict__ qkv,
                                      T* __restrict__ pool, long long unit_stride, int n_ctx, int layer, int d) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x;
   const int s = row_seq[r], pos = row_pos[r];
   T* kdst = pool + (long long)s * unit_stride + ((long long)(layer * 2 + 0) * n_ctx + pos) * d;
@@ -135,8 +141,7 @@ template <typename T>
 void layernorm(const float* x, const float* gamma, const float* beta, T* out, int rows, int d, cudaStream_t stream) {
   BW_CHECK(d <= 1536 && d % 4 == 0, "layernorm supports d <= 1536, d % 4 == 0");
   if (rows <= 0) return;
-  layernorm_kernel<T, false><<<rows, 128, 0, stream>>>(x, nullptr, gamma, beta, out, rows, d);
-  BW_CUDA(cudaGetLastError());
+  launch_kernel(layernorm_kernel<T, false>, dim3(rows), dim3(128), 0, stream, x, (const int*)nullptr, gamma, beta, out, rows, d);
   ++g_kernel_launches;
 }
 template void layernorm<float>(const float*, const float*, const float*, float*, int, int, cudaStream_t);
@@ -151,8 +156,7 @@ void layernorm_gather(const float* x, const int* rows_idx, const float* gamma, c
                       cudaStream_t stream) {
   BW_CHECK(d <= 1536 && d % 4 == 0, "layernorm supports d <= 1536, d % 4 == 0");
   if (n <= 0) return;
-  layernorm_kernel<T, true><<<n, 128, 0, stream>>>(x, rows_idx, gamma, beta, out, n, d);
-  BW_CUDA(cudaGetLastError());
+  launch_kernel(layernorm_kernel<T, true>, dim3(n), dim3(128), 0, stream, x, rows_idx, gamma, beta, out, n, d);
   ++g_kernel_launches;
 }
 template void layernorm_gather<float>(const float*, const int*, const float*, const float*, float*, int, int, cudaStream_t);
@@ -197,8 +201,7 @@ template <typename T>
 void dec_embed(const DecRows& rows, const int* next_tok, const T* tok_emb, const T* pos_emb, float* x, int d,
                cudaStream_t stream) {
   if (rows.n_rows <= 0) return;
-  dec_embed_kernel<T><<<rows.n_rows, 128, 0, stream>>>(rows.row_seq, rows.row_pos, rows.row_tok, next_tok, tok_emb, pos_emb, x, d);
-  BW_CUDA(cudaGetLastError());
+  launch_kernel(dec_embed_kernel<T>, dim3(rows.n_rows), dim3(128), 0, stream, rows.row_seq, rows.row_pos, rows.row_tok, next_tok, tok_emb, pos_emb, x, d);
   ++g_kernel_launches;
 }
 template void dec_embed<float>(const DecRows&, const int*, const float*, const float*, float*, int, cudaStream_t);
@@ -207,9 +210,8 @@ template void dec_embed<bf16>(const DecRows&, const int*, const bf16*, const bf1
 template <typename T>
 void dec_kv_append(const DecRows& rows, const float* qkv, const SelfKV& kv, int layer, int d, cudaStream_t stream) {
   if (rows.n_rows <= 0) return;
-  dec_kv_append_kernel<T><<<rows.n_rows, 128, 0, stream>>>(rows.row_seq, rows.row_pos, qkv, reinterpret_cast<T*>(kv.pool),
-                                                           kv.unit_stride, kv.n_ctx, layer, d);
-  BW_CUDA(cudaGetLastError());
+  launch_kernel(dec_kv_append_kernel<T>, dim3(rows.n_rows), dim3(128), 0, stream, rows.row_seq, rows.row_pos, qkv,
+                reinterpret_cast<T*>(kv.pool), kv.unit_stride, kv.n_ctx, layer, d);
   ++g_kernel_launches;
 }
 template void dec_kv_append<float>(const DecRows&, const float*, const SelfKV&, int, int, cudaStream_t);

@@ -6,6 +6,7 @@
 #include "engine.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -172,6 +173,8 @@ struct Impl {
     const int *row_seq, *row_pos, *row_tok, *grp_first, *grp_n, *grp_x, *lrow_src;
   };
   void decoder_layers(const StepCtl& c) const {
+    static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;
+    PdlScope pdl(use_pdl && !std::is_same<T, float>::value);
     const auto& d = D();
     const int dm = d.n_text_state, L = d.n_text_layer, H = d.n_text_head;
     cudaStream_t st = e->stream;

@@ -20,6 +20,7 @@
 namespace bw {
 
 std::atomic<long long> g_kernel_launches{0};
+thread_local bool tl_pdl = false;
 
 namespace {
 
@@ -86,6 +87,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -286,6 +289,14 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // PDL: let the next kernel start its prologue, pull this CTA's slice of the WEIGHT operand (B, never written
+  // during a step) towards L2 while the preceding kernel is still draining, then wait for it.
+  pdl_trigger();
+  if (warp == 0 && lane == 0) {
+    const int zb = p.b_z_bcast ? 0 : z;
+    for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_l2_3d(&tmB, (kb0 + kb) * BK, n0, zb);
+  }
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -723,8 +734,7 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
   }
   p.ksplit = ksplit;
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.Z * ksplit);
-  kern<<<grid, 192, L::kTotal, stream>>>(tmA, tmB, p);
-  BW_CUDA(cudaGetLastError());
+  launch_kernel(kern, grid, dim3(192), L::kTotal, stream, tmA, tmB, p);
   ++g_kernel_launches;
 }
 
@@ -755,11 +765,13 @@ void launch_splitk(const GemmArgs& g, cudaStream_t stream) {
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = KS;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = tl_pdl ? 2 : 1;
   BW_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   ++g_kernel_launches;
 }

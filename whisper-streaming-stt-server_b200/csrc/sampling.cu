@@ -75,8 +75,9 @@ sample_topk_kernel(const float* __restrict__ logits, int ld, int V, const int* _
   __shared__ float sh_m[ST / 32], sh_s[ST / 32];
   __shared__ float wv[ST / 32];
   __shared__ int wi[ST / 32];
-  __shared__ float win_v;
   __shared__ int win_i;
+  pdl_trigger();
+  pdl_wait();
   const int lr = blockIdx.x;
   const int q = lrow_req[lr], s = lrow_seq[lr];
   const float* x = logits + (long long)srow_lrow[lr] * ld;
@@ -161,7 +162,7 @@ sample_topk_kernel(const float* __restrict__ logits, int ld, int V, const int* _
       float fv = wv[0]; int fi = wi[0];
       for (int w = 1; w < ST / 32; ++w)
         if (better(wv[w], wi[w], fv, fi)) { fv = wv[w]; fi = wi[w]; }
-      win_v = fv; win_i = fi;
+      win_i = fi;
       cand_tok[lr * kMaxCand + k] = (fi == INT_MAX) ? -1 : fi;
       cand_lp[lr * kMaxCand + k] = (fi == INT_MAX) ? -INFINITY : fv - lse;
     }
@@ -178,6 +179,8 @@ __global__ void __launch_bounds__(32)
 beam_update_kernel(const int* __restrict__ active_req, const int* __restrict__ req_first_lrow, const TokenTables tt,
                    const ReqState rs, const SeqState ss, int anc_cur, int n_ctx, const int* __restrict__ cand_tok,
                    const float* __restrict__ cand_lp) {
+  pdl_trigger();
+  pdl_wait();
   const int q = active_req[blockIdx.x];
   const int lr0 = req_first_lrow[blockIdx.x];
   const int lane = threadIdx.x;
@@ -284,6 +287,8 @@ __global__ void __launch_bounds__(ST)
 no_speech_kernel(const float* __restrict__ logits, int ld, int V, const int* __restrict__ lrows, const int* __restrict__ reqs,
                  int no_speech_id, float* __restrict__ out_prob) {
   __shared__ float sh_m[ST / 32], sh_s[ST / 32];
+  pdl_trigger();
+  pdl_wait();
   const float* x = logits + (long long)lrows[blockIdx.x] * ld;
   float m = -INFINITY, s = 0.f;
   for (int id = threadIdx.x; id < V; id += ST) ms_merge(m, s, x[id], 1.f);
@@ -325,24 +330,21 @@ void sample_topk(const float* logits, int ld, int V, const int* srow_lrow, const
                  cudaStream_t stream) {
   (void)anc_cur;
   if (n_lrows <= 0) return;
-  sample_topk_kernel<<<n_lrows, ST, 0, stream>>>(logits, ld, V, srow_lrow, lrow_req, lrow_seq, tt, rs, ss, cand_tok, cand_lp);
-  BW_CUDA(cudaGetLastError());
+  launch_kernel(sample_topk_kernel, dim3(n_lrows), dim3(ST), 0, stream, logits, ld, V, srow_lrow, lrow_req, lrow_seq, tt, rs, ss, cand_tok, cand_lp);
   ++g_kernel_launches;
 }
 
 void beam_update(const int* active_req, const int* req_first_lrow, int n_active, const TokenTables& tt, const ReqState& rs,
                  const SeqState& ss, int anc_cur, int n_ctx, const int* cand_tok, const float* cand_lp, cudaStream_t stream) {
   if (n_active <= 0) return;
-  beam_update_kernel<<<n_active, 32, 0, stream>>>(active_req, req_first_lrow, tt, rs, ss, anc_cur, n_ctx, cand_tok, cand_lp);
-  BW_CUDA(cudaGetLastError());
+  launch_kernel(beam_update_kernel, dim3(n_active), dim3(32), 0, stream, active_req, req_first_lrow, tt, rs, ss, anc_cur, n_ctx, cand_tok, cand_lp);
   ++g_kernel_launches;
 }
 
 void no_speech_prob(const float* logits, int ld, int V, const int* lrows, const int* reqs, int n, int no_speech_id,
                     float* out_prob, cudaStream_t stream) {
   if (n <= 0) return;
-  no_speech_kernel<<<n, ST, 0, stream>>>(logits, ld, V, lrows, reqs, no_speech_id, out_prob);
-  BW_CUDA(cudaGetLastError());
+  launch_kernel(no_speech_kernel, dim3(n), dim3(ST), 0, stream, logits, ld, V, lrows, reqs, no_speech_id, out_prob);
   ++g_kernel_launches;
 }
 
