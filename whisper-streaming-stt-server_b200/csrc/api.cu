@@ -14,8 +14,8 @@ void engine_encoder_forward(bw_engine* e, int nb);
 void engine_cross_kv(bw_engine* e, int bi, int q);
 void engine_window_to_A1(bw_engine* e, const float* logmel, int ld, int n_real, const int* gmax, int seek, int seg, int bi);
 void engine_decoder_layers(bw_engine* e, int R, int n_groups, int max_group_rows, int n_lrows, const int* row_seq,
-                           const int* row_pos, const int* row_tok, const int* grp_first, const int* grp_n, const int* grp_x,
-                           const int* lrow_src);
+                           const int* row_pos, const int* row_tok, const int* row_bpos, const int* grp_first, const int* grp_n,
+                           const int* grp_x, const int* lrow_src);
 void engine_init_requests(bw_engine* e, const int* init_dev, int n);
 }  // namespace bw
 
@@ -55,13 +55,13 @@ void finish_request(Request* r, int status, const std::string& err) {
 
 // ---- control-block layout (ints) ----
 struct Ctl {
-  int *row_seq, *row_pos, *row_tok, *grp_first, *grp_n, *grp_x, *lrow_src, *srow_lrow, *srow_req, *srow_seq, *act_req,
+  int *row_seq, *row_pos, *row_tok, *row_bpos, *grp_first, *grp_n, *grp_x, *lrow_src, *srow_lrow, *srow_req, *srow_seq, *act_req,
       *act_first, *ns_lrow, *ns_req, *init;
   size_t total;
   void layout(int* base, int R, int LR, int Q) {
     int* p = base;
     auto take = [&](size_t n) { int* r = p; p += n; return r; };
-    row_seq = take(R); row_pos = take(R); row_tok = take(R);
+    row_seq = take(R); row_pos = take(R); row_tok = take(R); row_bpos = take(R);
     grp_first = take(R); grp_n = take(R); grp_x = take(R);
     lrow_src = take(LR); srow_lrow = take(LR); srow_req = take(LR); srow_seq = take(LR);
     act_req = take(Q); act_first = take(Q); ns_lrow = take(Q); ns_req = take(Q);
@@ -227,7 +227,7 @@ void decode_step(bw_engine* e, Ctl& ctl) {
       const int n_init = (int)r->initial.size();
       const int row0 = R;
       for (int t = 0; t < n_init; ++t) {
-        ctl.row_seq[R] = r->first_seq; ctl.row_pos[R] = t; ctl.row_tok[R] = r->initial[t];
+        ctl.row_seq[R] = r->first_seq; ctl.row_pos[R] = t; ctl.row_tok[R] = r->initial[t]; ctl.row_bpos[R] = 0;
         ++R;
       }
       for (int t = 0; t < n_init; t += 8) {
@@ -261,7 +261,7 @@ void decode_step(bw_engine* e, Ctl& ctl) {
       ++NG;
       ctl.act_req[NA] = r->q; ctl.act_first[NA] = SR; ++NA;
       for (int j = 0; j < r->G; ++j) {
-        ctl.row_seq[R] = r->first_seq + j; ctl.row_pos[R] = r->cur_len - 1; ctl.row_tok[R] = -1;
+        ctl.row_seq[R] = r->first_seq + j; ctl.row_pos[R] = r->cur_len - 1; ctl.row_tok[R] = -1; ctl.row_bpos[R] = r->cur_len - 1;
         ctl.lrow_src[LR] = R;
         ctl.srow_lrow[SR] = LR; ctl.srow_req[SR] = r->q; ctl.srow_seq[SR] = r->first_seq + j;
         ++R; ++LR; ++SR;
@@ -273,7 +273,7 @@ void decode_step(bw_engine* e, Ctl& ctl) {
   const size_t used = (size_t)(ctl.init - e->h_ctrl);
   BW_CUDA(cudaMemcpyAsync(dbase, e->h_ctrl, used * 4, cudaMemcpyHostToDevice, e->stream));
   e->stat_h2d += (long long)used * 4;
-  engine_decoder_layers(e, R, NG, max_grp, LR, dev(ctl.row_seq), dev(ctl.row_pos), dev(ctl.row_tok), dev(ctl.grp_first),
+  engine_decoder_layers(e, R, NG, max_grp, LR, dev(ctl.row_seq), dev(ctl.row_pos), dev(ctl.row_tok), dev(ctl.row_bpos), dev(ctl.grp_first),
                         dev(ctl.grp_n), dev(ctl.grp_x), dev(ctl.lrow_src));
   const float* logits = e->d_logits.as<float>();
   const int V = d.n_vocab;
@@ -979,7 +979,7 @@ void synthetic_step(bw_engine* e, Ctl& ctl, int n_segments, int n_group, int cur
     ctl.grp_first[i] = R; ctl.grp_n[i] = n_group; ctl.grp_x[i] = i;
     ctl.act_req[i] = i; ctl.act_first[i] = SR;
     for (int j = 0; j < n_group; ++j) {
-      ctl.row_seq[R] = i * n_group + j; ctl.row_pos[R] = cur - 1; ctl.row_tok[R] = -1;
+      ctl.row_seq[R] = i * n_group + j; ctl.row_pos[R] = cur - 1; ctl.row_tok[R] = -1; ctl.row_bpos[R] = cur - 1;
       ctl.lrow_src[R] = R; ctl.srow_lrow[SR] = R; ctl.srow_req[SR] = i; ctl.srow_seq[SR] = i * n_group + j;
       ++R; ++SR;
     }
@@ -987,7 +987,7 @@ void synthetic_step(bw_engine* e, Ctl& ctl, int n_segments, int n_group, int cur
   int* dbase = e->d_ctrl.as<int>();
   auto dev = [&](int* h) { return dbase + (h - e->h_ctrl); };
   BW_CUDA(cudaMemcpyAsync(dbase, e->h_ctrl, (size_t)(ctl.init - e->h_ctrl) * 4, cudaMemcpyHostToDevice, e->stream));
-  engine_decoder_layers(e, R, n_segments, n_group, R, dev(ctl.row_seq), dev(ctl.row_pos), dev(ctl.row_tok), dev(ctl.grp_first),
+  engine_decoder_layers(e, R, n_segments, n_group, R, dev(ctl.row_seq), dev(ctl.row_pos), dev(ctl.row_tok), dev(ctl.row_bpos), dev(ctl.grp_first),
                         dev(ctl.grp_n), dev(ctl.grp_x), dev(ctl.lrow_src));
   const int V = e->dims.n_vocab;
   static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;

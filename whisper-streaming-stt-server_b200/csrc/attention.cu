@@ -127,85 +127,110 @@ template <> struct Vec16<float> {
   __device__ static void load_stream(const float* p, float* f) { load(p, f); }
 };
 
+constexpr int kSingleBeamFlag = 0x40000000;  // set in seq_first[s] when the request has one hypothesis (anc == 0)
+
+// One CTA per (head, row).  Fuses the KV append: this row's k/v head slice (fp32 qkv buffer -> T) is written to
+// the pool, and keys/values of positions fed in THIS step (the row itself; earlier prefill rows of the same
+// sequence) are read from the qkv buffer instead of the pool, so no ordering between CTAs is needed.
+// Single pass: K and V of a position are loaded together (two 16-byte loads in flight per lane), online softmax
+// per lane group, one shared-memory merge at the end.
 template <typename T>
 __global__ void __launch_bounds__(128)
-dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const float* __restrict__ qkv,
-                          const T* __restrict__ pool, long long unit_stride, int n_ctx, const int* __restrict__ seq_first,
-                          const unsigned char* __restrict__ anc, int layer, int d, T* __restrict__ out) {
+dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const int* __restrict__ row_bpos,
+                          const float* __restrict__ qkv, T* __restrict__ pool, long long unit_stride, int n_ctx,
+                          const int* __restrict__ seq_first, const unsigned char* __restrict__ anc, int layer, int d,
+                          T* __restrict__ out) {
   constexpr int VEC = Vec16<T>::N, LPR = 64 / VEC, RPW = 32 / LPR;
-  __shared__ float sc[448];
-  __shared__ float red[4];
-  __shared__ float osm[4][64];
+  __shared__ float part[4][RPW > 0 ? 66 : 66];
   pdl_trigger();
   pdl_wait();
   const int h = blockIdx.x, r = blockIdx.y;
-  const int s = row_seq[r], pos = row_pos[r];
-  const int first = seq_first[s];
+  const int s = row_seq[r], pos = row_pos[r], bpos = row_bpos[r];
+  const int sf = seq_first[s];
+  const bool single = (sf & kSingleBeamFlag) != 0;
+  const int first = sf & ~kSingleBeamFlag;
   const unsigned char* my_anc = anc + (long long)s * n_ctx;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane % LPR, rg = lane / LPR;
+  const float* qrow = qkv + (long long)r * 3 * d + h * 64;
+  // fused append: k/v of this row -> pool[unit s][layer][k|v][pos]
+  {
+    const int c = threadIdx.x & 63, kvsel = threadIdx.x >> 6;  // 0: k, 1: v
+    pool[(long long)s * unit_stride + ((long long)(layer * 2 + kvsel) * n_ctx + pos) * d + h * 64 + c] =
+        from_f<T>(qrow[(1 + kvsel) * d + c]);
+  }
   float qf[VEC];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) qf[i] = qkv[(long long)r * 3 * d + h * 64 + sub * VEC + i] * 0.125f;
+  for (int i = 0; i < VEC; ++i) qf[i] = qrow[sub * VEC + i] * 0.125f;
   const long long koff = ((long long)(layer * 2 + 0) * n_ctx) * d + h * 64 + sub * VEC;
   const long long voff = ((long long)(layer * 2 + 1) * n_ctx) * d + h * 64 + sub * VEC;
   const int n = pos + 1;
-  for (int tg = warp * RPW; tg < n; tg += 4 * RPW) {
-    const int t = tg + rg;
-    float acc = 0.f;
-    if (t < n) {
-      float kf[VEC];
-      Vec16<T>::load(pool + (long long)(first + my_anc[t]) * unit_stride + koff + (long long)t * d, kf);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) acc = fmaf(qf[i], kf[i], acc);
-    }
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (t < n && sub == 0) sc[t] = acc;
-  }
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int t = threadIdx.x; t < n; t += 128) mx = fmaxf(mx, sc[t]);
-  mx = warp_max(mx);
-  if (lane == 0) red[warp] = mx;
-  __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-  __syncthreads();
-  float sum = 0.f;
-  for (int t = threadIdx.x; t < n; t += 128) {
-    const float p = exp_t<T>(sc[t] - mx);
-    sc[t] = p;
-    sum += p;
-  }
-  sum = warp_sum(sum);
-  if (lane == 0) red[warp] = sum;
-  __syncthreads();
-  sum = red[0] + red[1] + red[2] + red[3];
-  float acc[VEC];
+  float m = -INFINITY, l = 0.f, acc[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
   for (int tg = warp * RPW; tg < n; tg += 4 * RPW) {
     const int t = tg + rg;
+    float kf[VEC], vf[VEC];
+    float sc = -INFINITY;
     if (t < n) {
-      float vf[VEC];
-      Vec16<T>::load(pool + (long long)(first + my_anc[t]) * unit_stride + voff + (long long)t * d, vf);
-      const float p = sc[t];
+      if (t < bpos) {
+        const T* base = pool + (long long)(single ? first : first + my_anc[t]) * unit_stride + (long long)t * d;
+        Vec16<T>::load(base + koff, kf);
+        Vec16<T>::load(base + voff, vf);
+      } else {  // fed in this step: fp32 rows of the qkv buffer, rounded like the pool copy
+        const float* src = qkv + (long long)(r - (pos - t)) * 3 * d + h * 64 + sub * VEC;
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
+        for (int i = 0; i < VEC; ++i) { kf[i] = to_f(from_f<T>(src[d + i])); vf[i] = to_f(from_f<T>(src[2 * d + i])); }
+      }
+      sc = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) sc = fmaf(qf[i], kf[i], sc);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      const float other = __shfl_xor_sync(0xffffffffu, sc, o);
+      sc = (t < n) ? sc + other : sc;
+    }
+    if (t < n) {
+      const float m_new = fmaxf(m, sc);
+      const float a = exp_t<T>(m - m_new), pr = exp_t<T>(sc - m_new);
+      l = l * a + pr;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = fmaf(pr, vf[i], acc[i] * a);
+      m = m_new;
     }
   }
+  // merge the row groups of this warp, then the 4 warps
 #pragma unroll
-  for (int o = LPR; o < 32; o <<= 1)
+  for (int o = LPR; o < 32; o <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+    const float M = fmaxf(m, m2);
+    const float e1 = (m == -INFINITY) ? 0.f : exp_t<T>(m - M), e2 = (m2 == -INFINITY) ? 0.f : exp_t<T>(m2 - M);
+    l = l * e1 + l2 * e2;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-  if (rg == 0)
+    for (int i = 0; i < VEC; ++i) {
+      const float a2 = __shfl_xor_sync(0xffffffffu, acc[i], o);
+      acc[i] = acc[i] * e1 + a2 * e2;
+    }
+    m = M;
+  }
+  if (rg == 0) {
+    if (sub == 0) { part[warp][0] = m; part[warp][1] = l; }
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) osm[warp][sub * VEC + i] = acc[i];
+    for (int i = 0; i < VEC; ++i) part[warp][2 + sub * VEC + i] = acc[i];
+  }
   __syncthreads();
   if (threadIdx.x < 64) {
     const int c = threadIdx.x;
-    const float v = (osm[0][c] + osm[1][c] + osm[2][c] + osm[3][c]) / sum;
-    out[(long long)r * d + h * 64 + c] = from_f<T>(v);
+    float M = fmaxf(fmaxf(part[0][0], part[1][0]), fmaxf(part[2][0], part[3][0]));
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float e = (part[w][0] == -INFINITY) ? 0.f : exp_t<T>(part[w][0] - M);
+      num = fmaf(e, part[w][2 + c], num);
+      den = fmaf(e, part[w][1], den);
+    }
+    out[(long long)r * d + h * 64 + c] = from_f<T>(num / den);
   }
 }
 
@@ -406,8 +431,8 @@ void dec_self_attention(const DecRows& rows, const float* qkv, const SelfKV& kv,
   if (rows.n_rows <= 0) return;
   BW_CHECK(kv.n_ctx <= 448, "n_text_ctx > 448 unsupported");
   dim3 grid(n_head, rows.n_rows);
-  launch_kernel(dec_self_attention_kernel<T>, grid, dim3(128), 0, stream, rows.row_seq, rows.row_pos, qkv,
-                reinterpret_cast<const T*>(kv.pool), kv.unit_stride, kv.n_ctx, kv.seq_first, kv.anc, layer, d, out);
+  launch_kernel(dec_self_attention_kernel<T>, grid, dim3(128), 0, stream, rows.row_seq, rows.row_pos, rows.row_bpos, qkv,
+                reinterpret_cast<T*>(kv.pool), kv.unit_stride, kv.n_ctx, kv.seq_first, kv.anc, layer, d, out);
   ++g_kernel_launches;
 }
 template void dec_self_attention<float>(const DecRows&, const float*, const SelfKV&, int, int, int, float*, cudaStream_t);

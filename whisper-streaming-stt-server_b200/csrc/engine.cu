@@ -26,7 +26,8 @@ __global__ void init_requests_kernel(const int* __restrict__ init, int n, ReqSta
     rs.n_finished[q] = 0; rs.completed[q] = 0; rs.no_speech_prob[q] = nanf("");
     for (int j = 0; j < G; ++j) {
       const int s = first_seq + j;
-      ss.sum_logprob[s] = 0.f; ss.next_tok[s] = r[10]; ss.prev_tok[s] = -1; ss.last_ts[s] = -1; ss.seq_first[s] = first_seq;
+      ss.sum_logprob[s] = 0.f; ss.next_tok[s] = r[10]; ss.prev_tok[s] = -1; ss.last_ts[s] = -1;
+      ss.seq_first[s] = first_seq | (G == 1 ? 0x40000000 : 0);  // kSingleBeamFlag: ancestry is identically 0
     }
   }
   unsigned char* a = ss.anc[anc_cur] + (long long)first_seq * n_ctx;
@@ -170,7 +171,7 @@ struct Impl {
   // ---- one decoder step over `R` rows; control arrays already on the device ----
   struct StepCtl {
     int R = 0, n_groups = 0, max_group_rows = 1, n_lrows = 0;
-    const int *row_seq, *row_pos, *row_tok, *grp_first, *grp_n, *grp_x, *lrow_src;
+    const int *row_seq, *row_pos, *row_tok, *row_bpos, *grp_first, *grp_n, *grp_x, *lrow_src;
   };
   void decoder_layers(const StepCtl& c) const {
     static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;
@@ -179,7 +180,7 @@ struct Impl {
     const int dm = d.n_text_state, L = d.n_text_layer, H = d.n_text_head;
     cudaStream_t st = e->stream;
     DecRows rows;
-    rows.n_rows = c.R; rows.row_seq = c.row_seq; rows.row_pos = c.row_pos; rows.row_tok = c.row_tok;
+    rows.n_rows = c.R; rows.row_seq = c.row_seq; rows.row_pos = c.row_pos; rows.row_tok = c.row_tok; rows.row_bpos = c.row_bpos;
     float* x = e->d_x.as<float>();
     dec_embed<T>(rows, e->ss.next_tok, reinterpret_cast<const T*>(e->w.tok_emb), reinterpret_cast<const T*>(e->w.dec_pos), x, dm, st);
     SelfKV skv;
@@ -193,7 +194,6 @@ struct Impl {
       const LayerW& w = e->w.dec[l];
       layernorm<T>(x, w.ln1_g, w.ln1_b, e->d_xn.as<T>(), c.R, dm, st);
       linear_rows(e->d_xn.as<T>(), c.R, Ra, w.wqkv, 3 * dm, dm, w.bqkv, nullptr, e->d_qkv.p, false, true);
-      dec_kv_append<T>(rows, e->d_qkv.as<float>(), skv, l, dm, st);
       dec_self_attention<T>(rows, e->d_qkv.as<float>(), skv, l, dm, H, e->d_att.as<T>(), st);
       linear_rows(e->d_att.as<T>(), c.R, Ra, w.wo, dm, dm, w.bo, x, x, false, true);
       layernorm<T>(x, w.lnx_g, w.lnx_b, e->d_xn.as<T>(), c.R, dm, st);
@@ -355,15 +355,15 @@ void engine_window_to_A1(bw_engine* e, const float* logmel, int ld, int n_real, 
   else Impl<bf16>(e).window_to_A1(logmel, ld, n_real, gmax, seek, seg, bi);
 }
 void engine_decoder_layers(bw_engine* e, int R, int n_groups, int max_group_rows, int n_lrows, const int* row_seq,
-                           const int* row_pos, const int* row_tok, const int* grp_first, const int* grp_n, const int* grp_x,
-                           const int* lrow_src) {
+                           const int* row_pos, const int* row_tok, const int* row_bpos, const int* grp_first, const int* grp_n,
+                           const int* grp_x, const int* lrow_src) {
   if (e->fp32) {
     Impl<float>::StepCtl c; c.R = R; c.n_groups = n_groups; c.max_group_rows = max_group_rows; c.n_lrows = n_lrows;
-    c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
+    c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.row_bpos = row_bpos; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
     Impl<float>(e).decoder_layers(c);
   } else {
     Impl<bf16>::StepCtl c; c.R = R; c.n_groups = n_groups; c.max_group_rows = max_group_rows; c.n_lrows = n_lrows;
-    c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
+    c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.row_bpos = row_bpos; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
     Impl<bf16>(e).decoder_layers(c);
   }
 }

@@ -51,6 +51,7 @@ struct DecRows {
   const int* row_seq = nullptr;   // [R] sequence slot (state arrays are indexed by it)
   const int* row_pos = nullptr;   // [R] position of the row's token in its sequence
   const int* row_tok = nullptr;   // [R] token id, or -1: take next_tok[row_seq]
+  const int* row_bpos = nullptr;  // [R] position of the first row of this sequence fed in THIS step (<= row_pos)
 };
 
 // x[r] = E[tok] + pos_emb[pos]  (fp32 residual stream)
@@ -71,7 +72,8 @@ struct SelfKV {
 // scatter this step's k/v (from the fp32 qkv rows [R, 3d]) into the pool for `layer`
 template <typename T>
 void dec_kv_append(const DecRows& rows, const float* qkv, const SelfKV& kv, int layer, int d, cudaStream_t stream);
-// out[r] = softmax(q_r . K[0..pos_r]) V   (head dim 64); q = first d columns of the fp32 qkv rows
+// out[r] = softmax(q_r . K[0..pos_r]) V   (head dim 64); q = first d columns of the fp32 qkv rows.
+// Also appends this step's k/v to the pool (the separate dec_kv_append launch is no longer needed).
 template <typename T>
 void dec_self_attention(const DecRows& rows, const float* qkv, const SelfKV& kv, int layer, int d, int n_head, T* out,
                         cudaStream_t stream);

@@ -12,7 +12,8 @@
 namespace bw {
 namespace {
 
-constexpr int ST = 256;  // threads of the per-row kernels
+constexpr int ST = 512;  // threads of the per-row kernels
+constexpr int SU = 8;    // logits loaded per thread per batch (keeps 8 coalesced loads in flight)
 
 struct RowRules {
   int tb, eot, no_ts_id;
@@ -29,8 +30,7 @@ struct RowRules {
 
 __device__ __forceinline__ bool allowed(const RowRules& r, int id) {
   if (r.suppress_bits[id >> 5] >> (id & 31) & 1u) return false;
-  for (int i = 0; i < r.n_blank; ++i)
-    if (id == r.blank[i]) return false;
+  if (r.n_blank && (id == r.blank[0] || id == r.blank[1] || id == r.blank[2] || id == r.blank[3])) return false;
   if (!r.use_ts_rules) return true;
   if (id == r.no_ts_id) return false;
   if (id >= r.tb) {
@@ -105,13 +105,27 @@ sample_topk_kernel(const float* __restrict__ logits, int ld, int V, const int* _
     for (int i = 0; i < 4; ++i) r.blank[i] = tt.blank[i];
   }
 
-  // pass A: (max, sumexp) of the allowed text ids and of the allowed timestamp ids
+  // pass A: (max, sumexp) of the allowed text ids and of the allowed timestamp ids.
+  // Loads are issued SU at a time, unconditionally, so the L2 latency is paid once per batch, not per element.
   float tm = -INFINITY, tsum = 0.f, sm = -INFINITY, ssum = 0.f;
-  for (int id = threadIdx.x; id < V; id += ST) {
-    if (!allowed(r, id)) continue;
-    const float v = x[id];
-    if (id < tb) ms_merge(tm, tsum, v, 1.f);
-    else ms_merge(sm, ssum, v, 1.f);
+  for (int base = 0; base < V; base += ST * SU) {
+    float xv[SU];
+#pragma unroll
+    for (int u = 0; u < SU; ++u) {
+      const int id = base + u * ST + threadIdx.x;
+      xv[u] = (id < V) ? x[id] : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < SU; ++u) {
+      const int id = base + u * ST + threadIdx.x;
+      if (id >= V || !allowed(r, id)) continue;
+      const float v = xv[u];
+      if (id < tb) {
+        if (v > tm) { tsum = tsum * __expf(tm - v) + 1.f; tm = v; } else tsum += __expf(v - tm);
+      } else {
+        if (v > sm) { ssum = ssum * __expf(sm - v) + 1.f; sm = v; } else ssum += __expf(v - sm);
+      }
+    }
   }
   block_ms(tm, tsum, sh_m, sh_s);
   block_ms(sm, ssum, sh_m, sh_s);
@@ -131,11 +145,20 @@ sample_topk_kernel(const float* __restrict__ logits, int ld, int V, const int* _
 #pragma unroll
   for (int i = 0; i < kMaxCand; ++i) { v[i] = -INFINITY; ix[i] = INT_MAX; }
   const int K = rs.greedy[q] ? 1 : rs.n_beam[q] + 1;
-  for (int id = threadIdx.x; id < V; id += ST) {
-    if (mask_text && id < tb) continue;
-    if (!allowed(r, id)) continue;
-    const float val = x[id];
-    if (val > v[kMaxCand - 1]) {
+  for (int base = 0; base < V; base += ST * SU) {
+    float xv[SU];
+#pragma unroll
+    for (int u = 0; u < SU; ++u) {
+      const int id = base + u * ST + threadIdx.x;
+      xv[u] = (id < V) ? x[id] : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < SU; ++u) {
+      const int id = base + u * ST + threadIdx.x;
+      const float val = xv[u];
+      if (id >= V || !(val > v[kMaxCand - 1])) continue;  // cheap reject first: almost every element
+      if (mask_text && id < tb) continue;
+      if (!allowed(r, id)) continue;
       v[kMaxCand - 1] = val; ix[kMaxCand - 1] = id;
 #pragma unroll
       for (int i = kMaxCand - 1; i > 0; --i) {
