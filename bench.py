@@ -63,6 +63,16 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic(sessions: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed ncu --set full
+    capture (profiles/r1_xattn_mma_ncu_full.txt); only valid for the captured configuration (128 sessions)."""
+    path = os.path.join(ROOT, "profiles", "r1_xattn_mma_traffic.json")
+    if sessions == 128 and os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)["dram_bytes_per_launch"]
+    return None
+
+
 def window_lengths(rank: int, sessions: int):
     rng = np.random.default_rng(4242 + rank)
     return [float(np.round(rng.uniform(2.0, 10.0), 2)) for _ in range(sessions)]
@@ -311,8 +321,9 @@ def run_b200(args):
                 "ms_per_step": 1e3 * e2e_total / args.steps, "p95_partial_latency_s": p95, "host_threads": S},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "dec_cross_attention_kernel<bf16,1>", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
-                     "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None, "ms_per_launch": xa_ms,
+        "roofline": {"kernel": "dec_cross_attention_mma_kernel (decoder cross-attention over the cached encoder K/V)", "bound": "hbm",
+                     "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                     "traffic": ncu_traffic(S), "ms_per_launch": xa_ms,
                      "algorithmic_bytes_per_launch": xa_bytes},
         "stages": stages,
     }

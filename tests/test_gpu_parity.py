@@ -201,3 +201,24 @@ def test_errors_and_edge_cases():
         B200WhisperBackend(b.model_size, "cpu", "float32")
     with pytest.raises(ValueError):
         b.transcribe(synth_audio(1, 1.0), dict(REALTIME, language="xx"))
+
+
+@pytest.mark.parametrize("name", ["tiny.en", "base"])
+def test_real_model_sizes(name):
+    """BASELINE.json configs[0]/[1] architectures at full size (random init): encoder rel-L2 in bf16, token-exact
+    transcribe in the fp32 validation mode, bf16 logits close to the oracle."""
+    model = oracle_model(name)
+    audio = synth_audio(42, 6.0)
+    mel = wo.pad_or_trim(wo.log_mel_spectrogram(audio, model.dims.n_mels, padding=480000), 3000)
+    xa = model.encode(mel[None])
+    b16 = backend(name, "bfloat16")
+    r = rel_l2(b16.engine.encode(mel.numpy()), xa.numpy())
+    assert r <= 1e-2, f"{name}: encoder rel-L2 {r}"
+    lay = model.layout
+    toks = list(lay.sot_sequence("en", "transcribe")) + [lay.timestamp_begin, 500, 900, 12000]
+    ref = model.decode(torch.tensor([toks]), xa)[0].numpy()
+    r = rel_l2(b16.engine.decode_logits(mel.numpy(), toks), ref)
+    assert r <= 3e-2, f"{name}: bf16 logits rel-L2 {r}"
+    b32 = backend(name, "float32")
+    _check_transcribe(b32, name, audio, dict(REALTIME, language="en"))
+    _check_transcribe(b32, name, audio, dict(ACCURATE, language="en"))
