@@ -207,7 +207,7 @@ def run_reference(args):
     ms = 1e3 * float(np.mean(times))
     value = seconds / (ms / 1e3)
     sample = f"1 session x 1 partial window ({seconds:.0f} s audio -> full 30 s encoder pass + 224 decoder steps) per step"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "RTFx (audio-seconds transcribed per second)", "value": value, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic audio, random-init weights",
@@ -332,13 +332,25 @@ def run_b200(args):
         out["cpu_baseline"] = {"value": 6.0 / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
                                "sample": "1 session x 1 partial window (6 s audio, full 30 s encoder pass + 224 decoder steps), "
                                          f"fp32 torch on {cores} threads, {dt:.1f} s"}
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str) -> None:
+    """The ONE JSON line goes to the real stdout; everything else a library prints (NCCL banner, ...) went to stderr."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the duration of the run
     if args.impl == "reference":
         run_reference(args)
     else:

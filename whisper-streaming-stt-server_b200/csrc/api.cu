@@ -13,7 +13,7 @@ void engine_load_tensor(bw_engine* e, const bw_tensor_desc& t);
 void engine_encoder_forward(bw_engine* e, int nb);
 void engine_cross_kv(bw_engine* e, int bi, int q);
 void engine_window_to_A1(bw_engine* e, const float* logmel, int ld, int n_real, const int* gmax, int seek, int seg, int bi);
-void engine_decoder_layers(bw_engine* e, int R, int n_groups, int max_group_rows, int n_lrows, const int* row_seq,
+void engine_decoder_layers(bw_engine* e, DecGroup& G, int R, int n_groups, int max_group_rows, int n_lrows, const int* row_seq,
                            const int* row_pos, const int* row_tok, const int* row_bpos, const int* grp_first, const int* grp_n,
                            const int* grp_x, const int* lrow_src);
 void engine_init_requests(bw_engine* e, const int* init_dev, int n);
@@ -53,22 +53,53 @@ void finish_request(Request* r, int status, const std::string& err) {
   r->cv.notify_all();
 }
 
-// ---- control-block layout (ints) ----
+// ---- per-group control block (ints), mirrored host (pinned) / device ----
 struct Ctl {
   int *row_seq, *row_pos, *row_tok, *row_bpos, *grp_first, *grp_n, *grp_x, *lrow_src, *srow_lrow, *srow_req, *srow_seq, *act_req,
-      *act_first, *ns_lrow, *ns_req, *init;
-  size_t total;
-  void layout(int* base, int R, int LR, int Q) {
-    int* p = base;
+      *act_first, *ns_lrow, *ns_req;
+  int* base = nullptr;
+  size_t total = 0;
+  // fill counters of the step being built
+  int R = 0, NG = 0, LR = 0, SR = 0, NA = 0, NNS = 0, max_grp = 1;
+  void layout(int* b, int Rm, int LRm, int Q) {
+    base = b;
+    int* p = b;
     auto take = [&](size_t n) { int* r = p; p += n; return r; };
-    row_seq = take(R); row_pos = take(R); row_tok = take(R); row_bpos = take(R);
-    grp_first = take(R); grp_n = take(R); grp_x = take(R);
-    lrow_src = take(LR); srow_lrow = take(LR); srow_req = take(LR); srow_seq = take(LR);
+    row_seq = take(Rm); row_pos = take(Rm); row_tok = take(Rm); row_bpos = take(Rm);
+    grp_first = take(Rm); grp_n = take(Rm); grp_x = take(Rm);
+    lrow_src = take(LRm); srow_lrow = take(LRm); srow_req = take(LRm); srow_seq = take(LRm);
     act_req = take(Q); act_first = take(Q); ns_lrow = take(Q); ns_req = take(Q);
-    init = take((size_t)Q * 12);
-    total = (size_t)(p - base);
+    total = (size_t)(p - b);
   }
+  void reset() { R = NG = LR = SR = NA = NNS = 0; max_grp = 1; }
 };
+
+// H2D of the control block + the whole decoder step (all layers, logits, filters/top-k, beam update) of one group,
+// enqueued on the group's stream.  No host synchronisation here.
+void enqueue_group_step(bw_engine* e, DecGroup& G, Ctl& c) {
+  if (c.R == 0) return;
+  int* dbase = G.d_ctrl.as<int>();
+  auto dev = [&](int* h) { return dbase + (h - c.base); };
+  BW_CUDA(cudaMemcpyAsync(dbase, c.base, c.total * 4, cudaMemcpyHostToDevice, G.stream));
+  e->stat_h2d += (long long)c.total * 4;
+  engine_decoder_layers(e, G, c.R, c.NG, c.max_grp, c.LR, dev(c.row_seq), dev(c.row_pos), dev(c.row_tok), dev(c.row_bpos),
+                        dev(c.grp_first), dev(c.grp_n), dev(c.grp_x), dev(c.lrow_src));
+  const float* logits = G.d_logits.as<float>();
+  const int V = e->dims.n_vocab;
+  static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;
+  PdlScope pdl(use_pdl && !e->fp32);
+  no_speech_prob(logits, V, V, dev(c.ns_lrow), dev(c.ns_req), c.NNS, e->tt.no_speech, e->rs.no_speech_prob, G.stream);
+  sample_topk(logits, V, V, dev(c.srow_lrow), dev(c.srow_req), dev(c.srow_seq), c.SR, e->tt, e->rs, e->ss, e->anc_cur,
+              G.d_cand_tok.as<int>(), G.d_cand_lp.as<float>(), G.stream);
+  beam_update(dev(c.act_req), dev(c.act_first), c.NA, e->tt, e->rs, e->ss, e->anc_cur, e->dims.n_text_ctx, G.d_cand_tok.as<int>(),
+              G.d_cand_lp.as<float>(), G.stream);
+}
+
+int choose_groups(int n_segments) {
+  static const int forced = getenv("B200W_GROUPS") ? atoi(getenv("B200W_GROUPS")) : 0;
+  if (forced > 0) return std::min(forced, (int)kMaxGroups);
+  return std::max(1, std::min((int)kMaxGroups, n_segments / 24));
+}
 
 void release_slots(bw_engine* e, Request* r) {
   if (r->q >= 0) e->free_q.push_back(r->q);
@@ -171,7 +202,7 @@ void fail_all(bw_engine* e, std::vector<Request*>& fresh, const std::string& msg
   e->live.clear();
 }
 
-void admit_batch(bw_engine* e, std::vector<Request*>& fresh, Ctl& ctl) {
+void admit_batch(bw_engine* e, std::vector<Request*>& fresh) {
   const auto& d = e->dims;
   const int nb = (int)fresh.size();
   for (int i = 0; i < nb; ++i) {
@@ -195,7 +226,7 @@ void admit_batch(bw_engine* e, std::vector<Request*>& fresh, Ctl& ctl) {
   for (int i = 0; i < nb; ++i) engine_cross_kv(e, i, fresh[i]->q);
   for (int i = 0; i < nb; ++i) {
     Request* r = fresh[i];
-    int* rec = ctl.init + i * 12;
+    int* rec = e->h_init + i * 12;
     const int n_init = (int)r->initial.size();
     rec[0] = r->q; rec[1] = r->G; rec[2] = r->greedy; rec[3] = n_init; rec[4] = n_init; rec[5] = r->first_seq;
     rec[6] = r->without_ts; rec[7] = r->suppress_blank; rec[8] = r->max_initial_ts;
@@ -205,8 +236,8 @@ void admit_batch(bw_engine* e, std::vector<Request*>& fresh, Ctl& ctl) {
     r->steps = 0;
     r->prefilled = false;
   }
-  int* init_dev = e->d_ctrl.as<int>() + (ctl.init - e->h_ctrl);
-  BW_CUDA(cudaMemcpyAsync(init_dev, ctl.init, (size_t)nb * 12 * 4, cudaMemcpyHostToDevice, e->stream));
+  int* init_dev = e->d_init.as<int>();
+  BW_CUDA(cudaMemcpyAsync(init_dev, e->h_init, (size_t)nb * 12 * 4, cudaMemcpyHostToDevice, e->stream));
   engine_init_requests(e, init_dev, nb);
   // the pinned control block is rewritten by the next step: make sure the copy has been consumed
   BW_CUDA(cudaStreamSynchronize(e->stream));
@@ -217,12 +248,17 @@ void admit_batch(bw_engine* e, std::vector<Request*>& fresh, Ctl& ctl) {
   fresh.clear();
 }
 
-void decode_step(bw_engine* e, Ctl& ctl) {
+void decode_step(bw_engine* e, Ctl* ctls) {
   const auto& d = e->dims;
-  int R = 0, NG = 0, LR = 0, SR = 0, NA = 0, NNS = 0, max_grp = 1;
-  struct Special { Request* r; int lrow0; int n; };
+  struct Special { Request* r; int grp; int lrow0; int n; };
   std::vector<Special> lang_reqs, logit_reqs;
+  const int ng = choose_groups((int)e->live.size());
+  for (int g = 0; g < ng; ++g) ctls[g].reset();
   for (Request* r : e->live) {
+    int gi = 0;  // least-loaded group (rows)
+    for (int g = 1; g < ng; ++g) if (ctls[g].R < ctls[gi].R) gi = g;
+    Ctl& ctl = ctls[gi];
+    int &R = ctl.R, &NG = ctl.NG, &LR = ctl.LR, &SR = ctl.SR, &NA = ctl.NA, &NNS = ctl.NNS, &max_grp = ctl.max_grp;
     if (!r->prefilled) {
       const int n_init = (int)r->initial.size();
       const int row0 = R;
@@ -237,10 +273,10 @@ void decode_step(bw_engine* e, Ctl& ctl) {
       }
       if (r->kind == REQ_LANG) {
         ctl.lrow_src[LR] = row0;
-        lang_reqs.push_back({r, LR, 1});
+        lang_reqs.push_back({r, gi, LR, 1});
         ++LR;
       } else if (r->kind == REQ_LOGITS) {
-        logit_reqs.push_back({r, LR, n_init});
+        logit_reqs.push_back({r, gi, LR, n_init});
         for (int t = 0; t < n_init; ++t) ctl.lrow_src[LR++] = row0 + t;
       } else {
         const int last_row = row0 + n_init - 1;
@@ -268,38 +304,28 @@ void decode_step(bw_engine* e, Ctl& ctl) {
       }
     }
   }
-  int* dbase = e->d_ctrl.as<int>();
-  auto dev = [&](int* h) { return dbase + (h - e->h_ctrl); };
-  const size_t used = (size_t)(ctl.init - e->h_ctrl);
-  BW_CUDA(cudaMemcpyAsync(dbase, e->h_ctrl, used * 4, cudaMemcpyHostToDevice, e->stream));
-  e->stat_h2d += (long long)used * 4;
-  engine_decoder_layers(e, R, NG, max_grp, LR, dev(ctl.row_seq), dev(ctl.row_pos), dev(ctl.row_tok), dev(ctl.row_bpos), dev(ctl.grp_first),
-                        dev(ctl.grp_n), dev(ctl.grp_x), dev(ctl.lrow_src));
-  const float* logits = e->d_logits.as<float>();
+  int total_rows = 0;
+  for (int g = 0; g < ng; ++g) { enqueue_group_step(e, e->grp[g], ctls[g]); total_rows += ctls[g].R; }
   const int V = d.n_vocab;
-  static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;
-  PdlScope pdl(use_pdl && !e->fp32);
-  no_speech_prob(logits, V, V, dev(ctl.ns_lrow), dev(ctl.ns_req), NNS, e->tt.no_speech, e->rs.no_speech_prob, e->stream);
-  sample_topk(logits, V, V, dev(ctl.srow_lrow), dev(ctl.srow_req), dev(ctl.srow_seq), SR, e->tt, e->rs, e->ss, e->anc_cur,
-              e->d_cand_tok.as<int>(), e->d_cand_lp.as<float>(), e->stream);
-  beam_update(dev(ctl.act_req), dev(ctl.act_first), NA, e->tt, e->rs, e->ss, e->anc_cur, d.n_text_ctx, e->d_cand_tok.as<int>(),
-              e->d_cand_lp.as<float>(), e->stream);
   for (auto& s : lang_reqs) {
-    language_probs(logits + (size_t)s.lrow0 * V, V, e->tt.first_language_token, e->tt.num_languages,
-                   e->d_lang_probs.as<float>(), e->d_lang_arg.as<int>(), e->stream);
-    BW_CUDA(cudaMemcpyAsync(s.r->lang_out->probs, e->d_lang_probs.p, (size_t)e->tt.num_languages * 4, cudaMemcpyDeviceToHost, e->stream));
-    BW_CUDA(cudaMemcpyAsync(&s.r->lang_out->language_token, e->d_lang_arg.p, 4, cudaMemcpyDeviceToHost, e->stream));
-    BW_CUDA(cudaStreamSynchronize(e->stream));
+    DecGroup& G = e->grp[s.grp];
+    language_probs(G.d_logits.as<float>() + (size_t)s.lrow0 * V, V, e->tt.first_language_token, e->tt.num_languages,
+                   e->d_lang_probs.as<float>(), e->d_lang_arg.as<int>(), G.stream);
+    BW_CUDA(cudaMemcpyAsync(s.r->lang_out->probs, e->d_lang_probs.p, (size_t)e->tt.num_languages * 4, cudaMemcpyDeviceToHost, G.stream));
+    BW_CUDA(cudaMemcpyAsync(&s.r->lang_out->language_token, e->d_lang_arg.p, 4, cudaMemcpyDeviceToHost, G.stream));
+    BW_CUDA(cudaStreamSynchronize(G.stream));
     s.r->lang_out->n_languages = e->tt.num_languages;
   }
   for (auto& s : logit_reqs)
-    BW_CUDA(cudaMemcpyAsync(s.r->logits_out, logits + (size_t)s.lrow0 * V, (size_t)s.n * V * 4, cudaMemcpyDeviceToHost, e->stream));
+    BW_CUDA(cudaMemcpyAsync(s.r->logits_out, e->grp[s.grp].d_logits.as<float>() + (size_t)s.lrow0 * V, (size_t)s.n * V * 4,
+                            cudaMemcpyDeviceToHost, e->grp[s.grp].stream));
+  for (int g = 0; g < ng; ++g) BW_CUDA(cudaStreamSynchronize(e->grp[g].stream));
   BW_CUDA(cudaMemcpyAsync(e->h_flags, e->rs.completed, (size_t)e->Q * 4, cudaMemcpyDeviceToHost, e->stream));
   BW_CUDA(cudaStreamSynchronize(e->stream));
   e->stat_d2h += (long long)e->Q * 4;
   e->anc_cur ^= 1;
   e->stat_steps += 1;
-  e->stat_rows += R;
+  e->stat_rows += total_rows;
 
   // bookkeeping + completion
   std::vector<Request*> still, done;
@@ -355,8 +381,8 @@ void decode_step(bw_engine* e, Ctl& ctl) {
 
 void scheduler_main(bw_engine* e) {
   cudaSetDevice(e->device);
-  Ctl ctl;
-  ctl.layout(e->h_ctrl, e->R_max, e->LR_max, e->Q);
+  Ctl ctls[kMaxGroups];
+  for (int g = 0; g < kMaxGroups; ++g) ctls[g].layout(e->grp[g].h_ctrl, e->R_max, e->LR_max, e->Q);
   const char* wenv = getenv("B200W_BATCH_WINDOW_US");
   const int window_us = wenv ? atoi(wenv) : 300;
   for (;;) {
@@ -396,8 +422,8 @@ void scheduler_main(bw_engine* e) {
     }
     try {
       std::lock_guard<std::mutex> g(e->gpu_mu);
-      if (!fresh.empty()) admit_batch(e, fresh, ctl);
-      if (!e->live.empty()) decode_step(e, ctl);
+      if (!fresh.empty()) admit_batch(e, fresh);
+      if (!e->live.empty()) decode_step(e, ctls);
     } catch (const std::exception& ex) {
       std::lock_guard<std::mutex> g(e->q_mu);
       fail_all(e, fresh, ex.what(), BW_ERR_CUDA);
@@ -599,15 +625,20 @@ int bw_engine_finalize(bw_engine* e) {
   e->enc_out.alloc((size_t)Be * 1500 * dm * ts);
   // decoder activations
   const size_t R = e->R_max, LR = e->LR_max;
-  e->d_x.alloc(R * dm * 4);
-  e->d_xn.alloc(R * dm * ts); e->d_qkv.alloc(R * 3 * dm * 4); e->d_att.alloc(R * dm * ts); e->d_q.alloc(R * dm * 4);
-  e->d_h.alloc(R * 4 * dm * ts); e->d_lnrows.alloc(LR * dm * ts);
-  e->d_logits.alloc(LR * (size_t)d.n_vocab * 4);
-  e->d_ws.alloc(dec_cross_workspace_floats((int)R, d.n_text_head) * 4);
-  e->d_cand_tok.alloc(LR * kMaxCand * 4); e->d_cand_lp.alloc(LR * kMaxCand * 4);
+  for (int gi = 0; gi < kMaxGroups; ++gi) {
+    DecGroup& G = e->grp[gi];
+    BW_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+    G.d_x.alloc(R * dm * 4);
+    G.d_xn.alloc(R * dm * ts); G.d_qkv.alloc(R * 3 * dm * 4); G.d_att.alloc(R * dm * ts); G.d_q.alloc(R * dm * 4);
+    G.d_h.alloc(R * 4 * dm * ts); G.d_lnrows.alloc(LR * dm * ts);
+    G.d_logits.alloc(LR * (size_t)d.n_vocab * 4);
+    G.d_ws.alloc(dec_cross_workspace_floats((int)R, d.n_text_head) * 4);
+    G.d_cand_tok.alloc(LR * kMaxCand * 4); G.d_cand_lp.alloc(LR * kMaxCand * 4);
+    // rows past the live count are read (and discarded) by the GEMMs' TMA boxes: keep them finite
+    for (DevBuf* b : {&G.d_xn, &G.d_qkv, &G.d_att, &G.d_q, &G.d_h, &G.d_lnrows}) BW_CUDA(cudaMemset(b->p, 0, b->bytes));
+  }
   e->d_lang_probs.alloc(128 * 4); e->d_lang_arg.alloc(4);
-  // zero the GEMM operand buffers once: rows past the live count are read (and discarded) by the swap-AB GEMMs
-  for (DevBuf* b : {&e->d_xn, &e->d_qkv, &e->d_att, &e->d_q, &e->d_h, &e->d_lnrows, &e->self_pool}) BW_CUDA(cudaMemset(b->p, 0, b->bytes));
+  BW_CUDA(cudaMemset(e->self_pool.p, 0, e->self_pool.bytes));
   // decoder state
   const size_t n_ctx = d.n_text_ctx;
   e->st_int.alloc(((size_t)Q * 11 + (size_t)Q * kMaxFinished * 2 + (size_t)S * 4) * 4);
@@ -632,13 +663,17 @@ int bw_engine_finalize(bw_engine* e) {
     ss.anc[0] = e->st_anc0.as<unsigned char>(); ss.anc[1] = e->st_anc1.as<unsigned char>();
     rs.tok = e->st_tok.as<int>(); rs.parent = e->st_parent.as<unsigned char>();
   }
-  // control block
+  // control blocks (one per group) + admission records
   {
     Ctl probe;
     probe.layout(nullptr, e->R_max, e->LR_max, Q);
     e->ctrl_ints = probe.total;
-    BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_ctrl), e->ctrl_ints * 4));
-    e->d_ctrl.alloc(e->ctrl_ints * 4);
+    for (int gi = 0; gi < kMaxGroups; ++gi) {
+      BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->grp[gi].h_ctrl), e->ctrl_ints * 4));
+      e->grp[gi].d_ctrl.alloc(e->ctrl_ints * 4);
+    }
+    BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_init), (size_t)Q * 12 * 4));
+    e->d_init.alloc((size_t)Q * 12 * 4);
     BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_flags), (size_t)Q * 4));
     e->h_fin_bytes = fin_blob_bytes(e) * (size_t)Q;
     BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_fin), e->h_fin_bytes));
@@ -683,7 +718,8 @@ int bw_engine_destroy(bw_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   for (auto& b : e->call_pool) { cudaFree(b.pcm); cudaFree(b.logmel); cudaFree(b.gmax); }
-  if (e->h_ctrl) cudaFreeHost(e->h_ctrl);
+  for (auto& G : e->grp) { if (G.h_ctrl) cudaFreeHost(G.h_ctrl); if (G.stream) cudaStreamDestroy(G.stream); }
+  if (e->h_init) cudaFreeHost(e->h_init);
   if (e->h_flags) cudaFreeHost(e->h_flags);
   if (e->h_fin) cudaFreeHost(e->h_fin);
   for (auto& s : e->front) if (s) cudaStreamDestroy(s);
@@ -962,44 +998,41 @@ int bw_bench_encoder(bw_engine* e, int32_t batch, int32_t iters, float* ms_out, 
 namespace {
 // Synthetic resident decode: `n_segments` windows x `n_group` hypotheses, positions [start_len, start_len + n_steps).
 // Same launches, control upload and per-step completion read-back as the scheduler's decode_step().
-void synthetic_init(bw_engine* e, Ctl& ctl, int n_segments, int n_group, int start_len) {
+void synthetic_init(bw_engine* e, int n_segments, int n_group, int start_len) {
   for (int i = 0; i < n_segments; ++i) {
-    int* rec = ctl.init + i * 12;
+    int* rec = e->h_init + i * 12;
     rec[0] = i; rec[1] = n_group; rec[2] = 0; rec[3] = 3; rec[4] = start_len; rec[5] = i * n_group; rec[6] = 0; rec[7] = 1;
     rec[8] = 50; rec[9] = kMaxFinished; rec[10] = e->tt.timestamp_begin - 1000; rec[11] = 0;
   }
-  int* init_dev = e->d_ctrl.as<int>() + (ctl.init - e->h_ctrl);
-  BW_CUDA(cudaMemcpyAsync(init_dev, ctl.init, (size_t)n_segments * 48, cudaMemcpyHostToDevice, e->stream));
-  engine_init_requests(e, init_dev, n_segments);
+  BW_CUDA(cudaMemcpyAsync(e->d_init.p, e->h_init, (size_t)n_segments * 48, cudaMemcpyHostToDevice, e->stream));
+  engine_init_requests(e, e->d_init.as<int>(), n_segments);
   BW_CUDA(cudaStreamSynchronize(e->stream));
 }
-void synthetic_step(bw_engine* e, Ctl& ctl, int n_segments, int n_group, int cur) {
-  int R = 0, SR = 0;
+// same grouping, launches, control upload and per-step completion read-back as the scheduler's decode_step()
+void synthetic_step(bw_engine* e, Ctl* ctls, int n_segments, int n_group, int cur) {
+  const int ng = choose_groups(n_segments);
+  for (int g = 0; g < ng; ++g) ctls[g].reset();
   for (int i = 0; i < n_segments; ++i) {
-    ctl.grp_first[i] = R; ctl.grp_n[i] = n_group; ctl.grp_x[i] = i;
-    ctl.act_req[i] = i; ctl.act_first[i] = SR;
+    Ctl& c = ctls[i % ng];
+    c.grp_first[c.NG] = c.R; c.grp_n[c.NG] = n_group; c.grp_x[c.NG] = i; ++c.NG;
+    c.max_grp = std::max(c.max_grp, n_group);
+    c.act_req[c.NA] = i; c.act_first[c.NA] = c.SR; ++c.NA;
     for (int j = 0; j < n_group; ++j) {
-      ctl.row_seq[R] = i * n_group + j; ctl.row_pos[R] = cur - 1; ctl.row_tok[R] = -1; ctl.row_bpos[R] = cur - 1;
-      ctl.lrow_src[R] = R; ctl.srow_lrow[SR] = R; ctl.srow_req[SR] = i; ctl.srow_seq[SR] = i * n_group + j;
-      ++R; ++SR;
+      c.row_seq[c.R] = i * n_group + j; c.row_pos[c.R] = cur - 1; c.row_tok[c.R] = -1; c.row_bpos[c.R] = cur - 1;
+      c.lrow_src[c.LR] = c.R; c.srow_lrow[c.SR] = c.LR; c.srow_req[c.SR] = i; c.srow_seq[c.SR] = i * n_group + j;
+      ++c.R; ++c.LR; ++c.SR;
     }
   }
-  int* dbase = e->d_ctrl.as<int>();
-  auto dev = [&](int* h) { return dbase + (h - e->h_ctrl); };
-  BW_CUDA(cudaMemcpyAsync(dbase, e->h_ctrl, (size_t)(ctl.init - e->h_ctrl) * 4, cudaMemcpyHostToDevice, e->stream));
-  engine_decoder_layers(e, R, n_segments, n_group, R, dev(ctl.row_seq), dev(ctl.row_pos), dev(ctl.row_tok), dev(ctl.row_bpos), dev(ctl.grp_first),
-                        dev(ctl.grp_n), dev(ctl.grp_x), dev(ctl.lrow_src));
-  const int V = e->dims.n_vocab;
-  static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;
-  PdlScope pdl(use_pdl && !e->fp32);
-  sample_topk(e->d_logits.as<float>(), V, V, dev(ctl.srow_lrow), dev(ctl.srow_req), dev(ctl.srow_seq), SR, e->tt, e->rs, e->ss,
-              e->anc_cur, e->d_cand_tok.as<int>(), e->d_cand_lp.as<float>(), e->stream);
-  beam_update(dev(ctl.act_req), dev(ctl.act_first), n_segments, e->tt, e->rs, e->ss, e->anc_cur, e->dims.n_text_ctx,
-              e->d_cand_tok.as<int>(), e->d_cand_lp.as<float>(), e->stream);
+  for (int g = 0; g < ng; ++g) enqueue_group_step(e, e->grp[g], ctls[g]);
+  for (int g = 0; g < ng; ++g) BW_CUDA(cudaStreamSynchronize(e->grp[g].stream));
   BW_CUDA(cudaMemcpyAsync(e->h_flags, e->rs.completed, (size_t)e->Q * 4, cudaMemcpyDeviceToHost, e->stream));
   BW_CUDA(cudaStreamSynchronize(e->stream));
   e->anc_cur ^= 1;
 }
+struct SynCtls {
+  Ctl c[kMaxGroups];
+  explicit SynCtls(bw_engine* e) { for (int g = 0; g < kMaxGroups; ++g) c[g].layout(e->grp[g].h_ctrl, e->R_max, e->LR_max, e->Q); }
+};
 }  // namespace
 
 // One full decoder step (all layers + logits + sampling + beam update) over `n_segments` resident
@@ -1014,15 +1047,14 @@ int bw_bench_decoder_step(bw_engine* e, int32_t n_segments, int32_t n_group, int
   DeviceGuard dg(e->device);
   std::lock_guard<std::mutex> g(e->gpu_mu);
   BW_CHECK(e->live.empty(), "engine busy");
-  Ctl ctl;
-  ctl.layout(e->h_ctrl, e->R_max, e->LR_max, e->Q);
+  SynCtls sc(e);
   BW_CUDA(cudaMemsetAsync(e->cross_cache.p, 0, (size_t)n_segments * (e->cross_cache.bytes / e->Q), e->stream));
-  synthetic_init(e, ctl, n_segments, n_group, context_len);
+  synthetic_init(e, n_segments, n_group, context_len);
   int cur = context_len;
-  synthetic_step(e, ctl, n_segments, n_group, cur++);
-  EvTimer t(e->stream);
+  synthetic_step(e, sc.c, n_segments, n_group, cur++);
+  EvTimer t(e->stream);  // e->stream is idle here and receives the completion read-back of every step
   t.start();
-  for (int i = 0; i < iters; ++i) synthetic_step(e, ctl, n_segments, n_group, cur++);
+  for (int i = 0; i < iters; ++i) synthetic_step(e, sc.c, n_segments, n_group, cur++);
   *ms_out = t.stop_ms() / iters;
   const double ts = e->fp32 ? 4 : 2, d = e->dims.n_text_state, L = e->dims.n_text_layer, V = e->dims.n_vocab;
   const double S = (double)n_segments * n_group;
@@ -1053,8 +1085,7 @@ int bw_bench_pipeline(bw_engine* e, const float* pcm_host, const int64_t* offset
   for (int i = 0; i < n_segments; ++i)
     BW_CUDA(cudaMemcpyAsync(bufs[i].pcm, pcm_host + offsets[i], (size_t)lengths[i] * 4, cudaMemcpyHostToDevice, e->stream));
   BW_CUDA(cudaStreamSynchronize(e->stream));
-  Ctl ctl;
-  ctl.layout(e->h_ctrl, e->R_max, e->LR_max, e->Q);
+  SynCtls sc(e);
   auto frames = [&](int i, int& total, int& n_real, int& seg) {
     total = (int)((lengths[i] + 480000) / 160);
     n_real = (int)std::min<long long>(total, (lengths[i] + 200 + 159) / 160);
@@ -1078,8 +1109,8 @@ int bw_bench_pipeline(bw_engine* e, const float* pcm_host, const int64_t* offset
     engine_encoder_forward(e, nb);
     for (int i = 0; i < nb; ++i) engine_cross_kv(e, i, s0 + i);
   }
-  synthetic_init(e, ctl, n_segments, n_group, 3);
-  for (int i = 0; i < n_steps; ++i) synthetic_step(e, ctl, n_segments, n_group, 3 + i);
+  synthetic_init(e, n_segments, n_group, 3);
+  for (int i = 0; i < n_steps; ++i) synthetic_step(e, sc.c, n_segments, n_group, 3 + i);
   *ms_out = t.stop_ms();
   {
     std::lock_guard<std::mutex> cg(e->call_mu);
@@ -1096,28 +1127,26 @@ int bw_bench_cross_attention(bw_engine* e, int32_t n_segments, int32_t n_group, 
   BW_CHECK(n_segments * n_group <= e->R_max, "too many rows");
   DeviceGuard dg(e->device);
   std::lock_guard<std::mutex> g(e->gpu_mu);
-  Ctl ctl;
-  ctl.layout(e->h_ctrl, e->R_max, e->LR_max, e->Q);
+  SynCtls sc(e);
+  Ctl& ctl = sc.c[0];
+  DecGroup& G = e->grp[0];
   for (int i = 0; i < n_segments; ++i) { ctl.grp_first[i] = i * n_group; ctl.grp_n[i] = n_group; ctl.grp_x[i] = i; }
-  int* dbase = e->d_ctrl.as<int>();
-  auto dev = [&](int* h) { return dbase + (h - e->h_ctrl); };
-  BW_CUDA(cudaMemcpyAsync(dbase, e->h_ctrl, (size_t)(ctl.init - e->h_ctrl) * 4, cudaMemcpyHostToDevice, e->stream));
+  int* dbase = G.d_ctrl.as<int>();
+  auto dev = [&](int* h) { return dbase + (h - ctl.base); };
+  BW_CUDA(cudaMemcpyAsync(dbase, ctl.base, ctl.total * 4, cudaMemcpyHostToDevice, e->stream));
   BW_CUDA(cudaMemsetAsync(e->cross_cache.p, 0, (size_t)n_segments * (e->cross_cache.bytes / e->Q), e->stream));
   const auto& d = e->dims;
   const int dm = d.n_text_state, L = d.n_text_layer;
   const int R = n_segments * n_group;
   auto run = [&](int layer) {
-    if (e->fp32) {
-      CrossKV x; x.cache = e->cross_cache.p; x.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; x.T_enc = d.n_audio_ctx;
-      x.n_slots = e->Q; x.n_layer = L;
-      dec_cross_attention<float>(dev(ctl.grp_first), dev(ctl.grp_n), dev(ctl.grp_x), n_segments, n_group, R, e->d_q.as<float>(), x, layer, dm,
-                                 d.n_text_head, e->d_att.as<float>(), e->d_ws.as<float>(), e->stream);
-    } else {
-      CrossKV x; x.cache = e->cross_cache.p; x.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; x.T_enc = d.n_audio_ctx;
-      x.n_slots = e->Q; x.n_layer = L;
-      dec_cross_attention<bf16>(dev(ctl.grp_first), dev(ctl.grp_n), dev(ctl.grp_x), n_segments, n_group, R, e->d_q.as<float>(), x, layer, dm,
-                                d.n_text_head, e->d_att.as<bf16>(), e->d_ws.as<float>(), e->stream);
-    }
+    CrossKV x; x.cache = e->cross_cache.p; x.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; x.T_enc = d.n_audio_ctx;
+    x.n_slots = e->Q; x.n_layer = L;
+    if (e->fp32)
+      dec_cross_attention<float>(dev(ctl.grp_first), dev(ctl.grp_n), dev(ctl.grp_x), n_segments, n_group, R, G.d_q.as<float>(), x, layer, dm,
+                                 d.n_text_head, G.d_att.as<float>(), G.d_ws.as<float>(), e->stream);
+    else
+      dec_cross_attention<bf16>(dev(ctl.grp_first), dev(ctl.grp_n), dev(ctl.grp_x), n_segments, n_group, R, G.d_q.as<float>(), x, layer, dm,
+                                d.n_text_head, G.d_att.as<bf16>(), G.d_ws.as<float>(), e->stream);
   };
   run(0);
   EvTimer t(e->stream);

@@ -66,14 +66,15 @@ inline float half_bits_to_float(uint16_t h) {
 template <typename T>
 struct Impl {
   bw_engine* e;
-  explicit Impl(bw_engine* eng) : e(eng) {}
+  cudaStream_t stream;
+  explicit Impl(bw_engine* eng, cudaStream_t st = nullptr) : e(eng), stream(st ? st : eng->stream) {}
   const bw_model_dims& D() const { return e->dims; }
 
   void gemm(const GemmArgs& g) const {
-    if constexpr (std::is_same<T, float>::value) gemm_simt<float>(g, e->stream);
+    if constexpr (std::is_same<T, float>::value) gemm_simt<float>(g, stream);
     else {
-      if (e->force_simt) gemm_simt<bf16>(g, e->stream);
-      else gemm_tc_bf16(g, e->stream);
+      if (e->force_simt) gemm_simt<bf16>(g, stream);
+      else gemm_tc_bf16(g, stream);
     }
   }
 
@@ -173,15 +174,15 @@ struct Impl {
     int R = 0, n_groups = 0, max_group_rows = 1, n_lrows = 0;
     const int *row_seq, *row_pos, *row_tok, *row_bpos, *grp_first, *grp_n, *grp_x, *lrow_src;
   };
-  void decoder_layers(const StepCtl& c) const {
+  void decoder_layers(const StepCtl& c, DecGroup& G) const {
     static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;
     PdlScope pdl(use_pdl && !std::is_same<T, float>::value);
     const auto& d = D();
     const int dm = d.n_text_state, L = d.n_text_layer, H = d.n_text_head;
-    cudaStream_t st = e->stream;
+    cudaStream_t st = stream;
     DecRows rows;
     rows.n_rows = c.R; rows.row_seq = c.row_seq; rows.row_pos = c.row_pos; rows.row_tok = c.row_tok; rows.row_bpos = c.row_bpos;
-    float* x = e->d_x.as<float>();
+    float* x = G.d_x.as<float>();
     dec_embed<T>(rows, e->ss.next_tok, reinterpret_cast<const T*>(e->w.tok_emb), reinterpret_cast<const T*>(e->w.dec_pos), x, dm, st);
     SelfKV skv;
     skv.pool = e->self_pool.p; skv.unit_stride = (long long)L * 2 * d.n_text_ctx * dm; skv.n_ctx = d.n_text_ctx;
@@ -192,22 +193,22 @@ struct Impl {
     const int Ra = e->R_max;
     for (int l = 0; l < L; ++l) {
       const LayerW& w = e->w.dec[l];
-      layernorm<T>(x, w.ln1_g, w.ln1_b, e->d_xn.as<T>(), c.R, dm, st);
-      linear_rows(e->d_xn.as<T>(), c.R, Ra, w.wqkv, 3 * dm, dm, w.bqkv, nullptr, e->d_qkv.p, false, true);
-      dec_self_attention<T>(rows, e->d_qkv.as<float>(), skv, l, dm, H, e->d_att.as<T>(), st);
-      linear_rows(e->d_att.as<T>(), c.R, Ra, w.wo, dm, dm, w.bo, x, x, false, true);
-      layernorm<T>(x, w.lnx_g, w.lnx_b, e->d_xn.as<T>(), c.R, dm, st);
-      linear_rows(e->d_xn.as<T>(), c.R, Ra, w.wq_x, dm, dm, w.bq_x, nullptr, e->d_q.p, false, true);
-      dec_cross_attention<T>(c.grp_first, c.grp_n, c.grp_x, c.n_groups, c.max_group_rows, c.R, e->d_q.as<float>(), xkv, l, dm, H,
-                             e->d_att.as<T>(), e->d_ws.as<float>(), st);
-      linear_rows(e->d_att.as<T>(), c.R, Ra, w.wo_x, dm, dm, w.bo_x, x, x, false, true);
-      layernorm<T>(x, w.ln2_g, w.ln2_b, e->d_xn.as<T>(), c.R, dm, st);
-      linear_rows(e->d_xn.as<T>(), c.R, Ra, w.w1, 4 * dm, dm, w.b1, nullptr, e->d_h.p, true, false);
-      linear_rows(e->d_h.as<T>(), c.R, Ra, w.w2, dm, 4 * dm, w.b2, x, x, false, true);
+      layernorm<T>(x, w.ln1_g, w.ln1_b, G.d_xn.as<T>(), c.R, dm, st);
+      linear_rows(G.d_xn.as<T>(), c.R, Ra, w.wqkv, 3 * dm, dm, w.bqkv, nullptr, G.d_qkv.p, false, true);
+      dec_self_attention<T>(rows, G.d_qkv.as<float>(), skv, l, dm, H, G.d_att.as<T>(), st);
+      linear_rows(G.d_att.as<T>(), c.R, Ra, w.wo, dm, dm, w.bo, x, x, false, true);
+      layernorm<T>(x, w.lnx_g, w.lnx_b, G.d_xn.as<T>(), c.R, dm, st);
+      linear_rows(G.d_xn.as<T>(), c.R, Ra, w.wq_x, dm, dm, w.bq_x, nullptr, G.d_q.p, false, true);
+      dec_cross_attention<T>(c.grp_first, c.grp_n, c.grp_x, c.n_groups, c.max_group_rows, c.R, G.d_q.as<float>(), xkv, l, dm, H,
+                             G.d_att.as<T>(), G.d_ws.as<float>(), st);
+      linear_rows(G.d_att.as<T>(), c.R, Ra, w.wo_x, dm, dm, w.bo_x, x, x, false, true);
+      layernorm<T>(x, w.ln2_g, w.ln2_b, G.d_xn.as<T>(), c.R, dm, st);
+      linear_rows(G.d_xn.as<T>(), c.R, Ra, w.w1, 4 * dm, dm, w.b1, nullptr, G.d_h.p, true, false);
+      linear_rows(G.d_h.as<T>(), c.R, Ra, w.w2, dm, 4 * dm, w.b2, x, x, false, true);
     }
     // final LayerNorm only on the rows whose logits are needed, then the tied-embedding projection
-    layernorm_gather<T>(x, c.lrow_src, e->w.ln_g, e->w.ln_b, e->d_lnrows.as<T>(), c.n_lrows, dm, st);
-    linear_rows(e->d_lnrows.as<T>(), c.n_lrows, e->LR_max, e->w.tok_emb, d.n_vocab, dm, nullptr, nullptr, e->d_logits.p, false, true);
+    layernorm_gather<T>(x, c.lrow_src, e->w.ln_g, e->w.ln_b, G.d_lnrows.as<T>(), c.n_lrows, dm, st);
+    linear_rows(G.d_lnrows.as<T>(), c.n_lrows, e->LR_max, e->w.tok_emb, d.n_vocab, dm, nullptr, nullptr, G.d_logits.p, false, true);
   }
 
   void window_to_A1(const float* logmel, int ld, int n_real, const int* gmax, int seek, int seg, int bi) const {
@@ -354,17 +355,17 @@ void engine_window_to_A1(bw_engine* e, const float* logmel, int ld, int n_real, 
   if (e->fp32) Impl<float>(e).window_to_A1(logmel, ld, n_real, gmax, seek, seg, bi);
   else Impl<bf16>(e).window_to_A1(logmel, ld, n_real, gmax, seek, seg, bi);
 }
-void engine_decoder_layers(bw_engine* e, int R, int n_groups, int max_group_rows, int n_lrows, const int* row_seq,
+void engine_decoder_layers(bw_engine* e, DecGroup& G, int R, int n_groups, int max_group_rows, int n_lrows, const int* row_seq,
                            const int* row_pos, const int* row_tok, const int* row_bpos, const int* grp_first, const int* grp_n,
                            const int* grp_x, const int* lrow_src) {
   if (e->fp32) {
     Impl<float>::StepCtl c; c.R = R; c.n_groups = n_groups; c.max_group_rows = max_group_rows; c.n_lrows = n_lrows;
     c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.row_bpos = row_bpos; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
-    Impl<float>(e).decoder_layers(c);
+    Impl<float>(e, G.stream).decoder_layers(c, G);
   } else {
     Impl<bf16>::StepCtl c; c.R = R; c.n_groups = n_groups; c.max_group_rows = max_group_rows; c.n_lrows = n_lrows;
     c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.row_bpos = row_bpos; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
-    Impl<bf16>(e).decoder_layers(c);
+    Impl<bf16>(e, G.stream).decoder_layers(c, G);
   }
 }
 void engine_init_requests(bw_engine* e, const int* init_dev, int n) {

@@ -67,6 +67,16 @@ struct ModelW {
 
 enum ReqKind { REQ_DECODE = 0, REQ_LANG = 1, REQ_LOGITS = 2 };
 
+// Decoder-step working set of one request group.  The live requests of a step are split into up to kMaxGroups
+// groups that run on their own streams: one group's latency-bound LayerNorm / skinny-GEMM chain executes
+// underneath another group's HBM-bound cross-attention.
+struct DecGroup {
+  cudaStream_t stream = nullptr;
+  DevBuf d_x, d_xn, d_qkv, d_att, d_q, d_h, d_lnrows, d_logits, d_ws, d_cand_tok, d_cand_lp, d_ctrl;
+  int* h_ctrl = nullptr;  // pinned host copy of the control block
+};
+constexpr int kMaxGroups = 4;
+
 struct CallBuf {
   float* pcm = nullptr;     // device
   float* logmel = nullptr;  // device [n_mels][ld]
@@ -144,16 +154,17 @@ struct bw_engine {
   bw::DevBuf cross_cache, self_pool;
   // encoder activations
   bw::DevBuf A1, y1, A2, enc_x, enc_xn, enc_qkv, enc_att, enc_h, enc_out;
-  // decoder activations
-  bw::DevBuf d_x, d_xn, d_qkv, d_att, d_q, d_h, d_lnrows, d_logits, d_ws, d_cand_tok, d_cand_lp, d_lang_probs, d_lang_arg;
+  // decoder activations: one working set per request group
+  bw::DecGroup grp[bw::kMaxGroups];
+  bw::DevBuf d_lang_probs, d_lang_arg;
   // decoder state
   bw::DevBuf st_int, st_float, st_anc0, st_anc1, st_tok, st_parent;
   bw::ReqState rs{};
   bw::SeqState ss{};
   int anc_cur = 0;
-  // per-step host->device control block
-  bw::DevBuf d_ctrl;
-  int* h_ctrl = nullptr;      // pinned
+  // admission records (init_requests_kernel input)
+  bw::DevBuf d_init;
+  int* h_init = nullptr;      // pinned
   size_t ctrl_ints = 0;
   int* h_flags = nullptr;     // pinned [Q] completed flags
   unsigned char* h_fin = nullptr;  // pinned scratch for finalisation
