@@ -76,12 +76,10 @@ struct Ctl {
 
 // H2D of the control block + the whole decoder step (all layers, logits, filters/top-k, beam update) of one group,
 // enqueued on the group's stream.  No host synchronisation here.
-void enqueue_group_step(bw_engine* e, DecGroup& G, Ctl& c) {
-  if (c.R == 0) return;
+void enqueue_group_step_eager(bw_engine* e, DecGroup& G, Ctl& c) {
   int* dbase = G.d_ctrl.as<int>();
   auto dev = [&](int* h) { return dbase + (h - c.base); };
   BW_CUDA(cudaMemcpyAsync(dbase, c.base, c.total * 4, cudaMemcpyHostToDevice, G.stream));
-  e->stat_h2d += (long long)c.total * 4;
   engine_decoder_layers(e, G, c.R, c.NG, c.max_grp, c.LR, dev(c.row_seq), dev(c.row_pos), dev(c.row_tok), dev(c.row_bpos),
                         dev(c.grp_first), dev(c.grp_n), dev(c.grp_x), dev(c.lrow_src));
   const float* logits = G.d_logits.as<float>();
@@ -95,10 +93,45 @@ void enqueue_group_step(bw_engine* e, DecGroup& G, Ctl& c) {
               G.d_cand_lp.as<float>(), G.stream);
 }
 
+void enqueue_group_step(bw_engine* e, DecGroup& G, Ctl& c) {
+  if (c.R == 0) return;
+  e->stat_h2d += (long long)c.total * 4;
+  static const bool use_graphs = getenv("B200W_NO_GRAPH") == nullptr;
+  if (!use_graphs) return enqueue_group_step_eager(e, G, c);
+  const StepGraphKey key{c.R, c.NG, c.LR, c.SR, c.NA, c.NNS, c.max_grp, e->anc_cur};
+  StepGraph& sg = G.graphs[key];
+  if (sg.exec) {
+    BW_CUDA(cudaGraphLaunch(sg.exec, G.stream));
+    return;
+  }
+  if (++sg.seen < 2) return enqueue_group_step_eager(e, G, c);  // first sighting also warms every lazy initialisation
+  // second sighting of this shape: capture it (the launch sequence depends only on the key)
+  cudaGraph_t graph = nullptr;
+  BW_CUDA(cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal));
+  try {
+    enqueue_group_step_eager(e, G, c);
+  } catch (...) {
+    cudaStreamEndCapture(G.stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  BW_CUDA(cudaStreamEndCapture(G.stream, &graph));
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t st = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (st != cudaSuccess) throw CudaError(std::string("cudaGraphInstantiate -> ") + cudaGetErrorString(st));
+  if (G.graphs.size() > 96) {  // bound the cache: shapes churn while requests come and go
+    for (auto& kv : G.graphs) if (kv.second.exec && !(kv.first == key)) { cudaGraphExecDestroy(kv.second.exec); kv.second.exec = nullptr; kv.second.seen = 0; }
+  }
+  sg.exec = exec;
+  BW_CUDA(cudaGraphLaunch(exec, G.stream));
+}
+
 int choose_groups(int n_segments) {
   static const int forced = getenv("B200W_GROUPS") ? atoi(getenv("B200W_GROUPS")) : 0;
   if (forced > 0) return std::min(forced, (int)kMaxGroups);
-  return std::max(1, std::min((int)kMaxGroups, n_segments / 24));
+  (void)n_segments;
+  return 1;  // measured: extra groups re-stream the weights and lengthen the step (profiles/r1_notes.md)
 }
 
 void release_slots(bw_engine* e, Request* r) {
@@ -718,7 +751,11 @@ int bw_engine_destroy(bw_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   for (auto& b : e->call_pool) { cudaFree(b.pcm); cudaFree(b.logmel); cudaFree(b.gmax); }
-  for (auto& G : e->grp) { if (G.h_ctrl) cudaFreeHost(G.h_ctrl); if (G.stream) cudaStreamDestroy(G.stream); }
+  for (auto& G : e->grp) {
+    for (auto& kv : G.graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (G.h_ctrl) cudaFreeHost(G.h_ctrl);
+    if (G.stream) cudaStreamDestroy(G.stream);
+  }
   if (e->h_init) cudaFreeHost(e->h_init);
   if (e->h_flags) cudaFreeHost(e->h_flags);
   if (e->h_fin) cudaFreeHost(e->h_fin);

@@ -70,8 +70,29 @@ enum ReqKind { REQ_DECODE = 0, REQ_LANG = 1, REQ_LOGITS = 2 };
 // Decoder-step working set of one request group.  The live requests of a step are split into up to kMaxGroups
 // groups that run on their own streams: one group's latency-bound LayerNorm / skinny-GEMM chain executes
 // underneath another group's HBM-bound cross-attention.
+struct StepGraphKey {
+  int R, NG, LR, SR, NA, NNS, max_grp, anc;
+  bool operator==(const StepGraphKey& o) const {
+    return R == o.R && NG == o.NG && LR == o.LR && SR == o.SR && NA == o.NA && NNS == o.NNS && max_grp == o.max_grp && anc == o.anc;
+  }
+};
+struct StepGraphKeyHash {
+  size_t operator()(const StepGraphKey& k) const {
+    size_t h = 1469598103934665603ull;
+    for (int v : {k.R, k.NG, k.LR, k.SR, k.NA, k.NNS, k.max_grp, k.anc}) h = (h ^ (size_t)v) * 1099511628211ull;
+    return h;
+  }
+};
+struct StepGraph {
+  int seen = 0;
+  cudaGraphExec_t exec = nullptr;
+};
+
 struct DecGroup {
   cudaStream_t stream = nullptr;
+  // CUDA graphs of the whole decoder step, keyed by its shape: while the set of live requests is unchanged only the
+  // control block's CONTENTS change from step to step, so ~360 launches collapse into one cudaGraphLaunch.
+  std::unordered_map<StepGraphKey, StepGraph, StepGraphKeyHash> graphs;
   DevBuf d_x, d_xn, d_qkv, d_att, d_q, d_h, d_lnrows, d_logits, d_ws, d_cand_tok, d_cand_lp, d_ctrl;
   int* h_ctrl = nullptr;  // pinned host copy of the control block
 };
