@@ -104,8 +104,8 @@ void enqueue_group_step(bw_engine* e, DecGroup& G, Ctl& c) {
     BW_CUDA(cudaGraphLaunch(sg.exec, G.stream));
     return;
   }
-  if (++sg.seen < 2) return enqueue_group_step_eager(e, G, c);  // first sighting also warms every lazy initialisation
-  // second sighting of this shape: capture it (the launch sequence depends only on the key)
+  if (++sg.seen < 3) return enqueue_group_step_eager(e, G, c);  // early sightings also warm every lazy initialisation
+  // third sighting of this shape: it is stable enough to pay for a capture (the launch sequence depends only on the key)
   cudaGraph_t graph = nullptr;
   BW_CUDA(cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal));
   try {
