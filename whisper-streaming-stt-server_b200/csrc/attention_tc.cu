@@ -13,6 +13,7 @@
 // Replaces F.scaled_dot_product_attention in upstream MultiHeadAttention.qkv_attention
 // (reached from reference torch_whisper.py:55); SURVEY.md section 2.2 row K5.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
@@ -226,6 +227,217 @@ attn_encoder_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// v3: two 128-query tiles (A, B) per CTA in ping-pong.  K/V tiles are loaded once for both; while the softmax
+// warps of one tile work on CUDA cores / MUFU, the tensor core runs the other tile's S = Q K^T and O = P V, so
+// neither pipe idles on the other's latency.  4 softmax warps per tile (one thread = one query row), TMEM:
+// S_A | S_B (128 columns each) + O_A | O_B (64 each); shared: Q_A,Q_B 32 KB + 3 K|V stages 96 KB + P_A,P_B 64 KB.
+constexpr int PP_Q = 0;
+constexpr int PP_KV = 32768;                       // 3 stages x (K 16 KB + V 16 KB)
+constexpr int PP_STAGES = 3;
+constexpr int PP_P = PP_KV + PP_STAGES * 32768;    // 2 x 32 KB
+constexpr int PP_BAR = PP_P + 2 * 32768;
+constexpr int PP_TOTAL = PP_BAR + 256 + 1024;
+constexpr int PP_THREADS = 320;
+
+__global__ void __launch_bounds__(PP_THREADS, 1)
+attn_encoder_pp_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ out, int T_len, int d) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PP_BAR);
+  uint64_t* q_full = bars;           // 1
+  uint64_t* kv_full = bars + 1;      // 3
+  uint64_t* kv_empty = bars + 4;     // 3
+  uint64_t* s_full = bars + 7;       // 2 (per tile)
+  uint64_t* p_full = bars + 9;       // 2 (128 arrivals each)
+  uint64_t* o_full = bars + 11;      // 2
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int row_base = b * T_len;
+  const int n_kt = (T_len + TK - 1) / TK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < PP_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tm_S = tmem_base;         // + 128 * tile
+  const uint32_t tm_O = tmem_base + 256;   // + 64 * tile
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 32768);
+      tma_load_3d(smem + PP_Q, &tm, q_full, h * HD, row_base + q0, 0);
+      tma_load_3d(smem + PP_Q + 16384, &tm, q_full, h * HD, row_base + q0 + 128, 0);
+      for (int j = 0; j < n_kt; ++j) {
+        const int s = j % PP_STAGES;
+        mbar_wait(&kv_empty[s], ((j / PP_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 32768);
+        tma_load_3d(smem + PP_KV + s * 32768, &tm, &kv_full[s], d + h * HD, row_base + j * TK, 0);
+        tma_load_3d(smem + PP_KV + s * 32768 + 16384, &tm, &kv_full[s], 2 * d + h * HD, row_base + j * TK, 0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
+      auto issue_S = [&](int tile, int j) {  // caller made sure K_j has landed
+        const uint64_t adesc = umma_smem_desc_sw128(smem_u32(smem + PP_Q + tile * 16384), 16, 1024);
+        const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem + PP_KV + (j % PP_STAGES) * 32768), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_f16(tm_S + tile * 128, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_s, k != 0);
+        umma_commit(&s_full[tile]);
+      };
+      auto issue_PV = [&](int tile, int j) {
+        mbar_wait(&p_full[tile], j & 1);
+        tc_fence_after();
+        const uint32_t sp = smem_u32(smem + PP_P + tile * 32768);
+        const uint32_t sv = smem_u32(smem + PP_KV + (j % PP_STAGES) * 32768 + 16384);
+#pragma unroll
+        for (int k = 0; k < TK / 16; ++k) {
+          const uint64_t adesc = umma_smem_desc_sw128(sp + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          const uint64_t bdesc = umma_smem_desc_sw128(sv + k * 2048, 1024, 1024);
+          umma_f16(tm_O + tile * 64, adesc, bdesc, idesc_o, k != 0);
+        }
+        umma_commit(&o_full[tile]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_S(0, 0);
+      issue_S(1, 0);
+      for (int j = 0; j < n_kt; ++j) {
+        const bool more = j + 1 < n_kt;
+        issue_PV(0, j);
+        if (more) {
+          mbar_wait(&kv_full[(j + 1) % PP_STAGES], ((j + 1) / PP_STAGES) & 1);
+          tc_fence_after();
+          issue_S(0, j + 1);
+        }
+        issue_PV(1, j);
+        umma_commit(&kv_empty[j % PP_STAGES]);  // K_j / V_j fully consumed by both tiles
+        if (more) issue_S(1, j + 1);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int tile = (warp - 2) >> 2;  // warps 2..5 -> tile A, 6..9 -> tile B
+    const int wq = warp & 3;           // TMEM lane quarter this warp may touch
+    const int row = wq * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const float sl2 = 0.125f * 1.4426950408889634f;
+    const uint32_t my_S = tm_S + tile * 128 + lane_off, my_O = tm_O + tile * 64 + lane_off;
+    uint8_t* prow = smem + PP_P + tile * 32768 + row * 128;
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+    float o[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    for (int j = 0; j < n_kt; ++j) {
+      mbar_wait(&s_full[tile], j & 1);
+      tc_fence_after();
+      const int kvalid = T_len - j * TK;
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(my_S + c * 32, r);
+        tmem_ld_wait();
+        if (kvalid >= TK) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < kvalid) ? __uint_as_float(r[i]) : -INFINITY);
+        }
+      }
+      const float m_new = fmaxf(m, mx * sl2);
+      const float alpha = fast_exp2(m - m_new);
+      if (j > 0) {  // PV_{j-1} has retired: fold it in (and P may be overwritten below)
+        mbar_wait(&o_full[tile], (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(my_O + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
+        }
+      }
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(my_S + c * 32, r);
+        tmem_ld_wait();
+        uint8_t* panel = prow + (c >> 1) * 16384;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float p[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float e = fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), sl2, -m_new));
+            p[i] = (kvalid >= TK || c * 32 + g * 8 + i < kvalid) ? e : 0.f;
+            lsum += p[i];
+          }
+          uint4 t;
+          t.x = pack_bf16x2(p[0], p[1]); t.y = pack_bf16x2(p[2], p[3]);
+          t.z = pack_bf16x2(p[4], p[5]); t.w = pack_bf16x2(p[6], p[7]);
+          *reinterpret_cast<uint4*>(panel + ((((c & 1) * 4 + g) ^ (row & 7)) << 4)) = t;
+        }
+      }
+      l = l * alpha + lsum;
+      m = m_new;
+      alpha_prev = alpha;
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(&p_full[tile]);
+    }
+    mbar_wait(&o_full[tile], (n_kt - 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(my_O + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
+    }
+    const int qrow = q0 + tile * 128 + row;
+    if (qrow < T_len) {
+      const float inv = 1.f / l;
+      bf16* orow = out + (long long)(row_base + qrow) * d + h * HD;
+#pragma unroll
+      for (int i = 0; i < HD; i += 8) {
+        uint4 t;
+        t.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv); t.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
+        t.z = pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv); t.w = pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
+        *reinterpret_cast<uint4*>(orow + i) = t;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 void attn_encoder_tc(const bf16* qkv, bf16* out, int batch, int T_len, int n_head, cudaStream_t stream) {
@@ -238,6 +450,19 @@ void attn_encoder_tc(const bf16* qkv, bf16* out, int batch, int T_len, int n_hea
     attr_set.fetch_or(1ull << dev);
   }
   CUtensorMap tm = make_operand_map(qkv, batch * T_len, 3 * d, 3 * d, 1, 0, 128);
+  static const bool v2 = getenv("B200W_ATTN_V2") != nullptr;
+  if (!v2) {
+    static std::atomic<unsigned long long> pp_set{0};
+    if (!(pp_set.load() >> dev & 1ull)) {
+      BW_CUDA(cudaFuncSetAttribute(attn_encoder_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_TOTAL));
+      pp_set.fetch_or(1ull << dev);
+    }
+    dim3 grid_pp((T_len + 255) / 256, n_head, batch);
+    attn_encoder_pp_kernel<<<grid_pp, PP_THREADS, PP_TOTAL, stream>>>(tm, out, T_len, d);
+    BW_CUDA(cudaGetLastError());
+    ++g_kernel_launches;
+    return;
+  }
   dim3 grid((T_len + TQ - 1) / TQ, n_head, batch);
   attn_encoder_tc_kernel<<<grid, kThreads, SM_TOTAL, stream>>>(tm, out, T_len, d);
   BW_CUDA(cudaGetLastError());
