@@ -379,25 +379,44 @@ attn_encoder_pp_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict_
         }
       }
       float lsum = 0.f;
+      if (kvalid >= TK) {  // full tile: no per-element masking instructions in the hot loop
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(my_S + c * 32, r);
-        tmem_ld_wait();
-        uint8_t* panel = prow + (c >> 1) * 16384;
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(my_S + c * 32, r);
+          tmem_ld_wait();
+          uint8_t* panel = prow + (c >> 1) * 16384;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float p[8];
+          for (int g = 0; g < 4; ++g) {
+            float p[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float e = fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), sl2, -m_new));
-            p[i] = (kvalid >= TK || c * 32 + g * 8 + i < kvalid) ? e : 0.f;
-            lsum += p[i];
+            for (int i = 0; i < 8; ++i) {
+              p[i] = fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), sl2, -m_new));
+              lsum += p[i];
+            }
+            *reinterpret_cast<uint4*>(panel + ((((c & 1) * 4 + g) ^ (row & 7)) << 4)) =
+                make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
           }
-          uint4 t;
-          t.x = pack_bf16x2(p[0], p[1]); t.y = pack_bf16x2(p[2], p[3]);
-          t.z = pack_bf16x2(p[4], p[5]); t.w = pack_bf16x2(p[6], p[7]);
-          *reinterpret_cast<uint4*>(panel + ((((c & 1) * 4 + g) ^ (row & 7)) << 4)) = t;
+        }
+      } else {  // last tile of the window: columns >= kvalid are padding / the next window
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(my_S + c * 32, r);
+          tmem_ld_wait();
+          uint8_t* panel = prow + (c >> 1) * 16384;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float p[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float e = fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), sl2, -m_new));
+              p[i] = (c * 32 + g * 8 + i < kvalid) ? e : 0.f;
+              lsum += p[i];
+            }
+            *reinterpret_cast<uint4*>(panel + ((((c & 1) * 4 + g) ^ (row & 7)) << 4)) =
+                make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+          }
         }
       }
       l = l * alpha + lsum;

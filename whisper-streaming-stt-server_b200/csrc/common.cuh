@@ -68,6 +68,13 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// two exponentials per MUFU op: packed bf16 in, packed bf16 out (the result is stored as bf16 anyway)
+__device__ __forceinline__ uint32_t fast_exp2_bf16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 // erf-GELU with Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): 2 MUFU + ~10 FMA instead of erff's
 // branchy polynomial; used by the bf16 tensor-core epilogues (output rounding is 4e-3 relative).
