@@ -388,14 +388,16 @@ attn_encoder_pp_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict_
           uint8_t* panel = prow + (c >> 1) * 16384;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float p[8];
+            uint32_t pb[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              p[i] = fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), sl2, -m_new));
-              lsum += p[i];
+              // bf16-round on the integer ALU and sum the ROUNDED values so that P / l stays consistent
+              pb[i] = bf16_round_bits(fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), sl2, -m_new)));
+              lsum += __uint_as_float(pb[i]);
             }
             *reinterpret_cast<uint4*>(panel + ((((c & 1) * 4 + g) ^ (row & 7)) << 4)) =
-                make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+                make_uint4(pack_bf16x2_bits(pb[0], pb[1]), pack_bf16x2_bits(pb[2], pb[3]), pack_bf16x2_bits(pb[4], pb[5]),
+                           pack_bf16x2_bits(pb[6], pb[7]));
           }
         }
       } else {  // last tile of the window: columns >= kvalid are padding / the next window

@@ -276,6 +276,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// fp32 -> bf16 on the integer ALU (round to nearest, ties away; operands are finite and >= 0 here): F2FP.PACK_AB
+// issues on the XU pipe, which the attention softmax needs for MUFU.EX2.
+__device__ __forceinline__ uint32_t bf16_round_bits(float x) { return (__float_as_uint(x) + 0x8000u) & 0xffff0000u; }
+__device__ __forceinline__ uint32_t pack_bf16x2_bits(uint32_t lo_bits, uint32_t hi_bits) { return __byte_perm(lo_bits, hi_bits, 0x7632); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
