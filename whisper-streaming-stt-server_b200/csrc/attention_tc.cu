@@ -346,81 +346,85 @@ attn_encoder_pp_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict_
     float o[HD];
 #pragma unroll
     for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    // TMEM loads are software-pipelined through two register buffers: the load of chunk c+1 is in flight while
+    // chunk c is processed (tcgen05.wait::ld waits for everything outstanding, so issue-after-wait ordering is used).
+    uint32_t ra[32], rb[32];
+    auto chunk_max = [&](const uint32_t* r, int c, int kvalid, float mx) {
+      if (kvalid >= TK) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < kvalid) ? __uint_as_float(r[i]) : -INFINITY);
+      }
+      return mx;
+    };
+    auto chunk_exp = [&](const uint32_t* r, int c, int kvalid, float m_new, float lsum) {
+      uint8_t* panel = prow + (c >> 1) * 16384;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t pb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float e = fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), sl2, -m_new));
+          if (kvalid < TK && c * 32 + g * 8 + i >= kvalid) e = 0.f;
+          pb[i] = bf16_round_bits(e);  // integer-ALU rounding; the row sum uses the ROUNDED values
+          lsum += __uint_as_float(pb[i]);
+        }
+        *reinterpret_cast<uint4*>(panel + ((((c & 1) * 4 + g) ^ (row & 7)) << 4)) =
+            make_uint4(pack_bf16x2_bits(pb[0], pb[1]), pack_bf16x2_bits(pb[2], pb[3]), pack_bf16x2_bits(pb[4], pb[5]),
+                       pack_bf16x2_bits(pb[6], pb[7]));
+      }
+      return lsum;
+    };
     for (int j = 0; j < n_kt; ++j) {
       mbar_wait(&s_full[tile], j & 1);
       tc_fence_after();
       const int kvalid = T_len - j * TK;
+      // ---- pass 1: row max ----
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(my_S + c * 32, r);
-        tmem_ld_wait();
-        if (kvalid >= TK) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < kvalid) ? __uint_as_float(r[i]) : -INFINITY);
-        }
-      }
+      tmem_ld_32x32b_x32(my_S, ra);
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(my_S + 32, rb);
+      mx = chunk_max(ra, 0, kvalid, mx);
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(my_S + 64, ra);
+      mx = chunk_max(rb, 1, kvalid, mx);
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(my_S + 96, rb);
+      mx = chunk_max(ra, 2, kvalid, mx);
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(my_S, ra);  // chunk 0 again, for pass 2
+      mx = chunk_max(rb, 3, kvalid, mx);
       const float m_new = fmaxf(m, mx * sl2);
       const float alpha = fast_exp2(m - m_new);
-      if (j > 0) {  // PV_{j-1} has retired: fold it in (and P may be overwritten below)
+      // ---- fold in O_{j-1} (PV_{j-1} has retired; P may be overwritten afterwards) ----
+      if (j > 0) {
         mbar_wait(&o_full[tile], (j - 1) & 1);
         tc_fence_after();
+        tmem_ld_32x32b_x32(my_O, rb);
+        tmem_ld_wait();  // also completes ra (S chunk 0)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(my_O + c * 32, r);
-          tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(rb[i]));
+        tmem_ld_32x32b_x32(my_O + 32, rb);
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
-        }
+        for (int i = 0; i < 32; ++i) o[32 + i] = fmaf(o[32 + i], alpha_prev, __uint_as_float(rb[i]));
+      } else {
+        tmem_ld_wait();
       }
+      // ---- pass 2: P = exp2(S * scale - max), bf16, swizzled K-major tile ----
       float lsum = 0.f;
-      if (kvalid >= TK) {  // full tile: no per-element masking instructions in the hot loop
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(my_S + c * 32, r);
-          tmem_ld_wait();
-          uint8_t* panel = prow + (c >> 1) * 16384;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t pb[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              // bf16-round on the integer ALU and sum the ROUNDED values so that P / l stays consistent
-              pb[i] = bf16_round_bits(fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), sl2, -m_new)));
-              lsum += __uint_as_float(pb[i]);
-            }
-            *reinterpret_cast<uint4*>(panel + ((((c & 1) * 4 + g) ^ (row & 7)) << 4)) =
-                make_uint4(pack_bf16x2_bits(pb[0], pb[1]), pack_bf16x2_bits(pb[2], pb[3]), pack_bf16x2_bits(pb[4], pb[5]),
-                           pack_bf16x2_bits(pb[6], pb[7]));
-          }
-        }
-      } else {  // last tile of the window: columns >= kvalid are padding / the next window
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(my_S + c * 32, r);
-          tmem_ld_wait();
-          uint8_t* panel = prow + (c >> 1) * 16384;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float p[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float e = fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), sl2, -m_new));
-              p[i] = (c * 32 + g * 8 + i < kvalid) ? e : 0.f;
-              lsum += p[i];
-            }
-            *reinterpret_cast<uint4*>(panel + ((((c & 1) * 4 + g) ^ (row & 7)) << 4)) =
-                make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
-          }
-        }
-      }
+      tmem_ld_32x32b_x32(my_S + 32, rb);
+      lsum = chunk_exp(ra, 0, kvalid, m_new, lsum);
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(my_S + 64, ra);
+      lsum = chunk_exp(rb, 1, kvalid, m_new, lsum);
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(my_S + 96, rb);
+      lsum = chunk_exp(ra, 2, kvalid, m_new, lsum);
+      tmem_ld_wait();
+      lsum = chunk_exp(rb, 3, kvalid, m_new, lsum);
       l = l * alpha + lsum;
       m = m_new;
       alpha_prev = alpha;
