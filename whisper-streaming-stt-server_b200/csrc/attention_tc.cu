@@ -231,15 +231,16 @@ attn_encoder_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict_
 // ------------------------------------------------------------------------------------------------
 // v3: two 128-query tiles (A, B) per CTA in ping-pong.  K/V tiles are loaded once for both; while the softmax
 // warps of one tile work on CUDA cores / MUFU, the tensor core runs the other tile's S = Q K^T and O = P V, so
-// neither pipe idles on the other's latency.  4 softmax warps per tile (one thread = one query row), TMEM:
+// neither pipe idles on the other's latency.  8 softmax warps per tile (4 per SM sub-partition overall), TMEM:
 // S_A | S_B (128 columns each) + O_A | O_B (64 each); shared: Q_A,Q_B 32 KB + 3 K|V stages 96 KB + P_A,P_B 64 KB.
 constexpr int PP_Q = 0;
 constexpr int PP_KV = 32768;                       // 3 stages x (K 16 KB + V 16 KB)
 constexpr int PP_STAGES = 3;
 constexpr int PP_P = PP_KV + PP_STAGES * 32768;    // 2 x 32 KB
 constexpr int PP_BAR = PP_P + 2 * 32768;
-constexpr int PP_TOTAL = PP_BAR + 256 + 1024;
-constexpr int PP_THREADS = 320;
+constexpr int PP_MX = PP_BAR + 256;               // row-max exchange: [2 tiles][2 parity][2 halves][128] floats
+constexpr int PP_TOTAL = PP_MX + 2 * 512 * 4 + 1024;
+constexpr int PP_THREADS = 576;
 
 __global__ void __launch_bounds__(PP_THREADS, 1)
 attn_encoder_pp_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ out, int T_len, int d) {
@@ -263,7 +264,7 @@ attn_encoder_pp_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict_
     tma_prefetch_desc(&tm);
     mbar_init(q_full, 1);
     for (int i = 0; i < PP_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&o_full[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -335,96 +336,74 @@ attn_encoder_pp_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict_
     }
     __syncwarp();
   } else {
-    const int tile = (warp - 2) >> 2;  // warps 2..5 -> tile A, 6..9 -> tile B
-    const int wq = warp & 3;           // TMEM lane quarter this warp may touch
+    // 16 softmax warps: warps 2..9 -> tile A, 10..17 -> tile B; inside a tile two warps share each TMEM lane
+    // quarter (= SM sub-partition) and split the 128 key columns / 64 output columns between them.
+    const int tile = (warp - 2) >> 3;
+    const int half = ((warp - 2) >> 2) & 1;
+    const int wq = warp & 3;
     const int row = wq * 32 + lane;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const float sl2 = 0.125f * 1.4426950408889634f;
-    const uint32_t my_S = tm_S + tile * 128 + lane_off, my_O = tm_O + tile * 64 + lane_off;
-    uint8_t* prow = smem + PP_P + tile * 32768 + row * 128;
+    const uint32_t my_S = tm_S + tile * 128 + lane_off + half * 64, my_O = tm_O + tile * 64 + lane_off + half * 32;
+    uint8_t* prow = smem + PP_P + tile * 32768 + half * 16384 + row * 128;  // panel `half` of P
+    float* mxbuf = reinterpret_cast<float*>(smem + PP_MX) + tile * 512;     // [2 parity][2 halves][128]
     float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    float o[HD];
+    float o[32];
 #pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
-    // TMEM loads are software-pipelined through two register buffers: the load of chunk c+1 is in flight while
-    // chunk c is processed (tcgen05.wait::ld waits for everything outstanding, so issue-after-wait ordering is used).
-    uint32_t ra[32], rb[32];
-    auto chunk_max = [&](const uint32_t* r, int c, int kvalid, float mx) {
-      if (kvalid >= TK) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < kvalid) ? __uint_as_float(r[i]) : -INFINITY);
-      }
-      return mx;
-    };
-    auto chunk_exp = [&](const uint32_t* r, int c, int kvalid, float m_new, float lsum) {
-      uint8_t* panel = prow + (c >> 1) * 16384;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint32_t pb[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float e = fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), sl2, -m_new));
-          if (kvalid < TK && c * 32 + g * 8 + i >= kvalid) e = 0.f;
-          pb[i] = bf16_round_bits(e);  // integer-ALU rounding; the row sum uses the ROUNDED values
-          lsum += __uint_as_float(pb[i]);
-        }
-        *reinterpret_cast<uint4*>(panel + ((((c & 1) * 4 + g) ^ (row & 7)) << 4)) =
-            make_uint4(pack_bf16x2_bits(pb[0], pb[1]), pack_bf16x2_bits(pb[2], pb[3]), pack_bf16x2_bits(pb[4], pb[5]),
-                       pack_bf16x2_bits(pb[6], pb[7]));
-      }
-      return lsum;
-    };
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
     for (int j = 0; j < n_kt; ++j) {
       mbar_wait(&s_full[tile], j & 1);
       tc_fence_after();
-      const int kvalid = T_len - j * TK;
-      // ---- pass 1: row max ----
+      const int kvalid = T_len - j * TK - half * 64;  // my 64 columns: those >= kvalid are padding / next window
       float mx = -INFINITY;
-      tmem_ld_32x32b_x32(my_S, ra);
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(my_S + 32, rb);
-      mx = chunk_max(ra, 0, kvalid, mx);
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(my_S + 64, ra);
-      mx = chunk_max(rb, 1, kvalid, mx);
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(my_S + 96, rb);
-      mx = chunk_max(ra, 2, kvalid, mx);
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(my_S, ra);  // chunk 0 again, for pass 2
-      mx = chunk_max(rb, 3, kvalid, mx);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(my_S + c * 32, r);
+        tmem_ld_wait();
+        if (kvalid >= 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < kvalid) ? __uint_as_float(r[i]) : -INFINITY);
+        }
+      }
+      mxbuf[((j & 1) * 2 + half) * 128 + row] = mx;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + tile) : "memory");
+      mx = fmaxf(mx, mxbuf[((j & 1) * 2 + (half ^ 1)) * 128 + row]);
       const float m_new = fmaxf(m, mx * sl2);
       const float alpha = fast_exp2(m - m_new);
-      // ---- fold in O_{j-1} (PV_{j-1} has retired; P may be overwritten afterwards) ----
-      if (j > 0) {
+      if (j > 0) {  // PV_{j-1} has retired: fold it in (and P may be overwritten below)
         mbar_wait(&o_full[tile], (j - 1) & 1);
         tc_fence_after();
-        tmem_ld_32x32b_x32(my_O, rb);
-        tmem_ld_wait();  // also completes ra (S chunk 0)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(rb[i]));
-        tmem_ld_32x32b_x32(my_O + 32, rb);
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(my_O, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[32 + i] = fmaf(o[32 + i], alpha_prev, __uint_as_float(rb[i]));
-      } else {
-        tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(r[i]));
       }
-      // ---- pass 2: P = exp2(S * scale - max), bf16, swizzled K-major tile ----
       float lsum = 0.f;
-      tmem_ld_32x32b_x32(my_S + 32, rb);
-      lsum = chunk_exp(ra, 0, kvalid, m_new, lsum);
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(my_S + 64, ra);
-      lsum = chunk_exp(rb, 1, kvalid, m_new, lsum);
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(my_S + 96, rb);
-      lsum = chunk_exp(ra, 2, kvalid, m_new, lsum);
-      tmem_ld_wait();
-      lsum = chunk_exp(rb, 3, kvalid, m_new, lsum);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(my_S + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t pb[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float e = fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), sl2, -m_new));
+            if (kvalid < 64 && c * 32 + g * 8 + i >= kvalid) e = 0.f;
+            pb[i] = bf16_round_bits(e);  // integer-ALU rounding; the row sum uses the ROUNDED values
+            lsum += __uint_as_float(pb[i]);
+          }
+          *reinterpret_cast<uint4*>(prow + (((c * 4 + g) ^ (row & 7)) << 4)) =
+              make_uint4(pack_bf16x2_bits(pb[0], pb[1]), pack_bf16x2_bits(pb[2], pb[3]), pack_bf16x2_bits(pb[4], pb[5]),
+                         pack_bf16x2_bits(pb[6], pb[7]));
+        }
+      }
       l = l * alpha + lsum;
       m = m_new;
       alpha_prev = alpha;
@@ -434,20 +413,24 @@ attn_encoder_pp_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict_
     }
     mbar_wait(&o_full[tile], (n_kt - 1) & 1);
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t r[32];
-      tmem_ld_32x32b_x32(my_O + c * 32, r);
+      tmem_ld_32x32b_x32(my_O, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
+      for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(r[i]));
     }
+    // total row sum = both column halves (they track the same running max)
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + tile) : "memory");
+    mxbuf[half * 128 + row] = l;
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + tile) : "memory");
+    l += mxbuf[(half ^ 1) * 128 + row];
     const int qrow = q0 + tile * 128 + row;
     if (qrow < T_len) {
       const float inv = 1.f / l;
-      bf16* orow = out + (long long)(row_base + qrow) * d + h * HD;
+      bf16* orow = out + (long long)(row_base + qrow) * d + h * HD + half * 32;
 #pragma unroll
-      for (int i = 0; i < HD; i += 8) {
+      for (int i = 0; i < 32; i += 8) {
         uint4 t;
         t.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv); t.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
         t.z = pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv); t.w = pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
