@@ -172,6 +172,12 @@ int bw_bench_decoder_step(bw_engine*, int32_t n_segments, int32_t n_group, int32
 int bw_bench_pipeline(bw_engine*, const float* pcm_host, const int64_t* offsets, const int64_t* lengths,
                       int32_t n_segments, int32_t n_group, int32_t n_steps, float* ms_out);
 
+/* Debug timeline of the decoder step: enable != 0 arms a device buffer that the step's kernels append
+ * (tag, globaltimer ns) records to; enable == 0 disarms it and copies up to `cap` records (2 x uint64 each:
+ * smid << 32 | kernel id << 24 | grid.x << 8 | phase, then the timestamp) to `out`, count in *n_out.
+ * Run with B200W_NO_GRAPH=1 (captured graphs keep the pointer they were captured with). */
+int bw_debug_trace(bw_engine*, int32_t enable, uint64_t* out, int32_t cap, int32_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,16 @@
+"""Decoder-step time over batch shapes (run once with and once without B200W_NO_GRAPH=1 for the graph/eager A-B).
+Usage: python tools/step_sweep.py [model]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from b200_whisper.backend import B200WhisperBackend  # noqa: E402
+
+model = sys.argv[1] if len(sys.argv) > 1 else "large-v3"
+b = B200WhisperBackend(f"random:{model}:0:0.1", "cuda:0", "bfloat16", max_segments=128, max_sequences=320, max_encoder_batch=1)
+eng = b.engine
+mode = "eager" if os.environ.get("B200W_NO_GRAPH") else "graph"
+for seg, grp in ((1, 1), (8, 1), (32, 1), (64, 1), (128, 1), (1, 5), (16, 5), (64, 5)):
+    for ctx in (20, 100, 200):
+        ms, by = eng.bench_decoder_step(seg, grp, ctx, 12)
+        print(f"{mode} step {seg:3d} x {grp}  ctx {ctx:3d}: {ms:7.3f} ms  {by / ms / 1e6:7.1f} GB/s  ({by / ms / 1e6 / 6546.6 * 100:4.1f} % of HBM)", flush=True)

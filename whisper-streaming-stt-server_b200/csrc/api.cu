@@ -1196,4 +1196,32 @@ int bw_bench_cross_attention(bw_engine* e, int32_t n_segments, int32_t n_group, 
   BW_API_END
 }
 
+int bw_debug_trace(bw_engine* e, int32_t enable, uint64_t* out, int32_t cap, int32_t* n_out) {
+  BW_API_BEGIN
+  BW_CHECK(e, "null argument");
+  DeviceGuard dg(e->device);
+  std::lock_guard<std::mutex> g(e->gpu_mu);
+  BW_CUDA(cudaDeviceSynchronize());
+  static DevBuf buf;
+  const size_t bytes = (1 + 2 * (size_t)kTraceCap) * 8;
+  if (enable) {
+    if (buf.bytes < bytes) buf.alloc(bytes);
+    BW_CUDA(cudaMemset(buf.p, 0, bytes));
+    g_trace_dev = buf.as<unsigned long long>();
+  } else {
+    BW_CHECK(out && n_out && cap >= 0, "null argument");
+    unsigned long long* dev = g_trace_dev;
+    g_trace_dev = nullptr;
+    *n_out = 0;
+    if (dev) {
+      unsigned long long cnt = 0;
+      BW_CUDA(cudaMemcpy(&cnt, dev, 8, cudaMemcpyDeviceToHost));
+      const int n = (int)std::min<unsigned long long>(std::min<unsigned long long>(cnt, kTraceCap), (unsigned long long)cap);
+      if (n > 0) BW_CUDA(cudaMemcpy(out, dev + 1, (size_t)n * 16, cudaMemcpyDeviceToHost));
+      *n_out = n;
+    }
+  }
+  BW_API_END
+}
+
 }  // extern "C"

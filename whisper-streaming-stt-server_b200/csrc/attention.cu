@@ -131,19 +131,45 @@ constexpr int kSingleBeamFlag = 0x40000000;  // set in seq_first[s] when the req
 
 // One CTA per (head, row).  Fuses the KV append: this row's k/v head slice (fp32 qkv buffer -> T) is written to
 // the pool, and keys/values of positions fed in THIS step (the row itself; earlier prefill rows of the same
-// sequence) are read from the qkv buffer instead of the pool, so no ordering between CTAs is needed.
-// Single pass: K and V of a position are loaded together (two 16-byte loads in flight per lane), online softmax
-// per lane group, one shared-memory merge at the end.
+// sequence) are taken from the qkv buffer instead of the pool, so no ordering between CTAs is needed.
+// The cached K/V head slices are staged into shared memory with cp.async (every 16-byte request of a 128-position
+// chunk in flight at once: the kernel is a pure HBM stream, 2*t*128 B per CTA), then consumed by 8-lane groups
+// with an online softmax; one shared-memory merge at the end.  (The first version walked the keys with dependent
+// global loads: 9 us per CTA and 2 waves at context 100 -- tools/trace_step.py.)
+constexpr int kSelfChunk = 128;  // positions staged per pass
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <typename T> __device__ __forceinline__ void load_smem_vec(const T* p, float* f);
+template <> __device__ __forceinline__ void load_smem_vec<bf16>(const bf16* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+template <> __device__ __forceinline__ void load_smem_vec<float>(const float* p, float* f) {
+  const float4 u = *reinterpret_cast<const float4*>(p);
+  f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128)
 dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const int* __restrict__ row_bpos,
                           const float* __restrict__ qkv, T* __restrict__ pool, long long unit_stride, int n_ctx,
                           const int* __restrict__ seq_first, const unsigned char* __restrict__ anc, int layer, int d,
-                          T* __restrict__ out) {
+                          T* __restrict__ out, unsigned long long* trace_buf) {
   constexpr int VEC = Vec16<T>::N, LPR = 64 / VEC, RPW = 32 / LPR;
-  __shared__ float part[4][RPW > 0 ? 66 : 66];
+  extern __shared__ __align__(16) unsigned char self_smem[];
+  T* Ks = reinterpret_cast<T*>(self_smem);  // [kSelfChunk][64]
+  T* Vs = Ks + kSelfChunk * 64;
+  __shared__ float part[4][66];
+  unsigned long long* const trace = ((blockIdx.x | blockIdx.y) == 0 && threadIdx.x == 0) ? trace_buf : nullptr;
+  trace_mark(trace, (3u << 24) | 1);
   pdl_trigger();
-  pdl_wait();
+  // Everything read before the dependency wait was written by earlier STEPS (control block, ancestry, cached K/V),
+  // never by the kernels of this step: the first chunk of the cache is already streaming in while the QKV
+  // projection that precedes this kernel drains.  Only q and this step's own k/v rows need the wait.
   const int h = blockIdx.x, r = blockIdx.y;
   const int s = row_seq[r], pos = row_pos[r], bpos = row_bpos[r];
   const int sf = seq_first[s];
@@ -152,6 +178,19 @@ dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict
   const unsigned char* my_anc = anc + (long long)s * n_ctx;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane % LPR, rg = lane / LPR;
+  const int n = pos + 1;
+  auto stage_cached = [&](int c0, int cn) {
+    for (int idx = threadIdx.x; idx < cn * 2 * LPR; idx += 128) {
+      const int ch = idx % LPR, kv = (idx / LPR) & 1, tl = idx / (2 * LPR);
+      const int t = c0 + tl;
+      if (t < bpos)
+        cp_async_16((kv ? Vs : Ks) + tl * 64 + ch * VEC, pool + (long long)(single ? first : first + my_anc[t]) * unit_stride +
+                                                               ((long long)(layer * 2 + kv) * n_ctx + t) * d + h * 64 + ch * VEC);
+    }
+  };
+  stage_cached(0, min(kSelfChunk, n));
+  pdl_wait();
+  trace_mark(trace, (3u << 24) | 2);
   const float* qrow = qkv + (long long)r * 3 * d + h * 64;
   // fused append: k/v of this row -> pool[unit s][layer][k|v][pos]
   {
@@ -162,42 +201,48 @@ dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict
   float qf[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) qf[i] = qrow[sub * VEC + i] * 0.125f;
-  const long long koff = ((long long)(layer * 2 + 0) * n_ctx) * d + h * 64 + sub * VEC;
-  const long long voff = ((long long)(layer * 2 + 1) * n_ctx) * d + h * 64 + sub * VEC;
-  const int n = pos + 1;
   float m = -INFINITY, l = 0.f, acc[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-  for (int tg = warp * RPW; tg < n; tg += 4 * RPW) {
-    const int t = tg + rg;
-    float kf[VEC], vf[VEC];
-    float sc = -INFINITY;
-    if (t < n) {
-      if (t < bpos) {
-        const T* base = pool + (long long)(single ? first : first + my_anc[t]) * unit_stride + (long long)t * d;
-        Vec16<T>::load(base + koff, kf);
-        Vec16<T>::load(base + voff, vf);
-      } else {  // fed in this step: fp32 rows of the qkv buffer, rounded like the pool copy
-        const float* src = qkv + (long long)(r - (pos - t)) * 3 * d + h * 64 + sub * VEC;
+  for (int c0 = 0; c0 < n; c0 += kSelfChunk) {
+    const int cn = min(kSelfChunk, n - c0);
+    if (c0 > 0) {
+      __syncthreads();  // the previous chunk has been consumed by every warp
+      stage_cached(c0, cn);
+    }
+    // positions fed in this step: fp32 rows of the qkv buffer, rounded like the pool copy
+    for (int idx = threadIdx.x; idx < cn * 2 * LPR; idx += 128) {
+      const int ch = idx % LPR, kv = (idx / LPR) & 1, tl = idx / (2 * LPR);
+      const int t = c0 + tl;
+      if (t >= bpos) {
+        T* dst = (kv ? Vs : Ks) + tl * 64 + ch * VEC;
+        const float* src = qkv + (long long)(r - (pos - t)) * 3 * d + (1 + kv) * d + h * 64 + ch * VEC;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) { kf[i] = to_f(from_f<T>(src[d + i])); vf[i] = to_f(from_f<T>(src[2 * d + i])); }
+        for (int i = 0; i < VEC; ++i) dst[i] = from_f<T>(src[i]);
       }
-      sc = 0.f;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) sc = fmaf(qf[i], kf[i], sc);
     }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int tg = warp * RPW; tg < cn; tg += 4 * RPW) {
+      const int tl = tg + rg;
+      float kf[VEC], vf[VEC];
+      float sc = 0.f;
+      if (tl < cn) {
+        load_smem_vec<T>(Ks + tl * 64 + sub * VEC, kf);
+        load_smem_vec<T>(Vs + tl * 64 + sub * VEC, vf);
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) {
-      const float other = __shfl_xor_sync(0xffffffffu, sc, o);
-      sc = (t < n) ? sc + other : sc;
-    }
-    if (t < n) {
-      const float m_new = fmaxf(m, sc);
-      const float a = exp_t<T>(m - m_new), pr = exp_t<T>(sc - m_new);
-      l = l * a + pr;
+        for (int i = 0; i < VEC; ++i) sc = fmaf(qf[i], kf[i], sc);
+      }
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[i] = fmaf(pr, vf[i], acc[i] * a);
-      m = m_new;
+      for (int o = LPR / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+      if (tl < cn) {
+        const float m_new = fmaxf(m, sc);
+        const float a = exp_t<T>(m - m_new), pr = exp_t<T>(sc - m_new);
+        l = l * a + pr;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(pr, vf[i], acc[i] * a);
+        m = m_new;
+      }
     }
   }
   // merge the row groups of this warp, then the 4 warps
@@ -232,6 +277,7 @@ dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict
     }
     out[(long long)r * d + h * 64 + c] = from_f<T>(num / den);
   }
+  trace_mark(trace, (3u << 24) | 8);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -431,8 +477,16 @@ void dec_self_attention(const DecRows& rows, const float* qkv, const SelfKV& kv,
   if (rows.n_rows <= 0) return;
   BW_CHECK(kv.n_ctx <= 448, "n_text_ctx > 448 unsupported");
   dim3 grid(n_head, rows.n_rows);
-  launch_kernel(dec_self_attention_kernel<T>, grid, dim3(128), 0, stream, rows.row_seq, rows.row_pos, rows.row_bpos, qkv,
-                reinterpret_cast<T*>(kv.pool), kv.unit_stride, kv.n_ctx, kv.seq_first, kv.anc, layer, d, out);
+  constexpr int smem = 2 * kSelfChunk * 64 * (int)sizeof(T);
+  static std::atomic<unsigned long long> attr_set{0};
+  int dev = 0;
+  BW_CUDA(cudaGetDevice(&dev));
+  if (!(attr_set.load() >> dev & 1ull)) {
+    BW_CUDA(cudaFuncSetAttribute(dec_self_attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set.fetch_or(1ull << dev);
+  }
+  launch_kernel(dec_self_attention_kernel<T>, grid, dim3(128), smem, stream, rows.row_seq, rows.row_pos, rows.row_bpos, qkv,
+                reinterpret_cast<T*>(kv.pool), kv.unit_stride, kv.n_ctx, kv.seq_first, kv.anc, layer, d, out, g_trace_dev);
   ++g_kernel_launches;
 }
 template void dec_self_attention<float>(const DecRows&, const float*, const SelfKV&, int, int, int, float*, cudaStream_t);

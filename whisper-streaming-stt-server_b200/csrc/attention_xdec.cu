@@ -44,8 +44,15 @@ __global__ void __launch_bounds__(160, 2)
 dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int* __restrict__ group_first_row,
                                const int* __restrict__ group_n_rows, const int* __restrict__ group_xslot,
                                const float* __restrict__ q, int T_enc, int n_layer, int layer, int d, int n_split,
-                               bf16* __restrict__ out, float* __restrict__ ws) {
+                               bf16* __restrict__ out, float* __restrict__ ws, unsigned long long* trace_buf) {
   extern __shared__ uint8_t smem_raw[];
+  unsigned long long* trace = nullptr;
+  unsigned ttag = 4u << 24;
+  if (threadIdx.x == 0) {
+    if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0) trace = trace_buf;
+    else if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1) { trace = trace_buf; ttag = 5u << 24; }
+  }
+  trace_mark(trace, ttag | 1);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + XSM_BAR);
   uint64_t* empty_bar = full_bar + XSTAGES;
@@ -83,6 +90,7 @@ dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int
     __syncwarp();
   } else {
     pdl_wait();
+    trace_mark(trace, ttag | 2);
     const int gid = lane >> 2, tig = lane & 3;  // query row (hypothesis) and column pair inside an n-tile
     // A fragments of q (rows 8..15 are zero): 4 k-steps of 16 dims; 1/sqrt(64) folded in (exact in bf16)
     uint32_t qa[4][2];
@@ -200,6 +208,7 @@ dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int
       }
     }
   }
+  trace_mark(trace, ttag | 8);
 }
 
 }  // namespace
@@ -225,7 +234,7 @@ void dec_cross_attention_mma(const int* group_first_row, const int* group_n_rows
   const CUtensorMap tm = cached_tm;
   dim3 grid(n_head, n_groups, n_split);
   launch_kernel(dec_cross_attention_mma_kernel, grid, dim3(160), XSM_TOTAL, stream, tm, group_first_row, group_n_rows, group_xslot, q,
-                kv.T_enc, n_layer, layer, d, n_split, out, ws);
+                kv.T_enc, n_layer, layer, d, n_split, out, ws, g_trace_dev);
   ++g_kernel_launches;
 }
 

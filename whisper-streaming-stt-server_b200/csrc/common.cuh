@@ -55,6 +55,23 @@ inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
   if (e != cudaSuccess) throw CudaError(std::string("kernel launch -> ") + cudaGetErrorString(e));
 }
 
+// ---- in-situ timeline (debug only): kernels of the decoder step append (tag, globaltimer ns) records when
+// bw_debug_trace armed a device buffer; a null pointer (the default) costs one predicated branch.
+extern unsigned long long* g_trace_dev;  // host-side copy of the device buffer pointer, null = off
+constexpr unsigned kTraceCap = 1u << 16;
+__device__ __forceinline__ void trace_mark(unsigned long long* buf, unsigned tag) {
+  if (buf == nullptr) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  const unsigned long long i = atomicAdd(buf, 1ull);
+  if (i < kTraceCap) {
+    buf[1 + 2 * i] = ((unsigned long long)smid << 32) | tag;
+    buf[2 + 2 * i] = t;
+  }
+}
+
 // ---- scalar conversion helpers (templated kernels run in float or bf16 storage) ----
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }

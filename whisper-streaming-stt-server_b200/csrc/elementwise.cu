@@ -12,10 +12,13 @@ namespace {
 template <typename TOut, bool GATHER>
 __global__ void __launch_bounds__(128)
 layernorm_kernel(const float* __restrict__ x, const int* __restrict__ rows_idx, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, TOut* __restrict__ out, int rows, int d) {
+                 const float* __restrict__ beta, TOut* __restrict__ out, int rows, int d, unsigned long long* trace_buf) {
   __shared__ float red[4];
+  unsigned long long* const trace = (blockIdx.x == 0 && threadIdx.x == 0) ? trace_buf : nullptr;
+  trace_mark(trace, (2u << 24) | 1);
   pdl_trigger();
   pdl_wait();
+  trace_mark(trace, (2u << 24) | 2);
   const int row = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)(GATHER ? rows_idx[row] : row) * d);
@@ -64,6 +67,7 @@ layernorm_kernel(const float* __restrict__ x, const int* __restrict__ rows_idx, 
       }
     }
   }
+  trace_mark(trace, (2u << 24) | 8);
 }
 
 template <typename T>
@@ -141,7 +145,7 @@ template <typename T>
 void layernorm(const float* x, const float* gamma, const float* beta, T* out, int rows, int d, cudaStream_t stream) {
   BW_CHECK(d <= 1536 && d % 4 == 0, "layernorm supports d <= 1536, d % 4 == 0");
   if (rows <= 0) return;
-  launch_kernel(layernorm_kernel<T, false>, dim3(rows), dim3(128), 0, stream, x, (const int*)nullptr, gamma, beta, out, rows, d);
+  launch_kernel(layernorm_kernel<T, false>, dim3(rows), dim3(128), 0, stream, x, (const int*)nullptr, gamma, beta, out, rows, d, g_trace_dev);
   ++g_kernel_launches;
 }
 template void layernorm<float>(const float*, const float*, const float*, float*, int, int, cudaStream_t);
@@ -156,7 +160,7 @@ void layernorm_gather(const float* x, const int* rows_idx, const float* gamma, c
                       cudaStream_t stream) {
   BW_CHECK(d <= 1536 && d % 4 == 0, "layernorm supports d <= 1536, d % 4 == 0");
   if (n <= 0) return;
-  launch_kernel(layernorm_kernel<T, true>, dim3(n), dim3(128), 0, stream, x, rows_idx, gamma, beta, out, n, d);
+  launch_kernel(layernorm_kernel<T, true>, dim3(n), dim3(128), 0, stream, x, rows_idx, gamma, beta, out, n, d, g_trace_dev);
   ++g_kernel_launches;
 }
 template void layernorm_gather<float>(const float*, const int*, const float*, const float*, float*, int, int, cudaStream_t);

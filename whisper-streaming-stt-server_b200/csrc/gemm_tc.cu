@@ -21,6 +21,7 @@ namespace bw {
 
 std::atomic<long long> g_kernel_launches{0};
 thread_local bool tl_pdl = false;
+unsigned long long* g_trace_dev = nullptr;
 
 namespace {
 
@@ -37,6 +38,7 @@ struct GemmDev {
   int a_z_bcast, b_z_bcast;
   int gelu, out_fp32, transposed;
   int accumulate, ksplit;
+  unsigned long long* trace;  // debug timeline (null = off)
 };
 
 template <int BN, int STAGES>
@@ -87,8 +89,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  unsigned long long* const trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? p.trace : nullptr;
+  if (threadIdx.x == 0) trace_mark(trace, (6u << 24) | 1);
   pdl_trigger();
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(trace, (6u << 24) | 2);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -226,6 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
   }
   __syncthreads();
+  if (threadIdx.x == 0) trace_mark(trace, (6u << 24) | 8);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
@@ -270,6 +276,9 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int total_kb = (p.K + BK - 1) / BK;
   const int kb0 = (int)((long long)ks * total_kb / KS);
   const int num_kb = (int)((long long)(ks + 1) * total_kb / KS) - kb0;  // >= 1: host guarantees KS <= total_kb
+  unsigned long long* const trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? p.trace : nullptr;
+  const unsigned ttag = (1u << 24) | (gridDim.x << 8);
+  if (threadIdx.x == 0) trace_mark(trace, ttag | 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -296,7 +305,9 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int zb = p.b_z_bcast ? 0 : z;
     for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_l2_3d(&tmB, (kb0 + kb) * BK, n0, zb);
   }
+  if (threadIdx.x == 0) trace_mark(trace, ttag | 1);
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(trace, ttag | 2);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -321,6 +332,7 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int s = kb % STAGES;
         const uint32_t phase = (kb / STAGES) & 1;
         mbar_wait(&full_bar[s], phase);
+        if (kb == 0) trace_mark(trace, ttag | 3);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
         const uint32_t sb = sa + L::kABytes;
@@ -339,6 +351,7 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int wq = warp & 3;
     const int row = wq * 32 + lane;
     mbar_wait(tmem_full_bar, 0);  // all MMAs retired -> the stage buffers are free to be overwritten
+    if (threadIdx.x == 64) trace_mark(trace, ttag | 4);
     tc_fence_after();
     float4* red = reinterpret_cast<float4*>(smem);
 #pragma unroll 1
@@ -354,8 +367,10 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
     tc_fence_before();
+    if (threadIdx.x == 64) trace_mark(trace, ttag | 5);
   }
   cluster_sync_all();  // every thread of every CTA in the cluster
+  if (threadIdx.x == 64) trace_mark(trace, ttag | 6);
   if (warp >= 2) {
     constexpr int RPC = BM / KS;  // tile rows reduced by this CTA
     const int t = threadIdx.x - 64;
@@ -414,10 +429,200 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   }
+  if (threadIdx.x == 64) trace_mark(trace, ttag | 7);
   cluster_sync_all();  // peers may still be reading this CTA's shared memory
+  if (threadIdx.x == 64) trace_mark(trace, ttag | 8);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Split-K v2 for the decoder step's row GEMMs (M = live hypotheses <= a few hundred, N a multiple of 64).
+// The in-situ timeline (tools/trace_step.py, profiles/r1_trace_notes.md) showed the v1 kernel spending 4-6 of its
+// ~10 us in the reduction: DSMEM *loads* plus the bias / residual loads sit on a serial latency chain.  Here
+//   * partial tiles are PUSHED: each epilogue thread reads its accumulator row from TMEM and stores it straight
+//     into the shared memory of the CTA that owns the row (st.shared::cluster, fire and forget);
+//   * one cluster barrier later every CTA sums its rows from LOCAL shared memory in fixed order (deterministic);
+//   * bias / residual for the elements a thread will finalise are loaded right after the dependency wait, i.e.
+//     underneath the TMA + MMA phase;
+//   * the first weight tiles are requested before griddepcontrol.wait (weights never change inside a step);
+//   * 128x64 tiles with a private 32 KB reduction area: 105 KB per CTA, two CTAs per SM, so N = 5120 at KS = 2
+//     (160 CTAs) or N = 1280 at KS = 8 (160 CTAs) are a single wave.
+constexpr int R_BN = 64, R_STAGES = 3;
+constexpr int R_A_BYTES = BM * BK * 2, R_B_BYTES = R_BN * BK * 2, R_STAGE_BYTES = R_A_BYTES + R_B_BYTES;
+constexpr int R_SLOT_OFF = R_STAGES * R_STAGE_BYTES;
+constexpr int R_SLOT_BYTES = BM * R_BN * 4;
+constexpr int R_BAR_OFF = R_SLOT_OFF + R_SLOT_BYTES;
+constexpr int R_SMEM_TOTAL = R_BAR_OFF + 128 + 1024;
+
+__device__ __forceinline__ void st_dsmem_f4(uint32_t remote_addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote_addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int KS>
+__global__ void __launch_bounds__(192, 2)
+gemm_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + R_BAR_OFF);
+  uint64_t* empty_bar = full_bar + R_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + R_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * R_BN, m0 = blockIdx.y * BM;
+  const int z = blockIdx.z / KS;
+  const int ks = (int)cluster_ctarank();  // == blockIdx.z % KS for cluster dims (1, 1, KS)
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int kb0 = (int)((long long)ks * total_kb / KS);
+  const int num_kb = (int)((long long)(ks + 1) * total_kb / KS) - kb0;  // >= 1: host guarantees KS <= total_kb
+  const int za = p.a_z_bcast ? 0 : z, zb = p.b_z_bcast ? 0 : z;
+  unsigned long long* const trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? p.trace : nullptr;
+  const unsigned ttag = (1u << 24) | (gridDim.x << 8);
+  if (threadIdx.x == 0) trace_mark(trace, ttag | 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < R_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, R_BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_trigger();
+  const int n_pre = min(num_kb, R_STAGES);
+  if (warp == 0 && lane == 0) {
+    for (int kb = 0; kb < n_pre; ++kb) {  // weight tiles of the first stages: in flight before the dependency resolves
+      mbar_arrive_expect_tx(&full_bar[kb], R_STAGE_BYTES);
+      tma_load_3d(smem + kb * R_STAGE_BYTES + R_A_BYTES, &tmB, &full_bar[kb], (kb0 + kb) * BK, n0, zb);
+    }
+    for (int kb = n_pre; kb < num_kb; ++kb) tma_prefetch_l2_3d(&tmB, (kb0 + kb) * BK, n0, zb);
+  }
+  if (threadIdx.x == 0) trace_mark(trace, ttag | 1);
+  pdl_wait();
+  if (threadIdx.x == 0) trace_mark(trace, ttag | 2);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % R_STAGES;
+        uint8_t* sa = smem + s * R_STAGE_BYTES;
+        if (kb >= n_pre) {
+          mbar_wait(&empty_bar[s], ((kb / R_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], R_STAGE_BYTES);
+          tma_load_3d(sa + R_A_BYTES, &tmB, &full_bar[s], (kb0 + kb) * BK, n0, zb);
+        }
+        tma_load_3d(sa, &tmA, &full_bar[s], (kb0 + kb) * BK, m0, za);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, R_BN, 0, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % R_STAGES;
+        mbar_wait(&full_bar[s], (kb / R_STAGES) & 1);
+        if (kb == 0) trace_mark(trace, ttag | 3);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * R_STAGE_BYTES);
+        const uint64_t adesc = umma_smem_desc_sw128(sa, 16, 1024);
+        const uint64_t bdesc = umma_smem_desc_sw128(sa + R_A_BYTES, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  }
+
+  // ---- epilogue threads: what this thread will finalise after the reduction ----
+  constexpr int RPC = BM / KS;      // tile rows owned (reduced + stored) by each CTA of the cluster
+  constexpr int NI = RPC / 8;       // float4 granules per epilogue thread (RPC rows x 16 granules / 128 threads)
+  const int t = threadIdx.x - 64;
+  float4 resv[NI], biasv[NI];
+  if (warp >= 2) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int e = t + i * 128;
+      const int gi = m0 + ks * RPC + (e >> 4), j0 = n0 + (e & 15) * 4;
+      const bool ok = gi < p.M && j0 < p.N;
+      biasv[i] = (p.bias && ok) ? __ldg(reinterpret_cast<const float4*>(p.bias + (long long)z * p.bias_zstride + j0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      resv[i] = (p.residual && ok) ? *reinterpret_cast<const float4*>(p.residual + (long long)z * p.res_zstride + (long long)gi * p.ldres + j0)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // ---- push my accumulator row into the owner CTA's reduction area: slots[ks][row % RPC][granule ^ (row & 15)] ----
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const int owner = row / RPC, lr = row % RPC;
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(smem + R_SLOT_OFF) + (uint32_t)((ks * RPC + lr) * 256)), "r"((uint32_t)owner));
+    mbar_wait(tmem_full_bar, 0);
+    if (threadIdx.x == 64) trace_mark(trace, ttag | 4);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < R_BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int f4 = c * 8 + g;
+        st_dsmem_f4(remote + (uint32_t)((f4 ^ (lr & 15)) << 4), __uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
+                    __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+      }
+    }
+    tc_fence_before();
+    if (threadIdx.x == 64) trace_mark(trace, ttag | 5);
+  }
+  cluster_sync_all();  // release/acquire: every partial row has landed in its owner's shared memory
+  if (threadIdx.x == 64) trace_mark(trace, ttag | 6);
+  if (warp >= 2) {
+    const float4* slots = reinterpret_cast<const float4*>(smem + R_SLOT_OFF);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int e = t + i * 128;
+      const int lr = e >> 4, c4 = e & 15;
+      const int gi = m0 + ks * RPC + lr, j0 = n0 + c4 * 4;
+      float4 acc = slots[(0 * RPC + lr) * 16 + (c4 ^ (lr & 15))];
+#pragma unroll
+      for (int pr = 1; pr < KS; ++pr) {
+        const float4 v = slots[(pr * RPC + lr) * 16 + (c4 ^ (lr & 15))];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      if (gi >= p.M || j0 >= p.N) continue;
+      float v[4] = {acc.x + biasv[i].x, acc.y + biasv[i].y, acc.z + biasv[i].z, acc.w + biasv[i].w};
+      if (p.gelu) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = gelu_erf_fast(v[q]);
+      }
+      v[0] += resv[i].x; v[1] += resv[i].y; v[2] += resv[i].z; v[3] += resv[i].w;
+      const long long oi = (long long)z * p.c_zstride + (long long)gi * p.ldc + j0;
+      if (p.out_fp32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + oi) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        uint2 w;
+        w.x = pack_bf16x2(v[0], v[1]);
+        w.y = pack_bf16x2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.C) + oi) = w;
+      }
+    }
+    if (threadIdx.x == 64) trace_mark(trace, ttag | 7);
+  }
+  if (warp == 1) {  // every epilogue thread read its TMEM row before the cluster barrier
+    tc_fence_after();
+    tmem_dealloc(tmem_base, R_BN);
   }
 }
 
@@ -724,6 +929,7 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
   p.a_z_bcast = a_bcast; p.b_z_bcast = b_bcast;
   p.gelu = g.gelu; p.out_fp32 = g.out_fp32; p.transposed = g.transposed;
   p.accumulate = g.accumulate;
+  p.trace = g_trace_dev;
   const int total_kb = (g.K + BK - 1) / BK;
   int ksplit = 1;
   if (g.accumulate) {
@@ -760,10 +966,48 @@ void launch_splitk(const GemmArgs& g, cudaStream_t stream) {
   p.a_z_bcast = a_bcast; p.b_z_bcast = b_bcast;
   p.gelu = g.gelu; p.out_fp32 = g.out_fp32; p.transposed = g.transposed;
   p.accumulate = 0; p.ksplit = KS;
+  p.trace = g_trace_dev;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.Z * KS);
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = KS;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tl_pdl ? 2 : 1;
+  BW_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  ++g_kernel_launches;
+}
+
+template <int KS>
+void launch_rows(const GemmArgs& g, cudaStream_t stream) {
+  static std::atomic<unsigned long long> attr_set{0};
+  auto kern = gemm_tc_rows_kernel<KS>;
+  int dev = 0;
+  BW_CUDA(cudaGetDevice(&dev));
+  if (!(attr_set.load() >> dev & 1ull)) {
+    BW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM_TOTAL));
+    attr_set.fetch_or(1ull << dev);
+  }
+  const bool a_bcast = (g.Z > 1 && g.a_zstride == 0), b_bcast = (g.Z > 1 && g.b_zstride == 0);
+  CUtensorMap tmA = make_operand_map(g.A, g.a_rows > g.M ? g.a_rows : g.M, g.K, g.lda, a_bcast ? 1 : g.Z, g.a_zstride, BM);
+  CUtensorMap tmB = make_operand_map(g.B, g.b_rows > g.N ? g.b_rows : g.N, g.K, g.ldb, b_bcast ? 1 : g.Z, g.b_zstride, R_BN);
+  GemmDev p;
+  p.C = g.C; p.bias = g.bias; p.residual = g.residual;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = g.ldc; p.ldres = g.ldres;
+  p.c_zstride = g.c_zstride; p.bias_zstride = g.bias_zstride; p.res_zstride = g.res_zstride;
+  p.a_z_bcast = a_bcast; p.b_z_bcast = b_bcast;
+  p.gelu = g.gelu; p.out_fp32 = g.out_fp32; p.transposed = 0;
+  p.accumulate = 0; p.ksplit = KS;
+  p.trace = g_trace_dev;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((g.N + R_BN - 1) / R_BN, (g.M + BM - 1) / BM, g.Z * KS);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = R_SMEM_TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -793,6 +1037,7 @@ void launch_pair(const GemmArgs& g, cudaStream_t stream) {
   p.c_zstride = g.c_zstride; p.bias_zstride = g.bias_zstride; p.res_zstride = g.res_zstride;
   p.a_z_bcast = a_bcast; p.b_z_bcast = b_bcast;
   p.gelu = g.gelu; p.out_fp32 = g.out_fp32; p.transposed = 0; p.accumulate = 0; p.ksplit = 1;
+  p.trace = nullptr;
   const int m_pairs = (g.M + 255) / 256, n_tiles = (g.N + 255) / 256;
   const int total = m_pairs * n_tiles * g.Z;
   static int sm_count = 0;
@@ -829,6 +1074,20 @@ void gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
     const long long tiles = mt * ((g.N + 127) / 128) * g.Z;
     const int total_kb = (g.K + BK - 1) / BK;
     static const bool no_splitk = getenv("B200W_NO_SPLITK") != nullptr;
+    static const bool no_rows = getenv("B200W_SPLITK_V1") != nullptr;
+    if (tiles < 120 && total_kb >= 4 && !no_splitk && !no_rows && !g.transposed && (g.N % 4) == 0 && (g.ldc % 4) == 0 &&
+        (!g.residual || (g.ldres % 4) == 0) && (!g.bias || (g.bias_zstride % 4) == 0)) {
+      // decoder-step row GEMMs: 128x64 tiles, push-reduced split-K; keep the whole grid co-resident (2 CTAs / SM,
+      // clusters packed per GPC: ~256 CTAs at KS = 8, ~288 at KS <= 4)
+      const long long tiles64 = mt * ((g.N + R_BN - 1) / R_BN) * g.Z;
+      int ks = 8;
+      while (ks > 2 && (tiles64 * ks > (ks == 8 ? 256 : 288) || total_kb < 2 * ks)) ks >>= 1;
+      if (tiles64 * ks <= 288 && total_kb >= ks) {
+        if (ks == 8) return launch_rows<8>(g, stream);
+        if (ks == 4) return launch_rows<4>(g, stream);
+        return launch_rows<2>(g, stream);
+      }
+    }
     if (tiles < 120 && total_kb >= 4 && !no_splitk) {
       int ks = 8;
       while (ks > 2 && (tiles * ks > 640 || total_kb < 2 * ks)) ks >>= 1;

@@ -185,6 +185,17 @@ class Engine:
     def bench_decoder_step(self, n_segments: int, n_group: int, context_len: int, iters: int):
         return self._bench(self.lib.bw_bench_decoder_step, n_segments, n_group, context_len, iters)
 
+    def trace_begin(self) -> None:
+        """Arm the debug timeline (run with B200W_NO_GRAPH=1)."""
+        L.check(self.lib.bw_debug_trace(self.handle, 1, None, 0, None), "bw_debug_trace")
+
+    def trace_end(self, cap: int = 1 << 16) -> np.ndarray:
+        """Disarm the timeline; returns records [n, 2] uint64: (smid << 32 | kernel << 24 | grid.x << 8 | phase, ns)."""
+        out = np.zeros((cap, 2), dtype=np.uint64)
+        n = C.c_int32()
+        L.check(self.lib.bw_debug_trace(self.handle, 0, out.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(n)), "bw_debug_trace")
+        return out[: n.value]
+
     def bench_pipeline(self, audios, n_group: int, n_steps: int) -> float:
         """Device-timed ms for mel -> encoder -> cross-KV -> n_steps decoder steps over `audios` (resident PCM)."""
         audios = [_as_f32(a) for a in audios]
