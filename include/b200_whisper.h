@@ -175,6 +175,7 @@ int bw_bench_pipeline(bw_engine*, const float* pcm_host, const int64_t* offsets,
 /* Debug timeline of the decoder step: enable != 0 arms a device buffer that the step's kernels append
  * (tag, globaltimer ns) records to; enable == 0 disarms it and copies up to `cap` records (2 x uint64 each:
  * smid << 32 | kernel id << 24 | grid.x << 8 | phase, then the timestamp) to `out`, count in *n_out.
+ * enable == 2 dumps the raw buffer instead (kernels that store into fixed slots).
  * Run with B200W_NO_GRAPH=1 (captured graphs keep the pointer they were captured with). */
 int bw_debug_trace(bw_engine*, int32_t enable, uint64_t* out, int32_t cap, int32_t* n_out);
 

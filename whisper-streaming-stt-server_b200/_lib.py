@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200whisper.so")
+LIB_PATH = os.environ.get("B200W_LIB", os.path.join(_HERE, "libb200whisper.so"))
 
 BW_MAX_TOKENS = 448
 BW_COMPUTE_BF16, BW_COMPUTE_FP32 = 0, 1

@@ -1198,16 +1198,24 @@ int bw_bench_cross_attention(bw_engine* e, int32_t n_segments, int32_t n_group, 
 
 int bw_debug_trace(bw_engine* e, int32_t enable, uint64_t* out, int32_t cap, int32_t* n_out) {
   BW_API_BEGIN
-  BW_CHECK(e, "null argument");
-  DeviceGuard dg(e->device);
-  std::lock_guard<std::mutex> g(e->gpu_mu);
+  // e may be null (kernel-level tools): then the current device is used
+  int cur_dev = 0;
+  BW_CUDA(cudaGetDevice(&cur_dev));
+  DeviceGuard dg(e ? e->device : cur_dev);
+  static std::mutex no_engine_mu;
+  std::lock_guard<std::mutex> g(e ? e->gpu_mu : no_engine_mu);
   BW_CUDA(cudaDeviceSynchronize());
   static DevBuf buf;
   const size_t bytes = (1 + 2 * (size_t)kTraceCap) * 8;
-  if (enable) {
+  if (enable == 1) {
     if (buf.bytes < bytes) buf.alloc(bytes);
     BW_CUDA(cudaMemset(buf.p, 0, bytes));
     g_trace_dev = buf.as<unsigned long long>();
+  } else if (enable == 2) {  // raw dump of the first `cap` records' worth of the buffer (fixed-slot users), then disarm
+    BW_CHECK(out && cap >= 0, "null argument");
+    unsigned long long* dev = g_trace_dev;
+    g_trace_dev = nullptr;
+    if (dev) BW_CUDA(cudaMemcpy(out, dev, std::min(bytes, (size_t)cap * 16), cudaMemcpyDeviceToHost));
   } else {
     BW_CHECK(out && n_out && cap >= 0, "null argument");
     unsigned long long* dev = g_trace_dev;
