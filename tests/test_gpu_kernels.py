@@ -107,6 +107,54 @@ def test_encoder_attention(impl, cfg):
     assert rel < 2e-2, f"impl {impl} cfg {cfg}: rel-L2 {rel}"
 
 
+def _attention_ref(qkv, batch, T, H):
+    d = 64 * H
+    q, k, v = [t.reshape(batch, T, H, 64).permute(0, 2, 1, 3).float() for t in qkv.split(d, dim=1)]
+    return torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(batch * T, d)
+
+
+@pytest.mark.parametrize("cfg", [(4, 1500, 8), (3, 700, 20), (2, 129, 3), (5, 1024, 7)])
+def test_encoder_attention_persistent_many_items(cfg):
+    """more (window, head, query-pair) items than SMs: every persistent CTA walks over several items, with ragged
+    last key / query tiles (the barrier phases and the K / V rings run across item boundaries)"""
+    L, lib = _lib()
+    batch, T, H = cfg
+    d = 64 * H
+    g = torch.Generator(device="cuda").manual_seed(100 + T + H)
+    qkv = torch.randn((batch * T, 3 * d), device="cuda", generator=g).bfloat16()
+    out = torch.full((batch * T, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    for _ in range(2):  # twice: results must not depend on what the previous launch left in TMEM / shared memory
+        L.check(lib.bw_attention_bf16(0, qkv.data_ptr(), out.data_ptr(), batch, T, H, None), "bw_attention_bf16")
+    torch.cuda.synchronize()
+    ref = _attention_ref(qkv, batch, T, H)
+    assert torch.isfinite(out.float()).all()
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    assert rel < 2e-2, f"cfg {cfg}: rel-L2 {rel}"
+    # per-window error too: a wrong item mapping would hide in the global norm of a large batch
+    per = (out.float() - ref).reshape(batch, -1).norm(dim=1) / ref.reshape(batch, -1).norm(dim=1)
+    assert per.max().item() < 2e-2, per
+
+
+def test_encoder_attention_lazy_rescale():
+    """scores whose row maximum keeps jumping by far more than 2^8 from key tile to key tile: the accumulators in
+    TMEM are rescaled in place (tcgen05.ld / st) whenever the reference maximum is raised"""
+    L, lib = _lib()
+    batch, T, H = 2, 1500, 4
+    d = 64 * H
+    g = torch.Generator(device="cuda").manual_seed(7)
+    qkv = torch.randn((batch * T, 3 * d), device="cuda", generator=g)
+    ramp = torch.linspace(0.5, 8.0, T, device="cuda").repeat(batch)[:, None]
+    qkv[:, :d] *= 3.0
+    qkv[:, d:2 * d] *= ramp  # later keys score higher: the running maximum grows all the way through
+    qkv = qkv.bfloat16()
+    out = torch.zeros((batch * T, d), device="cuda", dtype=torch.bfloat16)
+    L.check(lib.bw_attention_bf16(0, qkv.data_ptr(), out.data_ptr(), batch, T, H, None), "bw_attention_bf16")
+    torch.cuda.synchronize()
+    ref = _attention_ref(qkv, batch, T, H)
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    assert rel < 2e-2, f"rel-L2 {rel}"
+
+
 @pytest.mark.parametrize("shape", [(128, 1280, 1280), (100, 5120, 1280), (128, 1280, 5120), (300, 1280, 512), (7, 384, 1536), (1, 3840, 1280)])
 def test_gemm_cluster_splitk(shape):
     """few output tiles -> K is split over a thread-block cluster and reduced through DSMEM (decoder GEMMs)"""
