@@ -136,6 +136,17 @@ enum {
 /* Copies the PCM (host f32, 16 kHz, what ModelWorker._decode hands to transcribe, worker.py:119-125)
  * and computes the whole-call log-mel (global-max normalisation, padding = 30 s) on the device. */
 int bw_call_open(bw_engine*, const float* pcm, int64_t n_samples, bw_call** out);
+
+/* Raw ingest: the bytes the server receives -- PCM16 mono at `sample_rate` -- go to the device as
+ * they are (half the H2D bytes of the f32 path) and `pcm16_to_float32` + `ensure_16k` run there
+ * (stt_server/utils/audio.py:6-8 int16 -> float32 / 32768; :11-30 torchaudio sinc_interp_hann resampling to 16 kHz,
+ * lowpass_filter_width 6, rolloff 0.99), feeding the log-mel kernel directly.
+ * bw_engine_set_resampler registers the polyphase filter bank for one source rate: taps[new_freq][2*width+orig_freq]
+ * fp32 exactly as torchaudio's `_get_sinc_resample_kernel` builds it (orig/new reduced by their gcd); 16 kHz needs none. */
+int bw_engine_set_resampler(bw_engine*, int32_t sample_rate, int32_t orig_freq, int32_t new_freq, int32_t width, const float* taps);
+int bw_call_open_pcm16(bw_engine*, const int16_t* pcm, int64_t n_samples, int32_t sample_rate, bw_call** out);
+/* stage-level: resampled float32 audio back to the host (out holds ceil(new * n / orig) samples; count in *n_out) */
+int bw_resample_pcm16(bw_engine*, const int16_t* pcm, int64_t n_samples, int32_t sample_rate, float* out, int64_t* n_out);
 int bw_call_content_frames(bw_call*, int32_t* out);
 /* Encoder + batched decoder for the 30 s window starting at mel frame `seek`. Blocking. */
 int bw_call_decode(bw_call*, int32_t seek, const bw_decode_opts* opts, bw_result* out);

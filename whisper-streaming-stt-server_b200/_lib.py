@@ -76,6 +76,9 @@ SIGNATURES = {
     "bw_engine_retain": (C.c_int, [C.c_void_p]),
     "bw_engine_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "bw_call_open": (C.c_int, [C.c_void_p, c_f32_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "bw_engine_set_resampler": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32_p]),
+    "bw_call_open_pcm16": (C.c_int, [C.c_void_p, C.POINTER(C.c_int16), C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "bw_resample_pcm16": (C.c_int, [C.c_void_p, C.POINTER(C.c_int16), C.c_int64, C.c_int32, c_f32_p, C.POINTER(C.c_int64)]),
     "bw_call_content_frames": (C.c_int, [C.c_void_p, c_i32_p]),
     "bw_call_decode": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(DecodeOptsC), C.POINTER(ResultC)]),
     "bw_call_detect_language": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(LangResultC)]),

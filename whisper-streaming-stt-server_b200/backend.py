@@ -192,6 +192,56 @@ class B200WhisperBackend:
     def transcribe(self, audio: Any, options: Dict[str, Any]) -> Tuple[List[Segment], BackendInfo]:
         opts = self._normalize_options(options)
         result = self.transcribe_raw(audio, **opts)
+        return self._to_segments(result)
+
+    def transcribe_pcm16(self, pcm: Any, sample_rate: int, options: Dict[str, Any]) -> Tuple[List[Segment], BackendInfo]:
+        """Side door for the raw stream bytes: `pcm` = PCM16 LE mono bytes (or an int16 array) at
+        `sample_rate` Hz, exactly what `ModelWorker._decode` receives (worker.py:98-121).  `pcm16_to_float32` and
+        `ensure_16k` (utils/audio.py:6-30) run on the device in front of the log-mel kernel; results are the ones
+        `transcribe(ensure_16k(pcm16_to_float32(pcm), sample_rate), options)` gives."""
+        if int(sample_rate) != sample_rate or int(sample_rate) <= 0:
+            raise ValueError(f"sample_rate must be a positive integer, got {sample_rate!r}")
+        opts = self._normalize_options(options)
+        result = self.transcribe_raw(pcm, _sample_rate=int(sample_rate), **opts)
+        return self._to_segments(result)
+
+    def transcribe_many(self, audios: Sequence[Any], options: Any, sample_rates: Optional[Sequence[Optional[int]]] = None
+                        ) -> List[Tuple[List[Segment], BackendInfo]]:
+        """Explicit cross-session batch at the registry seam: what the reference declares as
+        `decode_batch_window_ms` / `max_decode_batch_size` (config/server.yaml:48-49) but never implements.  All
+        calls are handed to the engine together, so their windows share encoder launches and every decoder step;
+        one worker thread can serve a whole batch instead of one pool handle per concurrent decode.
+        `options`: one dict for all, or one per audio.  `sample_rates[i]` not None -> audios[i] is PCM16 at that rate.
+        Returns results in input order; the first failure is raised after all calls have finished."""
+        n = len(audios)
+        opt_list = [options] * n if isinstance(options, dict) else list(options)
+        rates = [None] * n if sample_rates is None else list(sample_rates)
+        if len(opt_list) != n or len(rates) != n:
+            raise ValueError("options / sample_rates must match audios in length")
+        results: List[Any] = [None] * n
+        errors: List[Optional[BaseException]] = [None] * n
+
+        def work(i: int) -> None:
+            try:
+                if rates[i] is None:
+                    results[i] = self.transcribe(audios[i], opt_list[i])
+                else:
+                    results[i] = self.transcribe_pcm16(audios[i], rates[i], opt_list[i])
+            except BaseException as exc:  # noqa: BLE001 - re-raised below
+                errors[i] = exc
+
+        # blocking C calls release the GIL; the engine's scheduler coalesces whatever is pending into one batch
+        threads = [threading.Thread(target=work, args=(i,), name=f"b200w-many-{i}") for i in range(n)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for exc in errors:
+            if exc is not None:
+                raise exc
+        return results
+
+    def _to_segments(self, result: dict) -> Tuple[List[Segment], BackendInfo]:
         segments: List[Segment] = []
         for seg in result.get("segments", []):
             segments.append(Segment(float(seg.get("start", 0.0)), float(seg.get("end", 0.0)), str(seg.get("text", "") or "")))
@@ -212,10 +262,15 @@ class B200WhisperBackend:
                        best_of: Optional[int] = None, patience: Optional[float] = None,
                        length_penalty: Optional[float] = None, **ignored) -> dict:
         v = self.vocab
-        if hasattr(audio, "detach"):
-            audio = audio.detach().cpu().numpy()
-        audio = np.ascontiguousarray(audio, dtype=np.float32).reshape(-1)
-        if audio.size == 0:
+        sample_rate = ignored.pop("_sample_rate", None)  # not None: `audio` is PCM16 at that rate (transcribe_pcm16)
+        if sample_rate is None:
+            if hasattr(audio, "detach"):
+                audio = audio.detach().cpu().numpy()
+            audio = np.ascontiguousarray(audio, dtype=np.float32).reshape(-1)
+            n_in = audio.size
+        else:
+            n_in = len(audio) // 2 if isinstance(audio, (bytes, bytearray, memoryview)) else int(np.asarray(audio).size)
+        if n_in == 0:
             return {"text": "", "segments": [], "language": language or "", "language_probability": None}
         if isinstance(temperature, (list, tuple)):
             if len(temperature) > 1:
@@ -229,7 +284,7 @@ class B200WhisperBackend:
         if beam is not None and not (1 <= beam <= 8):
             raise ValueError(f"beam_size must be in [1, 8], got {beam_size}")
 
-        with self.engine.open_call(audio) as call:
+        with self.engine.open_call(audio, sample_rate) as call:
             content_frames = call.content_frames
             language_probability = None
             if language is None:

@@ -490,6 +490,31 @@ void compute_call_mel(bw_engine* e, bw_call* c, const float* pcm, long long n) {
   e->stat_h2d += n * 4;
 }
 
+// raw ingest: H2D of the int16 samples, conversion (+ resampling) into the call's f32 PCM buffer, then the log-mel
+const Resampler* find_resampler(bw_engine* e, int sample_rate) {
+  if (sample_rate == 16000) return nullptr;
+  std::lock_guard<std::mutex> g(e->resampler_mu);
+  auto it = e->resamplers.find(sample_rate);
+  if (it == e->resamplers.end())
+    throw std::invalid_argument("no resampler registered for " + std::to_string(sample_rate) + " Hz (bw_engine_set_resampler)");
+  return it->second.get();
+}
+long long resampled_length(const Resampler* r, long long n) {
+  return r ? ((long long)r->nw * n + r->orig - 1) / r->orig : n;
+}
+// enqueue on `st`: pcm16 (host) -> staging -> f32 PCM at 16 kHz in `dst`
+void ingest_pcm16(bw_engine* e, int front_idx, cudaStream_t st, const int16_t* pcm, long long n, const Resampler* r, float* dst, long long n16) {
+  DevBuf& stage = e->front_pcm16[front_idx];
+  if (stage.bytes < (size_t)n * 2 + 16) {
+    BW_CUDA(cudaStreamSynchronize(st));  // earlier users of the old staging buffer
+    stage.alloc(std::max((size_t)n * 2 + 16, (size_t)4 << 20));
+  }
+  BW_CUDA(cudaMemcpyAsync(stage.p, pcm, (size_t)n * 2, cudaMemcpyHostToDevice, st));
+  if (r) pcm16_resample(stage.as<int16_t>(), n, r->taps.as<float>(), r->ranges.as<int2>(), r->orig, r->nw, r->K, r->width, dst, n16, st);
+  else pcm16_to_f32(stage.as<int16_t>(), n, dst, st);
+  e->stat_h2d += n * 2;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -809,6 +834,95 @@ int bw_call_open(bw_engine* e, const float* pcm, int64_t n_samples, bw_call** ou
   BW_CUDA(cudaEventCreateWithFlags(&c->mel_done, cudaEventDisableTiming));
   compute_call_mel(e, c.get(), pcm, n_samples);
   *out = c.release();
+  BW_API_END
+}
+
+int bw_engine_set_resampler(bw_engine* e, int32_t sample_rate, int32_t orig_freq, int32_t new_freq, int32_t width, const float* taps) {
+  BW_API_BEGIN
+  BW_CHECK(e && taps, "null argument");
+  BW_CHECK(sample_rate > 0 && sample_rate != 16000, "16 kHz needs no resampler");
+  BW_CHECK(orig_freq > 0 && new_freq > 0 && width > 0 && orig_freq <= 4096 && new_freq <= 4096 && width <= 4096, "bad filter geometry");
+  BW_CHECK((long long)sample_rate * new_freq == 16000LL * orig_freq, "orig_freq / new_freq must equal sample_rate / 16000");
+  DeviceGuard dg(e->device);
+  auto r = std::make_unique<Resampler>();
+  r->orig = orig_freq; r->nw = new_freq; r->width = width; r->K = 2 * width + orig_freq;
+  std::vector<int2> ranges(new_freq);
+  for (int i = 0; i < new_freq; ++i) {
+    int lo = r->K, hi = 0;
+    for (int k = 0; k < r->K; ++k)
+      if (fabsf(taps[(size_t)i * r->K + k]) >= 1e-20f) { lo = std::min(lo, k); hi = std::max(hi, k + 1); }
+    if (lo > hi) { lo = 0; hi = 0; }
+    ranges[i] = make_int2(lo, hi);
+  }
+  r->taps.alloc((size_t)new_freq * r->K * 4);
+  r->ranges.alloc((size_t)new_freq * sizeof(int2));
+  BW_CUDA(cudaMemcpy(r->taps.p, taps, (size_t)new_freq * r->K * 4, cudaMemcpyHostToDevice));
+  BW_CUDA(cudaMemcpy(r->ranges.p, ranges.data(), (size_t)new_freq * sizeof(int2), cudaMemcpyHostToDevice));
+  std::lock_guard<std::mutex> g(e->resampler_mu);
+  BW_CHECK(e->resamplers.find(sample_rate) == e->resamplers.end(), "resampler already registered for this rate");
+  e->resamplers[sample_rate] = std::move(r);
+  BW_API_END
+}
+
+int bw_call_open_pcm16(bw_engine* e, const int16_t* pcm, int64_t n_in, int32_t sample_rate, bw_call** out) {
+  BW_API_BEGIN
+  BW_CHECK(e && pcm && out, "null argument");
+  BW_CHECK(e->state == 1, "engine not finalized");
+  BW_CHECK(n_in >= 1, "empty audio");
+  DeviceGuard dg(e->device);
+  const Resampler* r = find_resampler(e, sample_rate);
+  const long long n_samples = resampled_length(r, n_in);
+  BW_CHECK(n_samples >= 1, "empty audio after resampling");
+  auto c = std::make_unique<bw_call>();
+  c->eng = e;
+  c->n_samples = n_samples;
+  c->total_frames = (int)((n_samples + 480000) / 160);
+  c->content_frames = c->total_frames - 3000;
+  c->n_real = (int)std::min<long long>(c->total_frames, (n_samples + 200 + 159) / 160);
+  {
+    std::lock_guard<std::mutex> g(e->call_mu);
+    if (n_samples <= e->call_pcm_cap && c->n_real <= e->call_ld && !e->call_pool.empty()) {
+      c->buf = e->call_pool.back();
+      e->call_pool.pop_back();
+    }
+  }
+  if (!c->buf.pcm) {
+    CallBuf b;
+    b.ld = (c->n_real + 15) / 16 * 16;
+    b.pcm_cap = n_samples;
+    BW_CUDA(cudaMalloc(reinterpret_cast<void**>(&b.pcm), (size_t)(n_samples + 4) * 4));
+    BW_CUDA(cudaMalloc(reinterpret_cast<void**>(&b.logmel), (size_t)e->dims.n_mels * b.ld * 4));
+    BW_CUDA(cudaMalloc(reinterpret_cast<void**>(&b.gmax), 4));
+    c->buf = b;
+  }
+  BW_CUDA(cudaEventCreateWithFlags(&c->mel_done, cudaEventDisableTiming));
+  {
+    const unsigned idx = e->front_rr.fetch_add(1) % bw_engine::kFrontStreams;
+    std::lock_guard<std::mutex> g(e->front_mu[idx]);
+    cudaStream_t st = e->front[idx];
+    ingest_pcm16(e, (int)idx, st, pcm, n_in, r, c->buf.pcm, n_samples);
+    mel_power(c->buf.pcm, n_samples, 480000, e->mel_tables.as<float>(), e->mel_filters.as<float>(), e->mel_ranges.as<int2>(),
+              e->dims.n_mels, c->buf.logmel, c->buf.ld, c->n_real, c->total_frames, c->buf.gmax, st);
+    BW_CUDA(cudaEventRecord(c->mel_done, st));
+  }
+  *out = c.release();
+  BW_API_END
+}
+
+int bw_resample_pcm16(bw_engine* e, const int16_t* pcm, int64_t n_in, int32_t sample_rate, float* out, int64_t* n_out) {
+  BW_API_BEGIN
+  BW_CHECK(e && pcm && out && n_out, "null argument");
+  BW_CHECK(n_in >= 1, "empty audio");
+  DeviceGuard dg(e->device);
+  const Resampler* r = find_resampler(e, sample_rate);
+  const long long n16 = resampled_length(r, n_in);
+  DevBuf dst;
+  dst.alloc((size_t)(n16 + 4) * 4);
+  std::lock_guard<std::mutex> g(e->front_mu[0]);
+  ingest_pcm16(e, 0, e->front[0], pcm, n_in, r, dst.as<float>(), n16);
+  BW_CUDA(cudaMemcpyAsync(out, dst.p, (size_t)n16 * 4, cudaMemcpyDeviceToHost, e->front[0]));
+  BW_CUDA(cudaStreamSynchronize(e->front[0]));
+  *n_out = n16;
   BW_API_END
 }
 

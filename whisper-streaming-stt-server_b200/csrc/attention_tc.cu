@@ -482,6 +482,7 @@ __device__ __forceinline__ float v4_chunk_max(const uint32_t* r, int c, int kval
   return mx;
 }
 
+#ifdef V6_MAX4
 // Row maximum over 64 scores with four independent accumulators (a single FMNMX3 chain is 32 dependent ops deep).
 template <bool MASK>
 __device__ __forceinline__ float v6_row_max(const uint32_t* sv, int kvalid) {
@@ -497,6 +498,8 @@ __device__ __forceinline__ float v6_row_max(const uint32_t* sv, int kvalid) {
   }
   return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
 }
+#endif
+#ifdef V6_NARROW_PP
 // The exponential of a row segment in three separately callable phases (see the ping-pong comment in v6): only the
 // MUFU block needs the XU pipe; the FFMA2 block before it and the pack / store block after it overlap the OTHER
 // query tile's MUFU block.
@@ -529,6 +532,7 @@ __device__ __forceinline__ void v6_exp_store(const uint32_t* sv, int kvalid, uin
     st_shared_v4(prow + (uint32_t)((g ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
   }
 }
+#endif
 
 // One tile row segment (64 scores) -> 64 truncated-bf16 probabilities in the swizzled P tile, in three explicit
 // phases so that the 64 MUFU.EX2 of a warp issue back to back (in-order issue: a PRMT scheduled right behind its

@@ -98,6 +98,12 @@ struct DecGroup {
 };
 constexpr int kMaxGroups = 4;
 
+// polyphase filter bank of one source sample rate (bw_engine_set_resampler)
+struct Resampler {
+  int orig = 0, nw = 0, width = 0, K = 0;
+  DevBuf taps, ranges;
+};
+
 struct CallBuf {
   float* pcm = nullptr;     // device
   float* logmel = nullptr;  // device [n_mels][ld]
@@ -157,6 +163,9 @@ struct bw_engine {
   static constexpr int kFrontStreams = 4;
   cudaStream_t front[kFrontStreams]{};
   std::mutex front_mu[kFrontStreams];
+  bw::DevBuf front_pcm16[kFrontStreams];  // int16 staging of the raw-ingest path (serialised by front_mu / stream order)
+  std::mutex resampler_mu;
+  std::unordered_map<int, std::unique_ptr<bw::Resampler>> resamplers;  // by source sample rate
   std::atomic<unsigned> front_rr{0};
   std::mutex gpu_mu;       // serialises users of `stream` and the activation buffers
 

@@ -20,6 +20,15 @@ template <typename T>
 void mel_window(const float* logmel, int ld, int n_real, const int* gmax_bits, int n_mels, int seek, int segment_size,
                 T* A1, cudaStream_t stream);
 
+// ---- ingest.cu ----
+// out[i] = pcm[i] / 32768  (stt_server/utils/audio.py:6-8)
+void pcm16_to_f32(const int16_t* pcm, long long n, float* out, cudaStream_t stream);
+// Polyphase Hann-windowed-sinc resampling of int16 PCM to float32 (utils/audio.py:11-30 -> torchaudio resample):
+// out[f * nw + i] = sum_k taps[i][k] * pcm[f * orig - width + k] / 32768, n_out = ceil(nw * n / orig).
+// ranges[i] = [lo, hi) taps of phase i that are not negligible (< 1e-20 in magnitude: the clamped window tails).
+void pcm16_resample(const int16_t* pcm, long long n, const float* taps, const int2* ranges, int orig, int nw, int K, int width,
+                    float* out, long long n_out, cudaStream_t stream);
+
 // ---- elementwise.cu ----
 // out[r][:] = LayerNorm(x[r][:]) * gamma + beta   (fp32 statistics, eps 1e-5)
 template <typename T>

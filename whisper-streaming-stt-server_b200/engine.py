@@ -19,15 +19,35 @@ def _as_f32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def _as_i16(pcm) -> np.ndarray:
+    """bytes / bytearray / memoryview (PCM16 LE, what the gRPC stream carries) or an int16 array"""
+    if isinstance(pcm, (bytes, bytearray, memoryview)):
+        if len(pcm) % 2:
+            raise ValueError("PCM16 byte length must be even")
+        return np.frombuffer(pcm, dtype="<i2")
+    a = np.asarray(pcm)
+    if a.dtype != np.int16:
+        raise TypeError(f"PCM16 samples must be int16, got {a.dtype}")
+    return np.ascontiguousarray(a.reshape(-1))
+
+
 class Call:
     """One `transcribe()` call: PCM resident on the device + its whole-call log-mel."""
 
-    def __init__(self, engine: "Engine", audio: np.ndarray):
+    def __init__(self, engine: "Engine", audio, sample_rate: Optional[int] = None):
+        """`audio`: float32 at 16 kHz (sample_rate None), or PCM16 bytes / int16 samples at `sample_rate` Hz
+        (converted and resampled on the device)."""
         self.engine = engine
         self._h = C.c_void_p()
-        audio = _as_f32(audio)
-        L.check(engine.lib.bw_call_open(engine.handle, audio.ctypes.data_as(L.c_f32_p), audio.size, C.byref(self._h)),
-                "bw_call_open")
+        if sample_rate is None:
+            audio = _as_f32(audio)
+            L.check(engine.lib.bw_call_open(engine.handle, audio.ctypes.data_as(L.c_f32_p), audio.size, C.byref(self._h)),
+                    "bw_call_open")
+        else:
+            pcm = _as_i16(audio)
+            engine.ensure_resampler(int(sample_rate))
+            L.check(engine.lib.bw_call_open_pcm16(engine.handle, pcm.ctypes.data_as(C.POINTER(C.c_int16)), pcm.size, int(sample_rate),
+                                                  C.byref(self._h)), "bw_call_open_pcm16")
         n = C.c_int32()
         L.check(engine.lib.bw_call_content_frames(self._h, C.byref(n)), "bw_call_content_frames")
         self.content_frames = n.value
@@ -83,6 +103,8 @@ class Engine:
         self.device_index = device_index
         self.handle = C.c_void_p()
         self._lock = threading.Lock()
+        self._resampler_lock = threading.Lock()
+        self._resamplers = set()
         cd = L.ModelDimsC(*[getattr(dims, f) for f, _ in L.ModelDimsC._fields_])
         cfg = L.EngineConfigC(device_index, L.BW_COMPUTE_FP32 if compute == "fp32" else L.BW_COMPUTE_BF16, max_segments,
                               max_sequences, max_encoder_batch, flags)
@@ -159,8 +181,8 @@ class Engine:
                 "bw_decode_logits")
         return out
 
-    def open_call(self, audio) -> Call:
-        return Call(self, audio)
+    def open_call(self, audio, sample_rate: Optional[int] = None) -> Call:
+        return Call(self, audio, sample_rate)
 
     def stats(self) -> Dict[str, int]:
         buf = (C.c_int64 * len(L.STAT_NAMES))()
@@ -184,6 +206,33 @@ class Engine:
 
     def bench_decoder_step(self, n_segments: int, n_group: int, context_len: int, iters: int):
         return self._bench(self.lib.bw_bench_decoder_step, n_segments, n_group, context_len, iters)
+
+    def ensure_resampler(self, sample_rate: int) -> None:
+        """Register the ensure_16k filter bank of `sample_rate` with the engine (once per rate)."""
+        if sample_rate == 16000:
+            return
+        with self._resampler_lock:
+            if sample_rate in self._resamplers:
+                return
+            from .ingest import resample_taps
+
+            orig, new, width, taps = resample_taps(sample_rate)
+            L.check(self.lib.bw_engine_set_resampler(self.handle, sample_rate, orig, new, width, taps.ctypes.data_as(L.c_f32_p)),
+                    "bw_engine_set_resampler")
+            self._resamplers.add(sample_rate)
+
+    def resample_pcm16(self, pcm, sample_rate: int) -> np.ndarray:
+        """Stage-level: PCM16 at `sample_rate` -> float32 at 16 kHz, computed on the device."""
+        from .ingest import resampled_length
+
+        pcm = _as_i16(pcm)
+        self.ensure_resampler(int(sample_rate))
+        out = np.empty(resampled_length(pcm.size, sample_rate), dtype=np.float32)
+        n = C.c_int64()
+        L.check(self.lib.bw_resample_pcm16(self.handle, pcm.ctypes.data_as(C.POINTER(C.c_int16)), pcm.size, int(sample_rate),
+                                           out.ctypes.data_as(L.c_f32_p), C.byref(n)), "bw_resample_pcm16")
+        assert n.value == out.size, (n.value, out.size)
+        return out
 
     def trace_begin(self) -> None:
         """Arm the debug timeline (run with B200W_NO_GRAPH=1)."""
