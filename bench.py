@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--model", default="large-v3")
     ap.add_argument("--sessions", type=int, default=128, help="concurrent sessions per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streaming-seconds", type=float, default=10.0,
+                    help="length of the real-time streaming-session run reported under `streaming` (0 = skip)")
+    ap.add_argument("--streaming-sessions", type=int, default=0, help="sessions per GPU in that run (0 = 3 x --sessions)")
     ap.add_argument("--cpu-threads", type=int, default=0)
     return ap.parse_args()
 
@@ -291,6 +294,20 @@ def run_b200(args):
     lat_sorted = sorted(lat)
     p95 = lat_sorted[max(0, int(np.ceil(0.95 * len(lat_sorted))) - 1)] if lat_sorted else None  # nearest rank
 
+    # ---- streaming sessions in real time (tools/stream_bench.py): the orchestrator's partial / final schedule ----
+    streaming = None
+    if args.streaming_seconds > 0:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from stream_bench import run_stream_sim
+
+        n_stream = args.streaming_sessions or 3 * S
+        while len(handles) < n_stream:
+            handles.append(B200WhisperBackend(spec, f"cuda:{local}", "bfloat16"))
+        barrier_max(dist, local, 0.0)
+        streaming = run_stream_sim(handles[:n_stream], args.streaming_seconds, seed=rank)
+        streaming["note"] = ("real-time pacing; decodes bounded by DecodingOptions.sample_len = 3.5 tokens per audio second + 4 "
+                             "(random weights never emit EOT); per GPU, rank 0 shown")
+
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (decoder cross-attention, HBM-bound), timed live ----
@@ -327,6 +344,8 @@ def run_b200(args):
                      "algorithmic_bytes_per_launch": xa_bytes},
         "stages": stages,
     }
+    if streaming is not None:
+        out["streaming"] = streaming
     if world == 1 and not args.no_cpu_baseline:
         dt, cores = cpu_oracle_window(state, args.model, 6.0, threads=args.cpu_threads)
         out["cpu_baseline"] = {"value": 6.0 / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",

@@ -260,7 +260,7 @@ class B200WhisperBackend:
                        condition_on_previous_text: bool = True, initial_prompt: Optional[str] = None,
                        language: Optional[str] = None, task: Optional[str] = None, beam_size: Optional[int] = None,
                        best_of: Optional[int] = None, patience: Optional[float] = None,
-                       length_penalty: Optional[float] = None, **ignored) -> dict:
+                       length_penalty: Optional[float] = None, sample_len: Optional[int] = None, **ignored) -> dict:
         v = self.vocab
         sample_rate = ignored.pop("_sample_rate", None)  # not None: `audio` is PCM16 at that rate (transcribe_pcm16)
         if sample_rate is None:
@@ -322,8 +322,10 @@ class B200WhisperBackend:
                 initial = list(sot_sequence)
                 if prompt:
                     initial = [v.sot_prev] + prompt[-(n_ctx // 2 - 1):] + initial
+                # sample_len: upstream DecodingOptions.sample_len (default n_text_ctx // 2); not reachable through
+                # transcribe() -- torch_whisper.py:78-110 drops it -- but tools use it to bound synthetic decodes
                 res = call.decode(seek, initial, initial.index(v.sot), beam, patience, length_penalty,
-                                  without_timestamps=without_ts)
+                                  sample_len=int(sample_len or 0), without_timestamps=without_ts)
                 tokens: List[int] = res["tokens"]
                 if no_speech_threshold is not None:
                     should_skip = res["no_speech_prob"] > no_speech_threshold
