@@ -183,6 +183,14 @@ int bw_bench_decoder_step(bw_engine*, int32_t n_segments, int32_t n_group, int32
 int bw_bench_pipeline(bw_engine*, const float* pcm_host, const int64_t* offsets, const int64_t* lengths,
                       int32_t n_segments, int32_t n_group, int32_t n_steps, float* ms_out);
 
+/* Test hook for the decoder LayerNorm fusion (device pointers): producer row GEMM x = res + A.Wp^T + bp (also
+ * emits bf16(x) and per-row LayerNorm partials) then consumer row GEMM out = [gelu](LayerNorm(x; gamma, beta).Wc^T + bc)
+ * with gamma folded into Wc.  A == NULL skips the producer (x = res).  A bf16 [M, Kp], Wp bf16 [d, Kp], Wc fp32 [N, d];
+ * x_out fp32 [M, d], out fp32 [M, N]; d % 64 == 0, N % 64 == 0. */
+int bw_test_ln_chain(const void* A, const void* Wp, const float* bp, const float* res, const float* gamma, const float* beta,
+                     const float* Wc, const float* bc, int32_t M, int32_t d, int32_t Kp, int32_t N, int32_t gelu, float* x_out,
+                     float* out, void* stream);
+
 /* Debug timeline of the decoder step: enable != 0 arms a device buffer that the step's kernels append
  * (tag, globaltimer ns) records to; enable == 0 disarms it and copies up to `cap` records (2 x uint64 each:
  * smid << 32 | kernel id << 24 | grid.x << 8 | phase, then the timestamp) to `out`, count in *n_out.

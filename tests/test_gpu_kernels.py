@@ -220,3 +220,42 @@ def test_gemm_throughput_report():
         torch.cuda.synchronize()
         ms_ref = t0.elapsed_time(t1) / 10
         print(f"GEMM {M}x{N}x{K}: ours {2 * M * N * K / ms / 1e9:.0f} TFLOP/s ({ms:.3f} ms), cuBLAS {2 * M * N * K / ms_ref / 1e9:.0f} TFLOP/s")
+
+
+@pytest.mark.parametrize("shape", [(128, 1280, 1280, 3840), (37, 1280, 5120, 1280), (300, 384, 384, 1536), (128, 1280, 0, 5120), (5, 512, 512, 512)])
+@pytest.mark.parametrize("gelu", [False, True])
+def test_layernorm_fused_row_gemms(shape, gelu):
+    """decoder LayerNorm fusion: producer GEMM (x = res + A.Wp^T + b, plus bf16(x) and LayerNorm partials) feeding a
+    consumer GEMM whose weight carries gamma and whose epilogue applies mean / rstd, vs torch LayerNorm + Linear"""
+    L, lib = _lib()
+    M, d, Kp, N = shape
+    g = torch.Generator(device="cuda").manual_seed(M + d + Kp + N)
+    res = torch.randn((M, d), device="cuda", generator=g) * 2.0 + 0.7          # non-zero mean rows
+    res[:, 5] += 30.0                                                            # an outlier channel, as in real residual streams
+    gamma = 1.0 + 0.3 * torch.randn((d,), device="cuda", generator=g)
+    beta = 0.2 * torch.randn((d,), device="cuda", generator=g)
+    Wc = torch.randn((N, d), device="cuda", generator=g) * 0.05
+    bc = torch.randn((N,), device="cuda", generator=g) * 0.1
+    if Kp:
+        A = (torch.randn((M, Kp), device="cuda", generator=g) * 0.5).bfloat16()
+        Wp = (torch.randn((d, Kp), device="cuda", generator=g) * 0.05).bfloat16()
+        bp = torch.randn((d,), device="cuda", generator=g) * 0.1
+        x_ref = res + A.float() @ Wp.float().T + bp
+    else:
+        A = Wp = bp = None
+        x_ref = res.clone()
+    x_out = torch.empty((M, d), device="cuda")
+    out = torch.empty((M, N), device="cuda")
+    torch.cuda.synchronize()
+    ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    L.check(lib.bw_test_ln_chain(ptr(A), ptr(Wp), ptr(bp), ptr(res), ptr(gamma), ptr(beta), ptr(Wc), ptr(bc), M, d, Kp, N, int(gelu),
+                                 ptr(x_out), ptr(out), None), "bw_test_ln_chain")
+    torch.cuda.synchronize()
+    assert ((x_out - x_ref).norm() / x_ref.norm()).item() < 2e-3
+    # reference on the same bf16 operand precision the product path has (bf16 activations and weights, fp32 accumulate)
+    y = torch.nn.functional.layer_norm(x_ref, (d,), gamma, beta, 1e-5)
+    ref = y.bfloat16().float() @ Wc.bfloat16().float().T + bc
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    rel = ((out - ref).norm() / ref.norm()).item()
+    assert rel < 1.5e-2, f"{shape} gelu={gelu}: rel-L2 {rel}"

@@ -96,6 +96,7 @@ SIGNATURES = {
                                     C.c_int32, c_f32_p]),
     "bw_bench_decoder_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32_p,
                                         C.POINTER(C.c_double)]),
+    "bw_test_ln_chain": (C.c_int, [C.c_void_p] * 8 + [C.c_int32] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bw_debug_trace": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64), C.c_int32, c_i32_p]),
 }
 

@@ -17,6 +17,7 @@ void engine_decoder_layers(bw_engine* e, DecGroup& G, int R, int n_groups, int m
                            const int* row_pos, const int* row_tok, const int* row_bpos, const int* grp_first, const int* grp_n,
                            const int* grp_x, const int* lrow_src);
 void engine_init_requests(bw_engine* e, const int* init_dev, int n);
+void engine_fold_layernorms(bw_engine* e);
 }  // namespace bw
 
 using namespace bw;
@@ -550,6 +551,7 @@ int bw_engine_create(const bw_model_dims* dims, const bw_engine_config* cfg, bw_
   e->device = cfg->cuda_device;
   e->fp32 = cfg->compute == BW_COMPUTE_FP32;
   e->force_simt = (cfg->flags & BW_FLAG_FORCE_SIMT_GEMM) != 0;
+  e->fuse_ln = !e->fp32 && !e->force_simt && (dims->n_text_state % 64) == 0 && getenv("B200W_NO_LN_FUSION") == nullptr;
   BW_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   for (auto& s : e->front) BW_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   e->staging.alloc((size_t)64 << 20);
@@ -642,6 +644,7 @@ int bw_engine_finalize(bw_engine* e) {
       }
     BW_CUDA(cudaMemcpy(e->w.enc_pos, pe.data(), pe.size() * 4, cudaMemcpyHostToDevice));
   }
+  engine_fold_layernorms(e);
   const size_t ts = e->fp32 ? 4 : 2;
   const size_t dm = d.n_audio_state;
   const size_t cross_slot = (size_t)d.n_text_layer * d.n_audio_ctx * 2 * dm * ts;
@@ -689,6 +692,12 @@ int bw_engine_finalize(bw_engine* e) {
     G.d_x.alloc(R * dm * 4);
     G.d_xn.alloc(R * dm * ts); G.d_qkv.alloc(R * 3 * dm * 4); G.d_att.alloc(R * dm * ts); G.d_q.alloc(R * dm * 4);
     G.d_h.alloc(R * 4 * dm * ts); G.d_lnrows.alloc(LR * dm * ts);
+    if (e->fuse_ln) {
+      G.d_xb.alloc(R * dm * 2);
+      G.d_lnst.alloc(R * (dm / 64) * sizeof(float2));
+      BW_CUDA(cudaMemset(G.d_xb.p, 0, G.d_xb.bytes));
+      BW_CUDA(cudaMemset(G.d_lnst.p, 0, G.d_lnst.bytes));
+    }
     G.d_logits.alloc(LR * (size_t)d.n_vocab * 4);
     G.d_ws.alloc(dec_cross_workspace_floats((int)R, d.n_text_head) * 4);
     G.d_cand_tok.alloc(LR * kMaxCand * 4); G.d_cand_lp.alloc(LR * kMaxCand * 4);
@@ -1081,6 +1090,38 @@ int bw_gemm_bf16(int impl, const void* A, const void* B, void* C, const float* b
     s.A = B; s.B = A; s.M = N; s.N = M; s.transposed = true;
     gemm_tc_bf16(s, reinterpret_cast<cudaStream_t>(stream));
   } else gemm_simt<bf16>(g, reinterpret_cast<cudaStream_t>(stream));
+  BW_API_END
+}
+
+// Test hook for the decoder LayerNorm fusion: a producer row GEMM (x = res + A.Wp^T + bp, which also leaves bf16(x)
+// and the LayerNorm partials) followed by a consumer row GEMM (out = [gelu](LayerNorm(x).Wc^T + bc) with the
+// LayerNorm folded into Wc).  If A is null the producer is skipped and x = res goes through rows_ln_partials (the
+// embedding path).  All pointers are device pointers; x_out fp32 [M, d], out fp32 [M, N].
+int bw_test_ln_chain(const void* A, const void* Wp, const float* bp, const float* res, const float* gamma, const float* beta,
+                     const float* Wc, const float* bc, int32_t M, int32_t d, int32_t Kp, int32_t N, int32_t gelu, float* x_out,
+                     float* out, void* stream) {
+  BW_API_BEGIN
+  BW_CHECK(res && gamma && beta && Wc && x_out && out && M > 0 && d > 0 && N > 0 && d % 64 == 0 && N % 64 == 0, "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DevBuf Wf, c1, c2, xb, lst;
+  Wf.alloc((size_t)N * d * 2); c1.alloc((size_t)N * 4); c2.alloc((size_t)N * 4);
+  xb.alloc((size_t)M * d * 2); lst.alloc((size_t)M * (d / 64) * sizeof(float2));
+  fold_layernorm(Wc, gamma, beta, bc, N, d, Wf.as<bf16>(), c1.as<float>(), c2.as<float>(), st);
+  BW_CUDA(cudaMemcpyAsync(x_out, res, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, st));
+  if (A) {
+    GemmArgs g;
+    g.A = A; g.B = Wp; g.M = M; g.N = d; g.K = Kp; g.lda = Kp; g.ldb = Kp; g.ldc = d; g.ldres = d;
+    g.bias = bp; g.residual = x_out; g.C = x_out; g.out_fp32 = true; g.xb_out = xb.p; g.ln_stats_out = lst.as<float2>();
+    gemm_tc_rows(g, st);
+  } else {
+    rows_ln_partials(x_out, M, d, xb.as<bf16>(), lst.as<float2>(), st);
+  }
+  GemmArgs c;
+  c.A = xb.p; c.B = Wf.p; c.M = M; c.N = N; c.K = d; c.lda = d; c.ldb = d; c.ldc = N;
+  c.bias = c2.as<float>(); c.C = out; c.out_fp32 = true; c.gelu = gelu != 0;
+  c.ln_stats_in = lst.as<float2>(); c.ln_c1 = c1.as<float>();
+  gemm_tc_rows(c, st);
+  BW_CUDA(cudaStreamSynchronize(st));
   BW_API_END
 }
 

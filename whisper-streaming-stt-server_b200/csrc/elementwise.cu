@@ -121,6 +121,81 @@ __global__ void dec_embed_kernel(const int* __restrict__ row_seq, const int* __r
     x[(long long)r * d + c] = to_f(tok_emb[(long long)tok * d + c]) + to_f(pos_emb[(long long)pos * d + c]);
 }
 
+// Decoder LayerNorm fusion, row side: bf16 copy of a freshly written residual row + its per-64-column-tile LayerNorm
+// partials (mean, M2 of the bf16-ROUNDED values), the format gemm_tc_rows' consumer epilogue combines.  `vals` = the
+// row in shared memory; warp w reduces tiles w, w + n_warps, ...
+__device__ __forceinline__ void row_xb_and_ln_partials(const float* vals, int d, bf16* xb_row, float2* st_row) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  for (int tile = warp; tile < d / 64; tile += n_warps) {
+    const bf16 b0 = __float2bfloat16(vals[tile * 64 + lane]), b1 = __float2bfloat16(vals[tile * 64 + 32 + lane]);
+    xb_row[tile * 64 + lane] = b0;
+    xb_row[tile * 64 + 32 + lane] = b1;
+    const float r0 = __bfloat162float(b0), r1 = __bfloat162float(b1);
+    const float tm = warp_sum(r0 + r1) * (1.f / 64.f);
+    const float dv = warp_sum((r0 - tm) * (r0 - tm) + (r1 - tm) * (r1 - tm));
+    if (lane == 0) st_row[tile] = make_float2(tm, dv);
+  }
+}
+
+template <typename T>
+__global__ void dec_embed_ln_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos,
+                                    const int* __restrict__ row_tok, const int* __restrict__ next_tok,
+                                    const T* __restrict__ tok_emb, const T* __restrict__ pos_emb, float* __restrict__ x, int d,
+                                    bf16* __restrict__ xb, float2* __restrict__ stats) {
+  extern __shared__ float embed_row[];
+  pdl_trigger();
+  pdl_wait();
+  const int r = blockIdx.x;
+  int tok = row_tok[r];
+  if (tok < 0) tok = next_tok[row_seq[r]];
+  const int pos = row_pos[r];
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float v = to_f(tok_emb[(long long)tok * d + c]) + to_f(pos_emb[(long long)pos * d + c]);
+    x[(long long)r * d + c] = v;
+    embed_row[c] = v;
+  }
+  __syncthreads();
+  row_xb_and_ln_partials(embed_row, d, xb + (long long)r * d, stats + (long long)r * (d / 64));
+}
+
+// fp32 rows -> bf16 copy + LayerNorm partials (test hook / any producer that is not a row GEMM)
+__global__ void rows_ln_partials_kernel(const float* __restrict__ x, int d, bf16* __restrict__ xb, float2* __restrict__ stats) {
+  extern __shared__ float embed_row[];
+  const int r = blockIdx.x;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) embed_row[c] = x[(long long)r * d + c];
+  __syncthreads();
+  row_xb_and_ln_partials(embed_row, d, xb + (long long)r * d, stats + (long long)r * (d / 64));
+}
+
+// Fold a LayerNorm into the Linear that consumes it (one block per output row n):
+//   Wf[n][k] = bf16(W[n][k] * gamma[k]),  c1[n] = sum_k float(Wf[n][k]),  c2[n] = sum_k beta[k] * W[n][k] + bias[n]
+// so that LN(x).W^T + b = rstd * (x.Wf^T - mean * c1) + c2 with mean / rstd of the row of x.
+__global__ void __launch_bounds__(256)
+fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+               const float* __restrict__ bias, int K, bf16* __restrict__ Wf, float* __restrict__ c1, float* __restrict__ c2) {
+  __shared__ float red[2][8];
+  const int n = blockIdx.x;
+  const float* w = W + (long long)n * K;
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = threadIdx.x; k < K; k += 256) {
+    const float wk = w[k];
+    const bf16 f = __float2bfloat16(wk * gamma[k]);
+    Wf[(long long)n * K + k] = f;
+    s1 += __bfloat162float(f);
+    s2 = fmaf(beta[k], wk, s2);
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; b += red[1][i]; }
+    c1[n] = a;
+    c2[n] = b + (bias ? bias[n] : 0.f);
+  }
+}
+
 template <typename T>
 __global__ void dec_kv_append_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const float* __restrict__ qkv,
                                      T* __restrict__ pool, long long unit_stride, int n_ctx, int layer, int d) {
@@ -210,6 +285,31 @@ void dec_embed(const DecRows& rows, const int* next_tok, const T* tok_emb, const
 }
 template void dec_embed<float>(const DecRows&, const int*, const float*, const float*, float*, int, cudaStream_t);
 template void dec_embed<bf16>(const DecRows&, const int*, const bf16*, const bf16*, float*, int, cudaStream_t);
+
+template <typename T>
+void dec_embed_ln(const DecRows& rows, const int* next_tok, const T* tok_emb, const T* pos_emb, float* x, int d, bf16* xb,
+                  float2* stats, cudaStream_t stream) {
+  if (rows.n_rows <= 0) return;
+  BW_CHECK(d % 64 == 0, "LayerNorm-fused decoder needs d % 64 == 0");
+  launch_kernel(dec_embed_ln_kernel<T>, dim3(rows.n_rows), dim3(128), (size_t)d * 4, stream, rows.row_seq, rows.row_pos, rows.row_tok,
+                next_tok, tok_emb, pos_emb, x, d, xb, stats);
+  ++g_kernel_launches;
+}
+template void dec_embed_ln<bf16>(const DecRows&, const int*, const bf16*, const bf16*, float*, int, bf16*, float2*, cudaStream_t);
+
+void rows_ln_partials(const float* x, int rows, int d, bf16* xb, float2* stats, cudaStream_t stream) {
+  if (rows <= 0) return;
+  BW_CHECK(d % 64 == 0, "d % 64 == 0 required");
+  rows_ln_partials_kernel<<<rows, 128, (size_t)d * 4, stream>>>(x, d, xb, stats);
+  BW_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+
+void fold_layernorm(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K, bf16* Wf, float* c1,
+                    float* c2, cudaStream_t stream) {
+  fold_ln_kernel<<<N, 256, 0, stream>>>(W, gamma, beta, bias, K, Wf, c1, c2);
+  BW_CUDA(cudaGetLastError());
+}
 
 template <typename T>
 void dec_kv_append(const DecRows& rows, const float* qkv, const SelfKV& kv, int layer, int d, cudaStream_t stream) {

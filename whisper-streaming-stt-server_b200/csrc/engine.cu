@@ -183,6 +183,9 @@ struct Impl {
     DecRows rows;
     rows.n_rows = c.R; rows.row_seq = c.row_seq; rows.row_pos = c.row_pos; rows.row_tok = c.row_tok; rows.row_bpos = c.row_bpos;
     float* x = G.d_x.as<float>();
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (e->fuse_ln) return decoder_layers_fused(c, G, rows);
+    }
     dec_embed<T>(rows, e->ss.next_tok, reinterpret_cast<const T*>(e->w.tok_emb), reinterpret_cast<const T*>(e->w.dec_pos), x, dm, st);
     SelfKV skv;
     skv.pool = e->self_pool.p; skv.unit_stride = (long long)L * 2 * d.n_text_ctx * dm; skv.n_ctx = d.n_text_ctx;
@@ -209,6 +212,51 @@ struct Impl {
     // final LayerNorm only on the rows whose logits are needed, then the tied-embedding projection
     layernorm_gather<T>(x, c.lrow_src, e->w.ln_g, e->w.ln_b, G.d_lnrows.as<T>(), c.n_lrows, dm, st);
     linear_rows(G.d_lnrows.as<T>(), c.n_lrows, e->LR_max, e->w.tok_emb, d.n_vocab, dm, nullptr, nullptr, G.d_logits.p, false, true);
+  }
+
+  // bf16 tensor-core mode: the three LayerNorms of a block live inside the row GEMMs.  Each GEMM that writes the
+  // residual stream (attention out-projections, mlp.2; the embedding for layer 0) also leaves a bf16 copy of it and
+  // per-row LayerNorm partials; each GEMM that used to read a LayerNorm output multiplies the raw bf16 rows with
+  // W * gamma and normalises in its epilogue.  8 kernels per block instead of 11 (tools/trace_step.py: a LayerNorm
+  // launch costs ~2.4 us of work + ~1.4 us of dependency release on the step's critical path).
+  void rows_gemm(const void* A, int R, int a_rows, const void* W, int N, int K, const float* bias, const float* residual, void* out,
+                 bool gelu, bool out_fp32, void* xb_out, float2* st_out, const float2* st_in, const float* c1) const {
+    GemmArgs g;
+    g.A = A; g.B = W; g.M = R; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldc = N; g.ldres = N; g.a_rows = a_rows;
+    g.bias = bias; g.residual = residual; g.C = out; g.gelu = gelu; g.out_fp32 = out_fp32;
+    g.xb_out = xb_out; g.ln_stats_out = st_out; g.ln_stats_in = st_in; g.ln_c1 = c1;
+    gemm_tc_rows(g, stream);
+  }
+  void decoder_layers_fused(const StepCtl& c, DecGroup& G, const DecRows& rows) const {
+    const auto& d = D();
+    const int dm = d.n_text_state, L = d.n_text_layer, H = d.n_text_head;
+    cudaStream_t st = stream;
+    float* x = G.d_x.as<float>();
+    bf16* xb = G.d_xb.as<bf16>();
+    float2* lst = G.d_lnst.as<float2>();
+    dec_embed_ln<bf16>(rows, e->ss.next_tok, reinterpret_cast<const bf16*>(e->w.tok_emb), reinterpret_cast<const bf16*>(e->w.dec_pos), x, dm,
+                       xb, lst, st);
+    SelfKV skv;
+    skv.pool = e->self_pool.p; skv.unit_stride = (long long)L * 2 * d.n_text_ctx * dm; skv.n_ctx = d.n_text_ctx;
+    skv.seq_first = e->ss.seq_first; skv.anc = e->ss.anc[e->anc_cur];
+    CrossKV xkv;
+    xkv.cache = e->cross_cache.p; xkv.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; xkv.T_enc = d.n_audio_ctx;
+    xkv.n_slots = e->Q; xkv.n_layer = L;
+    const int Ra = e->R_max;
+    for (int l = 0; l < L; ++l) {
+      const LayerW& w = e->w.dec[l];
+      rows_gemm(xb, c.R, Ra, w.wqkv, 3 * dm, dm, w.c2_qkv, nullptr, G.d_qkv.p, false, true, nullptr, nullptr, lst, w.c1_qkv);
+      dec_self_attention<bf16>(rows, G.d_qkv.as<float>(), skv, l, dm, H, G.d_att.as<bf16>(), st);
+      rows_gemm(G.d_att.p, c.R, Ra, w.wo, dm, dm, w.bo, x, x, false, true, xb, lst, nullptr, nullptr);
+      rows_gemm(xb, c.R, Ra, w.wq_x, dm, dm, w.c2_qx, nullptr, G.d_q.p, false, true, nullptr, nullptr, lst, w.c1_qx);
+      dec_cross_attention<bf16>(c.grp_first, c.grp_n, c.grp_x, c.n_groups, c.max_group_rows, c.R, G.d_q.as<float>(), xkv, l, dm, H,
+                                G.d_att.as<bf16>(), G.d_ws.as<float>(), st);
+      rows_gemm(G.d_att.p, c.R, Ra, w.wo_x, dm, dm, w.bo_x, x, x, false, true, xb, lst, nullptr, nullptr);
+      rows_gemm(xb, c.R, Ra, w.w1, 4 * dm, dm, w.c2_w1, nullptr, G.d_h.p, true, false, nullptr, nullptr, lst, w.c1_w1);
+      rows_gemm(G.d_h.p, c.R, Ra, w.w2, dm, 4 * dm, w.b2, x, x, false, true, xb, lst, nullptr, nullptr);
+    }
+    layernorm_gather<bf16>(x, c.lrow_src, e->w.ln_g, e->w.ln_b, G.d_lnrows.as<bf16>(), c.n_lrows, dm, st);
+    linear_rows(G.d_lnrows.as<bf16>(), c.n_lrows, e->LR_max, e->w.tok_emb, d.n_vocab, dm, nullptr, nullptr, G.d_logits.p, false, true);
   }
 
   void window_to_A1(const float* logmel, int ld, int n_real, const int* gmax, int seek, int seg, int bi) const {
@@ -283,9 +331,27 @@ void engine_build_weight_table(bw_engine* e) {
   w.wkv_x = wt((size_t)d.n_text_layer * 2 * dt * dt);
   w.bkv_x = wf((size_t)d.n_text_layer * 2 * dt);
   w.dec.resize(d.n_text_layer);
+  auto master = [&](size_t elems) {
+    auto b = std::make_unique<DevBuf>();
+    b->alloc(elems * 4);
+    BW_CUDA(cudaMemset(b->p, 0, elems * 4));
+    float* p = b->as<float>();
+    e->fold_masters.push_back(std::move(b));
+    return p;
+  };
   for (int i = 0; i < d.n_text_layer; ++i) {
     const std::string p = "decoder.blocks." + std::to_string(i);
     block(p, w.dec[i], dt, true);
+    if (e->fuse_ln) {
+      LayerW& lw = w.dec[i];
+      lw.c1_qkv = wf(3 * dt); lw.c2_qkv = wf(3 * dt); lw.c1_qx = wf(dt); lw.c2_qx = wf(dt); lw.c1_w1 = wf(4 * dt); lw.c2_w1 = wf(4 * dt);
+      lw.m_wqkv = master(3 * dt * dt); lw.m_wqx = master(dt * dt); lw.m_w1 = master(4 * dt * dt);
+      e->named_master[p + ".attn.query.weight"] = lw.m_wqkv;
+      e->named_master[p + ".attn.key.weight"] = lw.m_wqkv + dt * dt;
+      e->named_master[p + ".attn.value.weight"] = lw.m_wqkv + 2 * dt * dt;
+      e->named_master[p + ".cross_attn.query.weight"] = lw.m_wqx;
+      e->named_master[p + ".mlp.0.weight"] = lw.m_w1;
+    }
     reg(p + ".cross_attn.key.weight", off(w.wkv_x, (size_t)i * 2 * dt * dt), dt * dt);
     reg(p + ".cross_attn.value.weight", off(w.wkv_x, (size_t)i * 2 * dt * dt + dt * dt), dt * dt);
     reg(p + ".cross_attn.value.bias", w.bkv_x + (size_t)i * 2 * dt + dt, dt);
@@ -337,11 +403,28 @@ void engine_load_tensor(bw_engine* e, const bw_tensor_desc& t) {
     BW_CUDA(cudaMemcpyAsync(dst, e->staging.p, n * 4, cudaMemcpyDeviceToDevice, e->stream));
   } else {
     convert_f32<bf16>(e->staging.as<float>(), reinterpret_cast<bf16*>(dst), (long long)n, e->stream);
+    auto mi = e->named_master.find(name);  // LayerNorm fusion: keep the fp32 values until bw_engine_finalize folds them
+    if (mi != e->named_master.end()) BW_CUDA(cudaMemcpyAsync(mi->second, e->staging.p, n * 4, cudaMemcpyDeviceToDevice, e->stream));
   }
   BW_CUDA(cudaStreamSynchronize(e->stream));  // `tmp` / caller memory may go away
   for (size_t i = 0; i < e->expected_names.size(); ++i)
     if (e->expected_names[i] == name) e->loaded[i] = 1;
   if (name == "encoder.positional_embedding") e->loaded.back() = 1;
+}
+
+// bw_engine_finalize: fold attn_ln / cross_attn_ln / mlp_ln of every decoder block into the Linear behind it
+void engine_fold_layernorms(bw_engine* e) {
+  if (!e->fuse_ln) return;
+  const int dt = e->dims.n_text_state;
+  for (LayerW& lw : e->w.dec) {
+    fold_layernorm(lw.m_wqkv, lw.ln1_g, lw.ln1_b, lw.bqkv, 3 * dt, dt, reinterpret_cast<bf16*>(lw.wqkv), lw.c1_qkv, lw.c2_qkv, e->stream);
+    fold_layernorm(lw.m_wqx, lw.lnx_g, lw.lnx_b, lw.bq_x, dt, dt, reinterpret_cast<bf16*>(lw.wq_x), lw.c1_qx, lw.c2_qx, e->stream);
+    fold_layernorm(lw.m_w1, lw.ln2_g, lw.ln2_b, lw.b1, 4 * dt, dt, reinterpret_cast<bf16*>(lw.w1), lw.c1_w1, lw.c2_w1, e->stream);
+    lw.m_wqkv = lw.m_wqx = lw.m_w1 = nullptr;
+  }
+  BW_CUDA(cudaStreamSynchronize(e->stream));
+  e->fold_masters.clear();
+  e->named_master.clear();
 }
 
 template <typename T> static void encoder_forward_t(bw_engine* e, int nb) { Impl<T>(e).encoder_forward(nb); }

@@ -51,6 +51,10 @@ struct LayerW {
   float *ln2_g, *ln2_b;      // mlp_ln
   void* w1;   float* b1;     // [4d, d]
   void* w2;   float* b2;     // [d, 4d]
+  // decoder LayerNorm fusion (engine->fuse_ln): wqkv / wq_x / w1 then hold W * gamma of the LayerNorm in front of
+  // them; c1 = row sums of the folded weight, c2 = W.beta + bias (what the row GEMM's consumer epilogue needs).
+  float *c1_qkv = nullptr, *c2_qkv = nullptr, *c1_qx = nullptr, *c2_qx = nullptr, *c1_w1 = nullptr, *c2_w1 = nullptr;
+  float *m_wqkv = nullptr, *m_wqx = nullptr, *m_w1 = nullptr;  // fp32 masters, only between load and finalize
 };
 
 struct ModelW {
@@ -94,6 +98,7 @@ struct DecGroup {
   // control block's CONTENTS change from step to step, so ~360 launches collapse into one cudaGraphLaunch.
   std::unordered_map<StepGraphKey, StepGraph, StepGraphKeyHash> graphs;
   DevBuf d_x, d_xn, d_qkv, d_att, d_q, d_h, d_lnrows, d_logits, d_ws, d_cand_tok, d_cand_lp, d_ctrl;
+  DevBuf d_xb, d_lnst;  // LayerNorm fusion: bf16 copy of the residual stream, per-row / per-64-column partials
   int* h_ctrl = nullptr;  // pinned host copy of the control block
 };
 constexpr int kMaxGroups = 4;
@@ -157,6 +162,9 @@ struct bw_engine {
   int device = 0;
   bool fp32 = false;       // validation mode
   bool force_simt = false;
+  bool fuse_ln = false;    // decoder LayerNorms folded into the row GEMMs (bf16 tensor-core mode)
+  std::vector<std::unique_ptr<bw::DevBuf>> fold_masters;                    // released by bw_engine_finalize
+  std::unordered_map<std::string, float*> named_master;                     // tensor name -> fp32 master slice
   std::atomic<int> refs{1};
   int state = 0;           // 0 = created, 1 = finalized
   cudaStream_t stream = nullptr;

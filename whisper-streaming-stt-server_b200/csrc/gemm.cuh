@@ -31,10 +31,23 @@ struct GemmArgs {
   // stream (or a zeroed buffer); `residual` must be null.  tcgen05 path only.
   bool accumulate = false;
   int ksplit = 0;  // 0 = choose
+  // ---- decoder LayerNorm fusion (gemm_tc_rows only; see gemm_tc.cu) ----
+  // producer: besides C (fp32 residual stream) also store bf16(C) into xb_out (leading dimension ldc) and, per row
+  // and 64-column tile, the LayerNorm partials (mean, M2) of the bf16-rounded values: ln_stats_out[row * N/64 + tile]
+  void* xb_out = nullptr;
+  float2* ln_stats_out = nullptr;
+  // consumer: A = bf16(x) un-normalised, B = W * gamma (folded), bias = beta.W + b, ln_c1[n] = sum_k B[n][k]:
+  //   out = rstd_r * (acc - mean_r * ln_c1[n]) + bias[n], mean / rstd from ln_stats_in[row * K/64 + tile]
+  const float2* ln_stats_in = nullptr;
+  const float* ln_c1 = nullptr;
+  float ln_eps = 1e-5f;
 };
 
 // bf16 inputs, fp32 accumulate, tcgen05.mma + TMEM + TMA. Throws on CUDA errors.
 void gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream);
+// Row GEMM of the decoder step (M = live hypotheses): always the push-reduced split-K kernel, any M (more waves for
+// many rows).  The only kernel that understands the LayerNorm-fusion fields of GemmArgs.  N % 64 == 0 required.
+void gemm_tc_rows(const GemmArgs& g, cudaStream_t stream);
 // SIMT tiled GEMM: T = float (validation mode) or bf16 (fallback / cross-check).
 template <typename T> void gemm_simt(const GemmArgs& g, cudaStream_t stream);
 

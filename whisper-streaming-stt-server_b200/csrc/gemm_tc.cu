@@ -39,6 +39,13 @@ struct GemmDev {
   int gelu, out_fp32, transposed;
   int accumulate, ksplit;
   unsigned long long* trace;  // debug timeline (null = off)
+  // LayerNorm fusion of the decoder row GEMMs (rows kernel only)
+  bf16* xb;               // producer: bf16 copy of C
+  float2* st_out;         // producer: [row][N / 64] (mean, M2) of the bf16-rounded outputs of each 64-column tile
+  const float2* st_in;    // consumer: [row][K / 64]
+  const float* c1;        // consumer: row sums of the folded weight
+  int st_in_tiles;
+  float ln_eps;
 };
 
 template <int BN, int STAGES>
@@ -551,16 +558,39 @@ gemm_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int RPC = BM / KS;      // tile rows owned (reduced + stored) by each CTA of the cluster
   constexpr int NI = RPC / 8;       // float4 granules per epilogue thread (RPC rows x 16 granules / 128 threads)
   const int t = threadIdx.x - 64;
-  float4 resv[NI], biasv[NI];
+  float4 resv[NI], biasv[NI], c1v[NI];
+  float ln_mean[NI], ln_rstd[NI];
   if (warp >= 2) {
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
       const int e = t + i * 128;
-      const int gi = m0 + ks * RPC + (e >> 4), j0 = n0 + (e & 15) * 4;
+      const int gi = m0 + ks * RPC + (e >> 4), c4 = e & 15, j0 = n0 + c4 * 4;
       const bool ok = gi < p.M && j0 < p.N;
       biasv[i] = (p.bias && ok) ? __ldg(reinterpret_cast<const float4*>(p.bias + (long long)z * p.bias_zstride + j0)) : make_float4(0.f, 0.f, 0.f, 0.f);
       resv[i] = (p.residual && ok) ? *reinterpret_cast<const float4*>(p.residual + (long long)z * p.res_zstride + (long long)gi * p.ldres + j0)
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      c1v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ln_mean[i] = 0.f; ln_rstd[i] = 1.f;
+      if (p.st_in) {
+        // LayerNorm statistics of row gi from the producer's per-tile partials.  The 16 lanes that share a row each
+        // fetch up to two tiles (K <= 2048) and combine them with Chan's formula through shuffles (all lanes take part).
+        c1v[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.c1 + j0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float2* sp = p.st_in + (long long)gi * p.st_in_tiles;
+        const bool row_ok = gi < p.M;
+        const float2 p0 = (row_ok && c4 < p.st_in_tiles) ? sp[c4] : make_float2(0.f, 0.f);
+        const float2 p1 = (row_ok && c4 + 16 < p.st_in_tiles) ? sp[c4 + 16] : make_float2(0.f, 0.f);
+        float ms = p0.x + p1.x;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) ms += __shfl_xor_sync(0xffffffffu, ms, o);
+        const float mean = ms / (float)p.st_in_tiles;
+        float m2 = 0.f;
+        if (c4 < p.st_in_tiles) m2 += p0.y + 64.f * (p0.x - mean) * (p0.x - mean);
+        if (c4 + 16 < p.st_in_tiles) m2 += p1.y + 64.f * (p1.x - mean) * (p1.x - mean);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+        ln_mean[i] = mean;
+        ln_rstd[i] = rsqrtf(m2 / (64.f * (float)p.st_in_tiles) + p.ln_eps);
+      }
     }
     // ---- push my accumulator row into the owner CTA's reduction area: slots[ks][row % RPC][granule ^ (row & 15)] ----
     const int wq = warp & 3;
@@ -601,21 +631,39 @@ gemm_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const float4 v = slots[(pr * RPC + lr) * 16 + (c4 ^ (lr & 15))];
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
-      if (gi >= p.M || j0 >= p.N) continue;
-      float v[4] = {acc.x + biasv[i].x, acc.y + biasv[i].y, acc.z + biasv[i].z, acc.w + biasv[i].w};
+      const bool ok = gi < p.M && j0 < p.N;  // no early exit: the statistics below use warp shuffles
+      float v[4] = {acc.x, acc.y, acc.z, acc.w};
+      if (p.st_in) {  // out = rstd * (x.W' - mean * sum_k W') + (beta.W + b)
+        const float mu = ln_mean[i], rs = ln_rstd[i];
+        v[0] = rs * (v[0] - mu * c1v[i].x); v[1] = rs * (v[1] - mu * c1v[i].y);
+        v[2] = rs * (v[2] - mu * c1v[i].z); v[3] = rs * (v[3] - mu * c1v[i].w);
+      }
+      v[0] += biasv[i].x; v[1] += biasv[i].y; v[2] += biasv[i].z; v[3] += biasv[i].w;
       if (p.gelu) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) v[q] = gelu_erf_fast(v[q]);
       }
       v[0] += resv[i].x; v[1] += resv[i].y; v[2] += resv[i].z; v[3] += resv[i].w;
       const long long oi = (long long)z * p.c_zstride + (long long)gi * p.ldc + j0;
-      if (p.out_fp32) {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + oi) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
-        uint2 w;
-        w.x = pack_bf16x2(v[0], v[1]);
-        w.y = pack_bf16x2(v[2], v[3]);
-        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.C) + oi) = w;
+      const uint32_t b01 = pack_bf16x2(v[0], v[1]), b23 = pack_bf16x2(v[2], v[3]);
+      if (ok) {
+        if (p.out_fp32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + oi) = make_float4(v[0], v[1], v[2], v[3]);
+        else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.C) + oi) = make_uint2(b01, b23);
+        if (p.xb) *reinterpret_cast<uint2*>(p.xb + oi) = make_uint2(b01, b23);
+      }
+      if (p.st_out) {
+        // LayerNorm partials of this row's 64-column tile, over the bf16-ROUNDED values (what the consumer GEMM will
+        // actually multiply): tile mean, then centred second moment; the 16 lanes of the row reduce by shuffles
+        const float r0 = __uint_as_float(b01 << 16), r1 = __uint_as_float(b01 & 0xffff0000u);
+        const float r2 = __uint_as_float(b23 << 16), r3 = __uint_as_float(b23 & 0xffff0000u);
+        float sm = (r0 + r1) + (r2 + r3);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        const float tm = sm * (1.f / 64.f);
+        float dv = (r0 - tm) * (r0 - tm) + (r1 - tm) * (r1 - tm) + (r2 - tm) * (r2 - tm) + (r3 - tm) * (r3 - tm);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) dv += __shfl_xor_sync(0xffffffffu, dv, o);
+        if (ok && c4 == 0) p.st_out[(long long)gi * gridDim.x + blockIdx.x] = make_float2(tm, dv);
       }
     }
     if (threadIdx.x == 64) trace_mark(trace, ttag | 7);
@@ -930,6 +978,7 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
   p.gelu = g.gelu; p.out_fp32 = g.out_fp32; p.transposed = g.transposed;
   p.accumulate = g.accumulate;
   p.trace = g_trace_dev;
+  p.xb = nullptr; p.st_out = nullptr; p.st_in = nullptr; p.c1 = nullptr; p.st_in_tiles = 0; p.ln_eps = 0.f;
   const int total_kb = (g.K + BK - 1) / BK;
   int ksplit = 1;
   if (g.accumulate) {
@@ -967,6 +1016,7 @@ void launch_splitk(const GemmArgs& g, cudaStream_t stream) {
   p.gelu = g.gelu; p.out_fp32 = g.out_fp32; p.transposed = g.transposed;
   p.accumulate = 0; p.ksplit = KS;
   p.trace = g_trace_dev;
+  p.xb = nullptr; p.st_out = nullptr; p.st_in = nullptr; p.c1 = nullptr; p.st_in_tiles = 0; p.ln_eps = 0.f;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.Z * KS);
   cfg.blockDim = dim3(192);
@@ -1004,6 +1054,10 @@ void launch_rows(const GemmArgs& g, cudaStream_t stream) {
   p.gelu = g.gelu; p.out_fp32 = g.out_fp32; p.transposed = 0;
   p.accumulate = 0; p.ksplit = KS;
   p.trace = g_trace_dev;
+  p.xb = reinterpret_cast<bf16*>(g.xb_out); p.st_out = g.ln_stats_out; p.st_in = g.ln_stats_in; p.c1 = g.ln_c1;
+  p.st_in_tiles = g.K / 64; p.ln_eps = g.ln_eps;
+  if (g.ln_stats_in) BW_CHECK(g.ln_c1 && g.K % 64 == 0 && g.K / 64 <= 32 && g.Z == 1, "LayerNorm-fused GEMM needs K % 64 == 0, K <= 2048");
+  if (g.ln_stats_out || g.xb_out) BW_CHECK(g.N % 64 == 0 && g.Z == 1 && g.out_fp32, "LayerNorm producer GEMM needs N % 64 == 0 and an fp32 C");
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((g.N + R_BN - 1) / R_BN, (g.M + BM - 1) / BM, g.Z * KS);
   cfg.blockDim = dim3(192);
@@ -1038,6 +1092,7 @@ void launch_pair(const GemmArgs& g, cudaStream_t stream) {
   p.a_z_bcast = a_bcast; p.b_z_bcast = b_bcast;
   p.gelu = g.gelu; p.out_fp32 = g.out_fp32; p.transposed = 0; p.accumulate = 0; p.ksplit = 1;
   p.trace = nullptr;
+  p.xb = nullptr; p.st_out = nullptr; p.st_in = nullptr; p.c1 = nullptr; p.st_in_tiles = 0; p.ln_eps = 0.f;
   const int m_pairs = (g.M + 255) / 256, n_tiles = (g.N + 255) / 256;
   const int total = m_pairs * n_tiles * g.Z;
   static int sm_count = 0;
@@ -1058,8 +1113,23 @@ void launch_pair(const GemmArgs& g, cudaStream_t stream) {
 }
 }  // namespace
 
+void gemm_tc_rows(const GemmArgs& g, cudaStream_t stream) {
+  BW_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.Z > 0, "empty GEMM");
+  BW_CHECK(!g.transposed && !g.accumulate && (g.N % 4) == 0 && (g.ldc % 4) == 0 && (!g.residual || (g.ldres % 4) == 0),
+           "row GEMM needs N, ldc, ldres % 4 == 0");
+  const long long tiles64 = (long long)((g.M + BM - 1) / BM) * ((g.N + R_BN - 1) / R_BN) * g.Z;
+  const int total_kb = (g.K + BK - 1) / BK;
+  int ks = 8;  // keep the grid within one co-resident wave when possible (see gemm_tc_bf16), never below 2
+  while (ks > 2 && (tiles64 * ks > (ks == 8 ? 256 : 288) || total_kb < 2 * ks)) ks >>= 1;
+  BW_CHECK(total_kb >= ks, "K too small for the row GEMM");
+  if (ks == 8) return launch_rows<8>(g, stream);
+  if (ks == 4) return launch_rows<4>(g, stream);
+  return launch_rows<2>(g, stream);
+}
+
 void gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   BW_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.Z > 0, "empty GEMM");
+  BW_CHECK(!g.xb_out && !g.ln_stats_out && !g.ln_stats_in, "LayerNorm-fusion fields are only understood by gemm_tc_rows");
   // Tile choice: 128x256 (fewer smem bytes per MMA) when it still fills the 148 SMs, else
   // 128x128 with two CTAs per SM; tiny N (swap-AB decode) uses the narrowest tile that covers it.
   const long long mt = (g.M + BM - 1) / BM;

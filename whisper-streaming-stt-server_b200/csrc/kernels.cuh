@@ -68,6 +68,16 @@ template <typename T>
 void dec_embed(const DecRows& rows, const int* next_tok, const T* tok_emb, const T* pos_emb, float* x, int d,
                cudaStream_t stream);
 
+// ---- decoder LayerNorm fusion (bf16 tensor-core mode): see gemm.cuh / gemm_tc_rows ----
+// embedding rows + their bf16 copy + per-64-column LayerNorm partials (the first layer's consumer GEMM reads them)
+template <typename T>
+void dec_embed_ln(const DecRows& rows, const int* next_tok, const T* tok_emb, const T* pos_emb, float* x, int d, bf16* xb,
+                  float2* stats, cudaStream_t stream);
+void rows_ln_partials(const float* x, int rows, int d, bf16* xb, float2* stats, cudaStream_t stream);
+// Wf = bf16(W * gamma), c1 = rowsum(Wf), c2 = W.beta + bias   (W fp32 [N, K])
+void fold_layernorm(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K, bf16* Wf, float* c1,
+                    float* c2, cudaStream_t stream);
+
 // Self-attention KV pool: unit u (= sequence slot) holds [L][2][n_ctx][d] of one hypothesis slot.
 // Beams of one request occupy adjacent units starting at seq_first[s]; the key/value of sequence s at
 // position t lives in unit seq_first[s] + anc[s][t] (beam reordering never copies K/V, it rewrites anc).
