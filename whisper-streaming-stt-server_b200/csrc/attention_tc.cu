@@ -1316,7 +1316,7 @@ void attn_encoder_tc(const bf16* qkv, bf16* out, int batch, int T_len, int n_hea
       }
       const int n_qp = (T_len + 255) / 256, n_items = n_qp * n_head * batch;
       const int grid = std::min(n_items, sm_count > 0 ? sm_count : 148);
-      const int pv_n = getenv("B200W_ATTN_PVN") ? atoi(getenv("B200W_ATTN_PVN")) : V4_ON;  // experiment knob
+      const int pv_n = V4_ON;
       if (g_trace_dev) attn_encoder_v6_kernel<true, true><<<grid, V5_THREADS, V4_TOTAL, stream>>>(tm, out, T_len, d, n_head, n_qp, n_items, g_trace_dev, pv_n);
       else if (getenv("B200W_ATTN_NOPP")) attn_encoder_v6_kernel<false, false><<<grid, V5_THREADS, V4_TOTAL, stream>>>(tm, out, T_len, d, n_head, n_qp, n_items, nullptr, pv_n);
       else attn_encoder_v6_kernel<true, false><<<grid, V5_THREADS, V4_TOTAL, stream>>>(tm, out, T_len, d, n_head, n_qp, n_items, nullptr, pv_n);

@@ -1121,6 +1121,7 @@ void gemm_tc_rows(const GemmArgs& g, cudaStream_t stream) {
   const int total_kb = (g.K + BK - 1) / BK;
   int ks = 8;  // keep the grid within one co-resident wave when possible (see gemm_tc_bf16), never below 2
   while (ks > 2 && (tiles64 * ks > (ks == 8 ? 256 : 288) || total_kb < 2 * ks)) ks >>= 1;
+  // (capping KS at 4 / 2 so that every SM hosts one CTA was measured slower: 7.20 -> 7.26 / 7.75 ms per step)
   BW_CHECK(total_kb >= ks, "K too small for the row GEMM");
   if (ks == 8) return launch_rows<8>(g, stream);
   if (ks == 4) return launch_rows<4>(g, stream);
