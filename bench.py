@@ -318,6 +318,7 @@ def run_b200(args):
     ems, eflops = eng.bench_encoder(enc_b, 3)
     stages["encoder"] = {"batch": enc_b, "ms": ems, "tflops": eflops / (ems * 1e-3) / 1e12,
                          "frac_of_bf16_sustained": eflops / (ems * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]}
+    eng.bench_decoder_step(S, 1, 60, 6)  # the step graph of this shape is captured at its third sighting: not in the timed run
     dms, dbytes = eng.bench_decoder_step(S, 1, 100, 20)
     stages["decoder_step"] = {"segments": S, "context": 100, "ms": dms, "gbs": dbytes / (dms * 1e-3) / 1e9,
                               "frac_of_hbm": dbytes / (dms * 1e-3) / 1e9 / pk["hbm_gbs"]}

@@ -105,13 +105,19 @@ def run_stream_sim(handles, seconds: float, seed: int = 0, partial_every: float 
                 final_lat.append(lat)
                 audio_s[0] += dur
 
+    s0 = handles[0].engine.stats()
     threads = [threading.Thread(target=session, args=(i,), daemon=True) for i in range(n)]
     for t in threads:
         t.start()
     for t in threads:
         t.join()
     wall = time.perf_counter() - t0
-    return {"sessions": n, "stream_s": seconds, "wall_s": wall, "partials": len(partial_lat), "finals": len(final_lat),
+    s1 = handles[0].engine.stats()
+    ds = {k: s1[k] - s0[k] for k in ("windows", "encoder_batches", "decode_steps", "rows")}
+    sched = {"windows_per_encoder_batch": ds["windows"] / max(1, ds["encoder_batches"]),
+             "rows_per_decoder_step": ds["rows"] / max(1, ds["decode_steps"]), "decoder_steps_per_s": ds["decode_steps"] / wall,
+             "encoder_batches_per_s": ds["encoder_batches"] / wall}
+    return {"scheduler": sched,"sessions": n, "stream_s": seconds, "wall_s": wall, "partials": len(partial_lat), "finals": len(final_lat),
             "skipped_partial_slots": skipped[0],
             "p50_partial_latency_s": nearest_rank(partial_lat, 0.50), "p95_partial_latency_s": nearest_rank(partial_lat, 0.95),
             "p99_partial_latency_s": nearest_rank(partial_lat, 0.99), "p95_final_latency_s": nearest_rank(final_lat, 0.95),

@@ -553,6 +553,11 @@ int bw_engine_create(const bw_model_dims* dims, const bw_engine_config* cfg, bw_
   e->force_simt = (cfg->flags & BW_FLAG_FORCE_SIMT_GEMM) != 0;
   e->fuse_ln = !e->fp32 && !e->force_simt && (dims->n_text_state % 64) == 0 && getenv("B200W_NO_LN_FUSION") == nullptr;
   BW_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  BW_CUDA(cudaEventCreateWithFlags(&e->enc_fork, cudaEventDisableTiming));
+  for (int i = 0; i < bw_engine::kEncStreams; ++i) {
+    BW_CUDA(cudaStreamCreateWithFlags(&e->enc_streams[i], cudaStreamNonBlocking));
+    BW_CUDA(cudaEventCreateWithFlags(&e->enc_join[i], cudaEventDisableTiming));
+  }
   for (auto& s : e->front) BW_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   e->staging.alloc((size_t)64 << 20);
   engine_build_weight_table(e.get());
@@ -794,6 +799,11 @@ int bw_engine_destroy(bw_engine* e) {
   if (e->h_flags) cudaFreeHost(e->h_flags);
   if (e->h_fin) cudaFreeHost(e->h_fin);
   for (auto& s : e->front) if (s) cudaStreamDestroy(s);
+  if (e->enc_fork) cudaEventDestroy(e->enc_fork);
+  for (int i = 0; i < bw_engine::kEncStreams; ++i) {
+    if (e->enc_join[i]) cudaEventDestroy(e->enc_join[i]);
+    if (e->enc_streams[i]) cudaStreamDestroy(e->enc_streams[i]);
+  }
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   BW_API_END

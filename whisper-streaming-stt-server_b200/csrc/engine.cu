@@ -97,64 +97,74 @@ struct Impl {
     gemm(g);
   }
 
-  // ---- encoder forward on `nb` windows whose conv1 operand already sits in A1 ----
-  void encoder_forward(int nb) const {
+  // ---- encoder forward on windows [w0, w0 + nb) whose conv1 operand already sits in A1, on this Impl's stream ----
+  // Every activation buffer is window-major, so a sub-batch is a row range of the same buffers.
+  void encoder_forward(int nb, int w0 = 0) const {
     const auto& d = D();
     const int dm = d.n_audio_state, T_enc = d.n_audio_ctx, K1 = 3 * d.n_mels;
     const int M = nb * T_enc;
-    cudaStream_t st = e->stream;
+    cudaStream_t st = stream;
+    const long long r0 = (long long)w0 * T_enc;  // first row of this sub-batch in the [windows * 1500, .] buffers
+    T* A1 = e->A1.as<T>() + (long long)w0 * 3000 * K1;
+    T* y1 = e->y1.as<T>() + (long long)w0 * 3000 * dm;
+    T* A2 = e->A2.as<T>() + r0 * 3 * dm;
+    float* x = e->enc_x.as<float>() + r0 * dm;
+    T* xn = e->enc_xn.as<T>() + r0 * dm;
+    T* qkv = e->enc_qkv.as<T>() + r0 * 3 * dm;
+    T* att = e->enc_att.as<T>() + r0 * dm;
+    T* hbuf = e->enc_h.as<T>() + r0 * 4 * dm;
+    T* out = e->enc_out.as<T>() + r0 * dm;
     {  // conv1 + GELU
       GemmArgs g;
-      g.A = e->A1.p; g.B = e->w.conv1_w; g.C = e->y1.p; g.bias = e->w.conv1_b;
+      g.A = A1; g.B = e->w.conv1_w; g.C = y1; g.bias = e->w.conv1_b;
       g.M = nb * 3000; g.N = dm; g.K = K1; g.lda = K1; g.ldb = K1; g.ldc = dm; g.gelu = true;
       gemm(g);
     }
-    im2col_conv2<T>(e->y1.as<T>(), e->A2.as<T>(), nb, dm, st);
+    im2col_conv2<T>(y1, A2, nb, dm, st);
     {  // conv2 + GELU + positional embedding -> fp32 residual stream
       GemmArgs g;
-      g.A = e->A2.p; g.B = e->w.conv2_w; g.C = e->enc_x.p; g.bias = e->w.conv2_b; g.residual = e->w.enc_pos;
+      g.A = A2; g.B = e->w.conv2_w; g.C = x; g.bias = e->w.conv2_b; g.residual = e->w.enc_pos;
       g.M = T_enc; g.N = dm; g.K = 3 * dm; g.lda = 3 * dm; g.ldb = 3 * dm; g.ldc = dm; g.ldres = dm;
       g.Z = nb; g.a_zstride = (long long)T_enc * 3 * dm; g.b_zstride = 0; g.c_zstride = (long long)T_enc * dm;
       g.res_zstride = 0; g.bias_zstride = 0; g.gelu = true; g.out_fp32 = true;
       gemm(g);
     }
-    float* x = e->enc_x.as<float>();
     for (int l = 0; l < d.n_audio_layer; ++l) {
       const LayerW& w = e->w.enc[l];
-      layernorm<T>(x, w.ln1_g, w.ln1_b, e->enc_xn.as<T>(), M, dm, st);
+      layernorm<T>(x, w.ln1_g, w.ln1_b, xn, M, dm, st);
       {
         GemmArgs g;
-        g.A = e->enc_xn.p; g.B = w.wqkv; g.C = e->enc_qkv.p; g.bias = w.bqkv;
+        g.A = xn; g.B = w.wqkv; g.C = qkv; g.bias = w.bqkv;
         g.M = M; g.N = 3 * dm; g.K = dm; g.lda = dm; g.ldb = dm; g.ldc = 3 * dm;
         gemm(g);
       }
       if constexpr (std::is_same<T, float>::value) {
-        attn_encoder_simt<float>(e->enc_qkv.as<float>(), e->enc_att.as<float>(), nb, T_enc, d.n_audio_head, st);
+        attn_encoder_simt<float>(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(att), nb, T_enc, d.n_audio_head, st);
       } else {
-        if (e->force_simt || (e->cfg.flags & 4)) attn_encoder_simt<bf16>(e->enc_qkv.as<bf16>(), e->enc_att.as<bf16>(), nb, T_enc, d.n_audio_head, st);
-        else attn_encoder_tc(e->enc_qkv.as<bf16>(), e->enc_att.as<bf16>(), nb, T_enc, d.n_audio_head, st);
+        if (e->force_simt || (e->cfg.flags & 4)) attn_encoder_simt<bf16>(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(att), nb, T_enc, d.n_audio_head, st);
+        else attn_encoder_tc(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(att), nb, T_enc, d.n_audio_head, st);
       }
       {
         GemmArgs g;
-        g.A = e->enc_att.p; g.B = w.wo; g.C = x; g.bias = w.bo; g.residual = x;
+        g.A = att; g.B = w.wo; g.C = x; g.bias = w.bo; g.residual = x;
         g.M = M; g.N = dm; g.K = dm; g.lda = dm; g.ldb = dm; g.ldc = dm; g.ldres = dm; g.out_fp32 = true;
         gemm(g);
       }
-      layernorm<T>(x, w.ln2_g, w.ln2_b, e->enc_xn.as<T>(), M, dm, st);
+      layernorm<T>(x, w.ln2_g, w.ln2_b, xn, M, dm, st);
       {
         GemmArgs g;
-        g.A = e->enc_xn.p; g.B = w.w1; g.C = e->enc_h.p; g.bias = w.b1;
+        g.A = xn; g.B = w.w1; g.C = hbuf; g.bias = w.b1;
         g.M = M; g.N = 4 * dm; g.K = dm; g.lda = dm; g.ldb = dm; g.ldc = 4 * dm; g.gelu = true;
         gemm(g);
       }
       {
         GemmArgs g;
-        g.A = e->enc_h.p; g.B = w.w2; g.C = x; g.bias = w.b2; g.residual = x;
+        g.A = hbuf; g.B = w.w2; g.C = x; g.bias = w.b2; g.residual = x;
         g.M = M; g.N = dm; g.K = 4 * dm; g.lda = 4 * dm; g.ldb = 4 * dm; g.ldc = dm; g.ldres = dm; g.out_fp32 = true;
         gemm(g);
       }
     }
-    layernorm<T>(x, e->w.ln_post_g, e->w.ln_post_b, e->enc_out.as<T>(), M, dm, st);
+    layernorm<T>(x, e->w.ln_post_g, e->w.ln_post_b, out, M, dm, st);
   }
 
   // cross K/V of every decoder layer for batch element `bi` -> cross-cache slot q (one launch, z = layer)
@@ -427,7 +437,29 @@ void engine_fold_layernorms(bw_engine* e) {
   e->named_master.clear();
 }
 
-template <typename T> static void encoder_forward_t(bw_engine* e, int nb) { Impl<T>(e).encoder_forward(nb); }
+// Large batches run as two sub-batches on two streams: the persistent GEMM / attention kernels end in a partly
+// filled last wave (e.g. 1410 tile pairs over 74 SM pairs) and every kernel boundary drains the machine; a second,
+// independent kernel chain fills those gaps (profiles/r1_notes.md: ~10 % of the encoder at batch 16).
+template <typename T> static void encoder_forward_t(bw_engine* e, int nb) {
+  static const bool no_split = getenv("B200W_ENC_NO_SPLIT") != nullptr;
+  static const int ways_env = getenv("B200W_ENC_WAYS") ? atoi(getenv("B200W_ENC_WAYS")) : 2;
+  const int ways = std::max(1, std::min({ways_env, (int)bw_engine::kEncStreams + 1, nb / 2}));
+  if (no_split || ways < 2 || !e->enc_streams[0]) return Impl<T>(e).encoder_forward(nb);
+  BW_CUDA(cudaEventRecord(e->enc_fork, e->stream));           // conv1 operands of all windows are in A1
+  int w0 = 0;
+  for (int k = 0; k < ways; ++k) {
+    const int n = (nb - w0) / (ways - k);
+    if (k == 0) Impl<T>(e).encoder_forward(n, w0);
+    else {
+      cudaStream_t s2 = e->enc_streams[k - 1];
+      BW_CUDA(cudaStreamWaitEvent(s2, e->enc_fork, 0));
+      Impl<T>(e, s2).encoder_forward(n, w0);
+      BW_CUDA(cudaEventRecord(e->enc_join[k - 1], s2));
+      BW_CUDA(cudaStreamWaitEvent(e->stream, e->enc_join[k - 1], 0));
+    }
+    w0 += n;
+  }
+}
 void engine_encoder_forward(bw_engine* e, int nb) {
   if (e->fp32) encoder_forward_t<float>(e, nb); else encoder_forward_t<bf16>(e, nb);
 }

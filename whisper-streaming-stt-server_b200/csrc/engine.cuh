@@ -168,6 +168,9 @@ struct bw_engine {
   std::atomic<int> refs{1};
   int state = 0;           // 0 = created, 1 = finalized
   cudaStream_t stream = nullptr;
+  static constexpr int kEncStreams = 3;                // extra streams for the sub-batches of a split encoder batch
+  cudaStream_t enc_streams[kEncStreams]{};
+  cudaEvent_t enc_fork = nullptr, enc_join[kEncStreams]{};
   static constexpr int kFrontStreams = 4;
   cudaStream_t front[kFrontStreams]{};
   std::mutex front_mu[kFrontStreams];
