@@ -47,7 +47,8 @@ class FakeEngine:
         self.script = script or []
         self.all_decodes = []
 
-    def open_call(self, audio):
+    def open_call(self, audio, sample_rate=None):
+        self.last_sample_rate = sample_rate
         return FakeCall(self, audio)
 
 
@@ -231,3 +232,28 @@ def test_detokenizer_placeholder():
     d = Detokenizer(vocab_for(51865))
     v = vocab_for(51865)
     assert d.decode([5, v.timestamp_begin + 3, 7]) == "<5><7>" and d.encode("hi") is None
+
+
+def test_side_doors_route_through_the_same_seek_loop(fake_backend):
+    """transcribe_pcm16 hands the raw bytes + rate to the engine (no host-side conversion); transcribe_many keeps the
+    input order, accepts one options dict or one per call, and re-raises the first failure after all calls finished"""
+    v = vocab_for(51865)
+    tb = v.timestamp_begin
+    res = {"tokens": [tb, 100, 200, tb + 50], "sum_logprob": -1.0, "avg_logprob": -0.2, "no_speech_prob": 0.1, "n_steps": 4,
+           "t_queue": 0.0, "t_encode": 0.0, "t_decode": 0.0}
+    b, eng = fake_backend([res])
+    pcm = (np.arange(48000) % 200 - 100).astype(np.int16).tobytes()
+    segs, info = b.transcribe_pcm16(pcm, 48000, {"language": "en", "beam_size": 1})
+    assert eng.last_sample_rate == 48000 and len(segs) == 1 and info.language == "en"
+    assert b.transcribe_pcm16(b"", 8000, {"language": "en"})[0] == []
+    with pytest.raises(ValueError):
+        b.transcribe_pcm16(pcm, -1, {})
+    audios = [np.zeros(16000 * (i + 1), np.float32) for i in range(3)]
+    out = b.transcribe_many(audios + [pcm], {"language": "en"}, [None, None, None, 48000])
+    assert len(out) == 4 and all(len(s) == 1 for s, _ in out)
+    out2 = b.transcribe_many(audios, [{"language": "en"}, {"language": "de"}, {"language": "en"}])
+    assert [i.language for _, i in out2] == ["en", "de", "en"]
+    with pytest.raises(ValueError):
+        b.transcribe_many(audios, {"language": "en", "beam_size": 99})  # every call fails on the option check
+    with pytest.raises(ValueError):
+        b.transcribe_many(audios, [{}], None)
