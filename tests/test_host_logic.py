@@ -198,7 +198,10 @@ def test_checkpoint_resolution(tmp_path, monkeypatch):
     with pytest.raises(RuntimeError):
         bk.load_checkpoint("definitely-not-a-model")
     d3, sd3, _ = bk.load_checkpoint("random:test-v3:3")
-    assert d3.n_mels == 128 and sd3["decoder.token_embedding.weight"].shape == (51866, 128)
+    assert d3.n_mels == 128 and dict(sd3.items())["decoder.token_embedding.weight"].shape == (51866, 128)
+    # the lazy view yields exactly the eager state dict (same generator order)
+    eager = random_state_dict(MODEL_DIMS["test-v3"], 3, emb_std=0.1)
+    assert all(torch.equal(t, eager[k]) for k, t in sd3.items())
 
 
 def test_registration_wraps_reference_get_backend(monkeypatch):

@@ -29,7 +29,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from .engine import Engine
-from .synth import MODEL_DIMS, ModelDims, random_state_dict
+from .synth import MODEL_DIMS, LazyRandomState, ModelDims, random_state_dict
 from .vocab import Detokenizer, Vocab, normalize_language, vocab_for
 
 LOGGER = logging.getLogger("stt_server.model_backend")
@@ -113,7 +113,8 @@ def load_checkpoint(model_size: str) -> Tuple[ModelDims, Dict[str, Any], str]:
         seed = int(parts[2]) if len(parts) > 2 else 0
         emb_std = float(parts[3]) if len(parts) > 3 else 0.1
         eot_bias = float(parts[4]) if len(parts) > 4 else 0.0
-        return MODEL_DIMS[name], random_state_dict(MODEL_DIMS[name], seed, emb_std=emb_std, eot_bias=eot_bias), model_size
+        # materialised one tensor at a time while the engine loads it (6 GB of host memory per process otherwise)
+        return MODEL_DIMS[name], LazyRandomState(MODEL_DIMS[name], seed, emb_std=emb_std, eot_bias=eot_bias), model_size
     candidates = [model_size]
     for root in (os.environ.get("B200_WHISPER_MODEL_DIR"), os.path.expanduser("~/.cache/whisper")):
         if root:

@@ -94,20 +94,15 @@ def state_dict_spec(dims: ModelDims):
     return spec
 
 
-def random_state_dict(dims: ModelDims, seed: int = 0, device: str = "cpu", eot_bias: float = 0.0,
-                      emb_std: float = 1.0):
-    """Seeded random init: torch-default distributions (Linear/Conv U(+-1/sqrt(fan_in)), LayerNorm
-    1/0 perturbed so the affine is exercised, Embedding N(0, emb_std^2); a small emb_std breaks the tied-embedding
-    self-loop that makes a random model repeat one token), positional embedding N(0, 0.01^2).
-
-    `eot_bias` c > 0 adds c * E[eot] / |E[eot]|^2 to `decoder.ln.bias`, i.e. a constant +c on the
-    end-of-text logit, so hypotheses end after a geometric number of tokens (exercises the early-exit
-    path; 0 keeps the no-EOT worst case: 224 steps per window)."""
+def random_state_items(dims: ModelDims, seed: int = 0, device: str = "cpu", eot_bias: float = 0.0, emb_std: float = 1.0):
+    """Generator over (name, tensor) in `state_dict_spec` order; `random_state_dict` is dict() of it.  Consumers that
+    load one tensor at a time (Engine._load) never hold more than one tensor on the host (large-v3: 265 MB instead of
+    6.2 GB per process, which matters with one process per GPU)."""
     import torch
 
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    out = {}
+    eot_row = None
     for name, shape, kind, fan_in in state_dict_spec(dims):
         if kind == "u":
             bound = 1.0 / np.sqrt(fan_in)
@@ -122,12 +117,33 @@ def random_state_dict(dims: ModelDims, seed: int = 0, device: str = "cpu", eot_b
             t = 0.01 * torch.randn(shape, generator=g, device=device)
         else:  # pragma: no cover
             raise AssertionError(kind)
-        out[name] = t
-    if eot_bias > 0:
-        eot = 50257 if dims.n_vocab >= 51865 else 50256
-        e = out["decoder.token_embedding.weight"][eot]
-        out["decoder.ln.bias"] = out["decoder.ln.bias"] + eot_bias * e / (e * e).sum()
-    return out
+        if eot_bias > 0:
+            if name == "decoder.token_embedding.weight":
+                eot_row = t[50257 if dims.n_vocab >= 51865 else 50256].clone()
+            elif name == "decoder.ln.bias":  # comes after the embedding in the spec
+                t = t + eot_bias * eot_row / (eot_row * eot_row).sum()
+        yield name, t
+
+
+class LazyRandomState:
+    """dict-like view (`items()` only) of a seeded random checkpoint that materialises one tensor at a time."""
+
+    def __init__(self, dims: ModelDims, seed: int = 0, eot_bias: float = 0.0, emb_std: float = 1.0):
+        self.dims, self.seed, self.eot_bias, self.emb_std = dims, seed, eot_bias, emb_std
+
+    def items(self):
+        return random_state_items(self.dims, self.seed, eot_bias=self.eot_bias, emb_std=self.emb_std)
+
+
+def random_state_dict(dims: ModelDims, seed: int = 0, device: str = "cpu", eot_bias: float = 0.0,
+                      emb_std: float = 1.0):
+    """Seeded random init: torch-default distributions (Linear/Conv U(+-1/sqrt(fan_in)), LayerNorm
+    1/0 perturbed so the affine is exercised, Embedding N(0, emb_std^2); a small emb_std breaks the tied-embedding
+    self-loop that makes a random model repeat one token), positional embedding N(0, 0.01^2).
+
+    `eot_bias` c > 0 adds c * E[eot] / |E[eot]|^2 to `decoder.ln.bias`, i.e. a constant +c on the
+    end-of-text logit (exercises the early-exit path; 0 keeps the no-EOT worst case: 224 steps per window)."""
+    return dict(random_state_items(dims, seed, device=device, eot_bias=eot_bias, emb_std=emb_std))
 
 
 def synth_audio(seed: int, seconds: float, sample_rate: int = 16000) -> np.ndarray:
