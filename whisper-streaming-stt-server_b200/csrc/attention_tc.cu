@@ -546,8 +546,24 @@ __device__ __forceinline__ void v5_row_exp(uint32_t* sv, int kvalid, float sl2, 
     ffma2(a0, a1, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]), sl2, sl2, neg_m, neg_m);
     sv[i] = __float_as_uint(a0); sv[i + 1] = __float_as_uint(a1);
   }
+#ifdef V6_POLY_PERIOD
+  // Experiment kept for the record (FlashAttention-4's trick): one pair in every V6_POLY_PERIOD / 2 pairs computed by
+  // exp2_poly2 on the FMA / ALU pipes instead of MUFU.EX2.  Measured at batch 16: 50 % -> 354 us, 25 % -> 318 us,
+  // 12.5 % -> 316 us, 0 % -> 315 us per layer: the exp phase is not XU-throughput-bound here, the extra issue slots cost
+  // more than the XU cycles they free (profiles/r1_notes.md).
+#pragma unroll
+  for (int i = 0; i < 64; i += 2) {
+    if ((i % (2 * V6_POLY_PERIOD / 2)) == V6_POLY_PERIOD - 2) {
+      exp2_poly2(sv[i], sv[i + 1], __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+    } else {
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(sv[i]));
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(sv[i + 1]));
+    }
+  }
+#else
 #pragma unroll
   for (int i = 0; i < 64; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(sv[i]));
+#endif
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     uint32_t pk[4];

@@ -347,6 +347,33 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
 }
 
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  uint64_t a, b, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
+// 2^x for a PAIR of arguments on the FMA / ALU pipes instead of the 16-lane-per-SM XU pipe (the trick FlashAttention-4
+// uses for head dim 64, where the exponentials, not the tensor core, are the bound): x = n + f with n = floor-ish
+// (magic-number rounding), 2^f by a degree-3 minimax polynomial on [0, 1] (max relative error 7.5e-5, far below the
+// bf16 precision of the consumer), 2^n by adding n to the exponent field (one LEA).  x is clamped at -126.
+__device__ __forceinline__ void exp2_poly2(uint32_t& r0, uint32_t& r1, float x0, float x1) {
+  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23: adding it rounds to an integer held in the low mantissa bits
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  float t0, t1, n0, n1, f0, f1, p0, p1;
+  fadd2(t0, t1, x0, x1, kMagic - 0.5f, kMagic - 0.5f);   // t = magic + round(x - 0.5)
+  fadd2(n0, n1, t0, t1, -kMagic, -kMagic);               // n as a float (exact)
+  ffma2(f0, f1, n0, n1, -1.f, -1.f, x0, x1);             // f = x - n in [0, 1]
+  ffma2(p0, p1, f0, f1, 0.07802452264047964f, 0.07802452264047964f, 0.226067155427483f, 0.226067155427483f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.6958335404947528f, 0.6958335404947528f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.9999252185627154f, 0.9999252185627154f);
+  r0 = __float_as_uint(p0) + (__float_as_uint(t0) << 23);  // p * 2^n
+  r1 = __float_as_uint(p1) + (__float_as_uint(t1) << 23);
+}
+
 // fp32 -> bf16 on the integer ALU (round to nearest, ties away; operands are finite and >= 0 here): F2FP.PACK_AB
 // issues on the XU pipe, which the attention softmax needs for MUFU.EX2.
 __device__ __forceinline__ uint32_t bf16_round_bits(float x) { return (__float_as_uint(x) + 0x8000u) & 0xffff0000u; }
