@@ -18,6 +18,7 @@ void engine_decoder_layers(bw_engine* e, DecGroup& G, int R, int n_groups, int m
                            const int* grp_x, const int* lrow_src);
 void engine_init_requests(bw_engine* e, const int* init_dev, int n);
 void engine_fold_layernorms(bw_engine* e);
+void engine_gather_final(bw_engine* e, const int* list_dev, int n, int blob_bytes, unsigned char* out_dev);
 }  // namespace bw
 
 using namespace bw;
@@ -374,23 +375,17 @@ void decode_step(bw_engine* e, Ctl* ctls) {
   if (!done.empty()) {
     const size_t blob = fin_blob_bytes(e);
     size_t nd = 0;
-    for (Request* r : done) {
+    for (Request* r : done) {  // (q, first sequence, hypotheses) of every finished decode; h_init is idle during a step
       if (r->kind != REQ_DECODE) continue;
-      unsigned char* b = e->h_fin + nd * blob;
-      const int q = r->q;
-      const int n_ctx = d.n_text_ctx;
-      BW_CUDA(cudaMemcpyAsync(b, e->rs.fin_score + q * kMaxFinished, kMaxFinished * 4, cudaMemcpyDeviceToHost, e->stream));
-      BW_CUDA(cudaMemcpyAsync(b + kMaxFinished * 4, e->rs.fin_pos + q * kMaxFinished, kMaxFinished * 4, cudaMemcpyDeviceToHost, e->stream));
-      BW_CUDA(cudaMemcpyAsync(b + kMaxFinished * 8, e->rs.fin_slot + q * kMaxFinished, kMaxFinished * 4, cudaMemcpyDeviceToHost, e->stream));
-      BW_CUDA(cudaMemcpyAsync(b + kMaxFinished * 12, e->rs.n_finished + q, 4, cudaMemcpyDeviceToHost, e->stream));
-      BW_CUDA(cudaMemcpyAsync(b + kMaxFinished * 12 + 4, e->rs.no_speech_prob + q, 4, cudaMemcpyDeviceToHost, e->stream));
-      BW_CUDA(cudaMemcpyAsync(b + kMaxFinished * 12 + 8, e->ss.sum_logprob + r->first_seq, (size_t)r->G * 4, cudaMemcpyDeviceToHost, e->stream));
-      unsigned char* tb = b + kMaxFinished * 12 + 8 + kMaxBeam * 4;
-      BW_CUDA(cudaMemcpyAsync(tb, e->rs.tok + (size_t)q * n_ctx * kMaxBeam, (size_t)n_ctx * kMaxBeam * 4, cudaMemcpyDeviceToHost, e->stream));
-      BW_CUDA(cudaMemcpyAsync(tb + (size_t)n_ctx * kMaxBeam * 4, e->rs.parent + (size_t)q * n_ctx * kMaxBeam, (size_t)n_ctx * kMaxBeam,
-                              cudaMemcpyDeviceToHost, e->stream));
-      e->stat_d2h += (long long)blob;
+      int* rec = e->h_init + nd * 3;
+      rec[0] = r->q; rec[1] = r->first_seq; rec[2] = r->G;
       ++nd;
+    }
+    if (nd > 0) {
+      BW_CUDA(cudaMemcpyAsync(e->d_init.p, e->h_init, nd * 12, cudaMemcpyHostToDevice, e->stream));
+      engine_gather_final(e, e->d_init.as<int>(), (int)nd, (int)blob, e->d_fin.as<unsigned char>());
+      BW_CUDA(cudaMemcpyAsync(e->h_fin, e->d_fin.p, nd * blob, cudaMemcpyDeviceToHost, e->stream));
+      e->stat_d2h += (long long)(nd * blob);
     }
     BW_CUDA(cudaStreamSynchronize(e->stream));
     nd = 0;
@@ -749,6 +744,7 @@ int bw_engine_finalize(bw_engine* e) {
     BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_flags), (size_t)Q * 4));
     e->h_fin_bytes = fin_blob_bytes(e) * (size_t)Q;
     BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_fin), e->h_fin_bytes));
+    e->d_fin.alloc(e->h_fin_bytes);
   }
   // call buffers: sized for 30 s of audio; longer calls allocate on demand
   e->call_pcm_cap = 480000 + 1600;

@@ -34,6 +34,32 @@ __global__ void init_requests_kernel(const int* __restrict__ init, int n, ReqSta
   for (int i = threadIdx.x; i < G * n_ctx; i += blockDim.x) a[i] = 0;
 }
 
+// Finished requests -> one contiguous blob each (layout: finalize_decode in api.cu), so that the host needs ONE
+// device-to-host copy per step instead of eight per finished request.
+__global__ void gather_final_kernel(const int* __restrict__ list, ReqState rs, SeqState ss, int n_ctx, int blob_bytes,
+                                    unsigned char* __restrict__ out) {
+  const int q = list[blockIdx.x * 3], first_seq = list[blockIdx.x * 3 + 1], G = list[blockIdx.x * 3 + 2];
+  unsigned char* b = out + (size_t)blockIdx.x * blob_bytes;
+  float* f = reinterpret_cast<float*>(b);
+  int* i32 = reinterpret_cast<int*>(b);
+  for (int i = threadIdx.x; i < kMaxFinished; i += blockDim.x) {
+    f[i] = rs.fin_score[q * kMaxFinished + i];
+    i32[kMaxFinished + i] = rs.fin_pos[q * kMaxFinished + i];
+    i32[2 * kMaxFinished + i] = rs.fin_slot[q * kMaxFinished + i];
+  }
+  if (threadIdx.x == 0) {
+    i32[3 * kMaxFinished] = rs.n_finished[q];
+    f[3 * kMaxFinished + 1] = rs.no_speech_prob[q];
+  }
+  for (int i = threadIdx.x; i < kMaxBeam; i += blockDim.x) f[3 * kMaxFinished + 2 + i] = i < G ? ss.sum_logprob[first_seq + i] : 0.f;
+  int* tok = i32 + 3 * kMaxFinished + 2 + kMaxBeam;
+  const int* tsrc = rs.tok + (size_t)q * n_ctx * kMaxBeam;
+  for (int i = threadIdx.x; i < n_ctx * kMaxBeam; i += blockDim.x) tok[i] = tsrc[i];
+  unsigned char* par = reinterpret_cast<unsigned char*>(tok + (size_t)n_ctx * kMaxBeam);
+  const unsigned char* psrc = rs.parent + (size_t)q * n_ctx * kMaxBeam;
+  for (int i = threadIdx.x; i < n_ctx * kMaxBeam; i += blockDim.x) par[i] = psrc[i];
+}
+
 inline float bf16_bits_to_float(uint16_t b) {
   uint32_t u = (uint32_t)b << 16;
   float f;
@@ -482,6 +508,12 @@ void engine_decoder_layers(bw_engine* e, DecGroup& G, int R, int n_groups, int m
     c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.row_bpos = row_bpos; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
     Impl<bf16>(e, G.stream).decoder_layers(c, G);
   }
+}
+void engine_gather_final(bw_engine* e, const int* list_dev, int n, int blob_bytes, unsigned char* out_dev) {
+  if (n <= 0) return;
+  gather_final_kernel<<<n, 256, 0, e->stream>>>(list_dev, e->rs, e->ss, e->dims.n_text_ctx, blob_bytes, out_dev);
+  BW_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
 }
 void engine_init_requests(bw_engine* e, const int* init_dev, int n) {
   if (n <= 0) return;

@@ -209,6 +209,7 @@ struct bw_engine {
   size_t ctrl_ints = 0;
   int* h_flags = nullptr;     // pinned [Q] completed flags
   unsigned char* h_fin = nullptr;  // pinned scratch for finalisation
+  bw::DevBuf d_fin;                // device side of it (gather_final_kernel packs finished requests here)
   size_t h_fin_bytes = 0;
 
   // call buffers
