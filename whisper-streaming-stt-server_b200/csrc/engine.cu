@@ -468,23 +468,21 @@ void engine_fold_layernorms(bw_engine* e) {
 // independent kernel chain fills those gaps (profiles/r1_notes.md: ~10 % of the encoder at batch 16).
 template <typename T> static void encoder_forward_t(bw_engine* e, int nb) {
   static const bool no_split = getenv("B200W_ENC_NO_SPLIT") != nullptr;
-  static const int ways_env = getenv("B200W_ENC_WAYS") ? atoi(getenv("B200W_ENC_WAYS")) : 2;
-  const int ways = std::max(1, std::min({ways_env, (int)bw_engine::kEncStreams + 1, nb / 2}));
-  if (no_split || ways < 2 || !e->enc_streams[0]) return Impl<T>(e).encoder_forward(nb);
+  static const int chunk_env = getenv("B200W_ENC_CHUNK") ? atoi(getenv("B200W_ENC_CHUNK")) : 8;
+  if (no_split || nb < 4 || !e->enc_streams[0]) return Impl<T>(e).encoder_forward(nb);
+  // sub-batches of <= `chunk` windows, dealt alternately to the engine stream and one extra stream
+  const int chunk = std::max(2, std::min(chunk_env, (nb + 1) / 2));
   BW_CUDA(cudaEventRecord(e->enc_fork, e->stream));           // conv1 operands of all windows are in A1
-  int w0 = 0;
-  for (int k = 0; k < ways; ++k) {
-    const int n = (nb - w0) / (ways - k);
-    if (k == 0) Impl<T>(e).encoder_forward(n, w0);
-    else {
-      cudaStream_t s2 = e->enc_streams[k - 1];
-      BW_CUDA(cudaStreamWaitEvent(s2, e->enc_fork, 0));
-      Impl<T>(e, s2).encoder_forward(n, w0);
-      BW_CUDA(cudaEventRecord(e->enc_join[k - 1], s2));
-      BW_CUDA(cudaStreamWaitEvent(e->stream, e->enc_join[k - 1], 0));
-    }
-    w0 += n;
+  cudaStream_t s2 = e->enc_streams[0];
+  BW_CUDA(cudaStreamWaitEvent(s2, e->enc_fork, 0));
+  int k = 0;
+  for (int w0 = 0; w0 < nb; w0 += chunk, ++k) {
+    const int n = std::min(chunk, nb - w0);
+    if ((k & 1) == 0) Impl<T>(e).encoder_forward(n, w0);
+    else Impl<T>(e, s2).encoder_forward(n, w0);
   }
+  BW_CUDA(cudaEventRecord(e->enc_join[0], s2));
+  BW_CUDA(cudaStreamWaitEvent(e->stream, e->enc_join[0], 0));
 }
 void engine_encoder_forward(bw_engine* e, int nb) {
   if (e->fp32) encoder_forward_t<float>(e, nb); else encoder_forward_t<bf16>(e, nb);
