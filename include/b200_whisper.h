@@ -92,6 +92,14 @@ typedef struct bw_decode_opts {
   int32_t without_timestamps;     /* 1 disables ApplyTimestampRules */
   int32_t suppress_blank;         /* upstream default 1 */
   int32_t max_initial_timestamp_index; /* < 0 -> None; upstream default 50 */
+  /* GreedyDecoder at temperature > 0 (one rung of transcribe.py's decode_with_fallback ladder): next token ~
+   * Categorical(logits / temperature), drawn by Gumbel-max with a counter-based generator keyed by
+   * (seed, hypothesis, position, token id) -- reproducible for a given seed whatever the batch it runs in.
+   * Needs beam_size == 0.  best_of = hypotheses sampled per window (0 -> 1); the best by the length-penalised
+   * sum of log-probabilities (MaximumLikelihoodRanker) is returned. */
+  float temperature;              /* 0 -> arg-max (fields below ignored) */
+  int32_t best_of;
+  uint32_t seed_lo, seed_hi;
 } bw_decode_opts;
 
 #define BW_MAX_TOKENS 448

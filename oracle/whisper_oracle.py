@@ -16,8 +16,14 @@ PARITY UNPINNED (see `oracle/__init__.py`).  Deviations, all explicit:
 * no tokenizer assets -> text is rendered by `render_text` (placeholder) and the
   suppress tables come from `oracle/tables.py`;
 * `decoder.positional_embedding` is `torch.empty` upstream; callers must supply it;
-* word timestamps / temperature fallback ladders are not restated (the server's
-  profiles use scalar temperature 0.0, `config/model.yaml:42-65`).
+* word timestamps are not restated (DTW alignment; out of scope, SURVEY.md A.7);
+* temperature > 0: upstream draws `Categorical(logits / T).sample()` from torch's global
+  generator, which no other implementation can reproduce.  With `sample_seed=None` the
+  oracle does exactly that; with an integer seed it draws the same distribution by
+  Gumbel-max from the counter-based generator `gumbel_noise` below, which is OUR
+  definition (restated bit for bit by `sample_uniform` in csrc/sampling.cu) so that the
+  device path can be checked token for token.  The fallback ladder itself
+  (`decode_with_fallback`) follows upstream transcribe.py.
 """
 from __future__ import annotations
 
@@ -229,6 +235,29 @@ class DecodingOptions:
     suppress_blank: bool = True
     without_timestamps: bool = False
     max_initial_timestamp: Optional[float] = 1.0
+    sample_seed: Optional[int] = None  # not upstream: see the module docstring (temperature > 0)
+
+
+_M64 = (1 << 64) - 1
+
+
+def window_seed(base_seed: int, seek: int, attempt: int) -> int:
+    """Seed of one decode attempt (window at `seek`, rung `attempt` of the temperature ladder)."""
+    return (base_seed + 0x632BE59BD9B4E019 * (seek + 1) + 0xD1342543DE82EF95 * (attempt + 1)) & _M64
+
+
+def gumbel_noise(seed: int, stream: int, pos: int, n_vocab: int) -> np.ndarray:
+    """-log(-log(u)) for every token id, u = the 23-bit uniform of (seed, hypothesis, position, id):
+    splitmix64 finaliser over the packed key.  float64 here; the device evaluates the logs in fp32."""
+    ids = np.arange(n_vocab, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64((seed + 0x9E3779B97F4A7C15 * (stream + 1)) & _M64)
+        z = z ^ ((np.uint64(pos) << np.uint64(32)) | ids)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = ((z >> np.uint64(41)).astype(np.float64) + 0.5) / 8388608.0
+    return -np.log(-np.log(u))
 
 
 @dataclass
@@ -322,11 +351,26 @@ class _Filters:
 
 
 class _Greedy:
-    def __init__(self, eot: int):
+    def __init__(self, eot: int, temperature: float = 0.0, sample_seed: Optional[int] = None):
         self.eot = eot
+        self.temperature = temperature
+        self.sample_seed = sample_seed
+        self.min_key_margin = float("inf")  # sampling mode: min top1 - top2 of (logits / T + noise)
 
     def update(self, tokens, logits, sum_logprobs, cache):
-        next_tokens = logits.argmax(dim=-1)
+        if self.temperature == 0:
+            next_tokens = logits.argmax(dim=-1)
+        elif self.sample_seed is None:
+            next_tokens = torch.distributions.Categorical(logits=logits / self.temperature).sample()
+        else:
+            pos = tokens.shape[1]
+            keys = (logits.double() / self.temperature).numpy().copy()
+            for j in range(keys.shape[0]):
+                keys[j] += gumbel_noise(self.sample_seed, j, pos, keys.shape[1])
+                if int(tokens[j, -1]) != self.eot:
+                    top2 = np.partition(keys[j], -2)[-2:]
+                    self.min_key_margin = min(self.min_key_margin, float(top2[1] - top2[0]))
+            next_tokens = torch.from_numpy(keys.argmax(axis=-1))
         logprobs = F.log_softmax(logits.float(), dim=-1)
         current = logprobs[torch.arange(logprobs.shape[0]), next_tokens]
         sum_logprobs += current * (tokens[:, -1] != self.eot)
@@ -413,7 +457,7 @@ def decode_window(model: Whisper, mel_segment: torch.Tensor, opts: DecodingOptio
     if opts.beam_size is not None:
         decoder = _Beam(opts.beam_size, lay.eot, opts.patience)
     else:
-        decoder = _Greedy(lay.eot)
+        decoder = _Greedy(lay.eot, opts.temperature, opts.sample_seed)
     filters = _Filters(lay, sample_begin, opts, dims.n_audio_ctx)
 
     if audio_features is None:
@@ -432,10 +476,11 @@ def decode_window(model: Whisper, mel_segment: torch.Tensor, opts: DecodingOptio
             no_speech_prob = float(probs_at_sot[0, lay.no_speech])
         logits = logits[:, -1]
         filters.apply(logits, tokens)
-        top2 = logits.topk(2, dim=-1).values
-        m = float((top2[:, 0] - top2[:, 1]).min())
-        if np.isfinite(m):
-            min_margin = min(min_margin, m)
+        if opts.temperature == 0 or opts.beam_size is not None:
+            top2 = logits.topk(2, dim=-1).values
+            m = float((top2[:, 0] - top2[:, 1]).min())
+            if np.isfinite(m):
+                min_margin = min(min_margin, m)
         tokens, completed = decoder.update(tokens, logits, sum_logprobs, cache)
         if completed or tokens.shape[-1] > n_ctx:
             break
@@ -463,7 +508,7 @@ def decode_window(model: Whisper, mel_segment: torch.Tensor, opts: DecodingOptio
         temperature=opts.temperature,
         compression_ratio=compression_ratio(text),
         sum_logprob=cand_lp[0][sel],
-        min_margin=min_margin,
+        min_margin=min_margin if (opts.temperature == 0 or opts.beam_size is not None) else decoder.min_key_margin,
     )
 
 
@@ -472,15 +517,17 @@ def transcribe(
     model: Whisper,
     audio: np.ndarray,
     *,
-    temperature: float = 0.0,
+    temperature=0.0,
     compression_ratio_threshold: Optional[float] = 2.4,
     logprob_threshold: Optional[float] = -1.0,
     no_speech_threshold: Optional[float] = 0.6,
     condition_on_previous_text: bool = True,
     initial_prompt_tokens: Optional[Sequence[int]] = None,
+    sample_seed: Optional[int] = None,
     **decode_options,
 ) -> dict:
-    """Scalar-temperature restatement; returns upstream's dict plus `windows` diagnostics."""
+    """`temperature`: a scalar or upstream's fallback ladder (a tuple, tried in order by `decode_with_fallback`).
+    Returns upstream's dict plus `windows` diagnostics (the accepted DecodingResult of every window)."""
     dims, lay = model.dims, model.layout
     decode_options.pop("fp16", None)
     decode_options.pop("word_timestamps", None)
@@ -494,11 +541,34 @@ def transcribe(
             _, language_probs = detect_language(model, pad_or_trim(mel, N_FRAMES))
             decode_options["language"] = max(language_probs, key=language_probs.get)
     language = decode_options["language"]
-    if temperature > 0:
-        decode_options.pop("beam_size", None)
-        decode_options.pop("patience", None)
-    else:
-        decode_options.pop("best_of", None)
+
+    def decode_with_fallback(segment: torch.Tensor, seek: int, prompt: Sequence[int]) -> DecodingResult:
+        temperatures = [temperature] if isinstance(temperature, (int, float)) else list(temperature)
+        decode_result = None
+        audio_features = None
+        for attempt, t in enumerate(temperatures):
+            kwargs = dict(decode_options)
+            if t > 0:  # disable beam_size and patience when t > 0
+                kwargs.pop("beam_size", None)
+                kwargs.pop("patience", None)
+            else:  # disable best_of when t == 0
+                kwargs.pop("best_of", None)
+            seed = None if sample_seed is None else window_seed(sample_seed, seek, attempt)
+            opts = DecodingOptions(**kwargs, temperature=t, prompt=prompt, sample_seed=seed)
+            if audio_features is None and len(temperatures) > 1:
+                audio_features = model.encode(segment[None].float())  # upstream re-encodes every rung: same numbers
+            decode_result = decode_window(model, segment, opts, audio_features)
+            needs_fallback = False
+            if compression_ratio_threshold is not None and decode_result.compression_ratio > compression_ratio_threshold:
+                needs_fallback = True  # too repetitive
+            if logprob_threshold is not None and decode_result.avg_logprob < logprob_threshold:
+                needs_fallback = True  # average log probability is too low
+            if (no_speech_threshold is not None and decode_result.no_speech_prob > no_speech_threshold
+                    and logprob_threshold is not None and decode_result.avg_logprob < logprob_threshold):
+                needs_fallback = False  # silence
+            if not needs_fallback:
+                break
+        return decode_result
 
     seek = 0
     input_stride = N_FRAMES // dims.n_audio_ctx
@@ -516,8 +586,7 @@ def transcribe(
         segment_size = min(N_FRAMES, content_frames - seek)
         mel_segment = pad_or_trim(mel[:, seek : seek + segment_size], N_FRAMES)
         segment_duration = segment_size * HOP_LENGTH / SAMPLE_RATE
-        opts = DecodingOptions(**decode_options, temperature=temperature, prompt=all_tokens[prompt_reset_since:])
-        result = decode_window(model, mel_segment, opts)
+        result = decode_with_fallback(mel_segment, seek, all_tokens[prompt_reset_since:])
         windows.append(result)
         tokens = result.tokens
 
@@ -604,12 +673,12 @@ def normalize_options(options: dict) -> dict:
     return {k: v for k, v in opts.items() if k in SUPPORTED_OPTIONS}
 
 
-def backend_transcribe(model: Whisper, audio: np.ndarray, options: dict):
+def backend_transcribe(model: Whisper, audio: np.ndarray, options: dict, sample_seed: Optional[int] = None):
     """TorchWhisperBackend.transcribe -> ([(start, end, text)], (language, -1.0), raw result)."""
     opts = normalize_options(options)
     for k in ("prepend_punctuations", "append_punctuations", "initial_prompt", "prompt"):
         opts.pop(k, None)  # need tokenizer assets / not reachable through the server's profiles
-    result = transcribe(model, audio, **opts)
+    result = transcribe(model, audio, sample_seed=sample_seed, **opts)
     segments = [(float(s["start"]), float(s["end"]), str(s["text"])) for s in result["segments"]]
     return segments, (result["language"] or "", -1.0), result
 

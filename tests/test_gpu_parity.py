@@ -157,6 +157,115 @@ def test_transcribe_bf16_first_divergence():
     assert total > 0
 
 
+def _raw_key(result):
+    return [(s["seek"], round(s["start"], 3), round(s["end"], 3), list(s["tokens"]), s["temperature"]) for s in result["segments"]]
+
+
+@pytest.mark.parametrize("name", ["test-tiny", "test-v3"])
+def test_temperature_sampling_token_exact_fp32(name):
+    """GreedyDecoder at temperature > 0 with best_of hypotheses: the device draws Categorical(logits / T) by Gumbel-max
+    from the counter-based generator the oracle restates (`gumbel_noise`), so the sampled token streams, the ranking
+    among the best_of hypotheses and the log-probabilities can be checked exactly.  Cases whose smallest top-1/top-2
+    margin of the perturbed logits is within fp32 noise are skipped, and enough must remain."""
+    checked = 0
+    for kw, extra in ((dict(eot_bias=4.0), {}), (dict(), dict(sample_len=20))):
+        b = backend(name, "float32", **kw)
+        for seed, temp, best_of in ((11, 0.7, 3), (12, 1.0, 5), (13, 0.2, 1), (14, 0.5, 8), (15, 0.9, None)):
+            opts = dict(REALTIME, language="en", temperature=temp, best_of=best_of)
+            if best_of is None:
+                opts.pop("best_of")
+            audio = synth_audio(40 + seed, 6.0)
+            model = oracle_model(name, **kw)
+            want = wo.transcribe(model, audio, sample_seed=seed, **{k: v for k, v in wo.normalize_options(opts).items()
+                                                                   if k not in ("word_timestamps",)}, **extra)
+            if min(w.min_margin for w in want["windows"]) < 5e-4:
+                continue
+            got = b.transcribe_raw(audio, _seed=seed, **b._normalize_options(opts), **extra)
+            assert _raw_key(got) == _raw_key(want), f"{name} seed {seed} T {temp} best_of {best_of}"
+            for sg, sw in zip(got["segments"], want["segments"]):
+                assert abs(sg["avg_logprob"] - sw["avg_logprob"]) < 1e-3 and abs(sg["no_speech_prob"] - sw["no_speech_prob"]) < 1e-4
+            # same seed -> same draw, whatever else the engine is batching; another seed -> another draw
+            again = b.transcribe_raw(audio, _seed=seed, **b._normalize_options(opts), **extra)
+            assert _raw_key(again) == _raw_key(got)
+            checked += 1
+    assert checked >= 6, f"only {checked} sampling cases had a usable margin"
+
+
+def test_temperature_fallback_ladder_fp32():
+    """decode_with_fallback on the device path: thresholds that no rung can meet walk the whole ladder (beam search at
+    T = 0, then sampling rungs) and keep the last result; a ladder whose first rung passes equals the scalar T = 0 run."""
+    kw = dict(eot_bias=4.0)
+    b = backend("test-tiny", "float32", **kw)
+    model = oracle_model("test-tiny", **kw)
+    audio = synth_audio(51, 8.0)
+    base = {k: v for k, v in wo.normalize_options(dict(ACCURATE, language="en", best_of=3)).items() if k != "word_timestamps"}
+    checked = 0
+    for seed in (21, 22, 23, 24):
+        o = dict(base, temperature=(0.0, 0.4, 0.8), logprob_threshold=10.0)
+        want = wo.transcribe(model, audio, sample_seed=seed, **o)
+        if min(w.min_margin for w in want["windows"]) < 5e-4:
+            continue
+        before = b.engine.stats()["windows"]
+        got = b.transcribe_raw(audio, _seed=seed, **dict(b._normalize_options(dict(ACCURATE, language="en", best_of=3)),
+                                                         temperature=(0.0, 0.4, 0.8), logprob_threshold=10.0))
+        assert _raw_key(got) == _raw_key(want)
+        assert all(s["temperature"] == 0.8 for s in got["segments"]) and got["segments"]
+        assert b.engine.stats()["windows"] - before == 3 * len(want["windows"])  # every rung re-decodes the window
+        checked += 1
+    assert checked >= 2
+    o = dict(base, temperature=(0.0, 0.2, 0.4), compression_ratio_threshold=None, logprob_threshold=None)
+    got = b.transcribe_raw(audio, **dict(b._normalize_options(dict(ACCURATE, language="en")), temperature=(0.0, 0.2, 0.4),
+                                         compression_ratio_threshold=None, logprob_threshold=None))
+    want = wo.transcribe(model, audio, **dict(o, temperature=0.0))
+    assert _raw_key(got) == _raw_key(want) and all(s["temperature"] == 0.0 for s in got["segments"])
+
+
+def test_temperature_sampling_distribution():
+    """The draws follow Categorical(softmax(filtered logits / T)): 600 seeds at the first sampled position (whose
+    support is the 51 allowed initial timestamps) against the oracle's probabilities, chi-square at ~5 sigma; and the
+    reported log-probability is the un-tempered log-softmax of the drawn token (GreedyDecoder.update)."""
+    b = backend("test-tiny", "float32")
+    model = oracle_model("test-tiny")
+    lay = model.layout
+    audio = synth_audio(61, 5.0)
+    temp = 1.3
+    mel = wo.log_mel_spectrogram(audio, model.dims.n_mels, padding=480000)
+    mel = wo.pad_or_trim(mel[:, : mel.shape[-1] - 3000], 3000)  # the window transcribe() decodes: content, then zeros
+    initial = list(lay.sot_sequence("en", "transcribe"))
+    logits = model.decode(torch.tensor([initial]), model.encode(mel[None]))[:, -1]
+    wo._Filters(lay, len(initial), wo.DecodingOptions(), model.dims.n_audio_ctx).apply(logits, torch.tensor([initial]))
+    logprobs = torch.log_softmax(logits[0].double(), -1).numpy()
+    p = torch.softmax(logits[0].double() / temp, -1).numpy()
+    n = 600
+    counts = np.zeros_like(p)
+    with b.engine.open_call(audio) as call:
+        for seed in range(n):
+            r = call.decode(0, initial, 0, None, None, None, sample_len=1, temperature=temp, best_of=1, seed=1000 + seed)
+            assert len(r["tokens"]) == 1
+            tok = r["tokens"][0]
+            assert p[tok] > 0, "drew a token the logit filters forbid"
+            assert abs(r["sum_logprob"] - logprobs[tok]) < 1e-3
+            counts[tok] += 1
+    order = np.argsort(-p)
+    exp = n * p[order]
+    keep = exp >= 5
+    obs_b = np.append(counts[order][keep], counts[order][~keep].sum())
+    exp_b = np.append(exp[keep], exp[~keep].sum())
+    if exp_b[-1] < 1e-9:
+        obs_b, exp_b = obs_b[:-1], exp_b[:-1]
+    chi2 = float(((obs_b - exp_b) ** 2 / exp_b).sum())
+    dof = len(exp_b) - 1
+    print(f"sampling chi-square {chi2:.1f} over {dof} degrees of freedom ({int(keep.sum())} tokens with expectation >= 5)")
+    assert dof >= 3 and chi2 < dof + 5 * np.sqrt(2 * dof)
+    # C-ABI contract: sampling is a GreedyDecoder mode
+    from b200_whisper._lib import B200WhisperError
+    with b.engine.open_call(audio) as call:
+        with pytest.raises(B200WhisperError):
+            call.decode(0, initial, 0, 5, 1.0, None, temperature=0.5, best_of=2)
+        with pytest.raises(B200WhisperError):
+            call.decode(0, initial, 0, None, None, None, temperature=0.5, best_of=9)
+
+
 def test_concurrent_sessions_batch_and_match_serial():
     """Many host threads (= pool handles, model_registry.py:564-606) transcribing at once are coalesced by
     the engine and still return exactly their serial results."""

@@ -123,15 +123,19 @@ def test_result_mapping_and_language(fake_backend):
 def _oracle_with_script(script, audio, n_vocab=51865, **opts):
     """Run the oracle's restatement of upstream transcribe() with decode_window replaced by the same script."""
     dims = MODEL_DIMS["test-tiny"]
-    model = types.SimpleNamespace(dims=wo.ModelDimensions(**dims.__dict__), layout=layout_for_vocab(n_vocab), is_multilingual=True)
+    model = types.SimpleNamespace(dims=wo.ModelDimensions(**dims.__dict__), layout=layout_for_vocab(n_vocab), is_multilingual=True,
+                                  encode=lambda mel: None)
     calls = []
+    _oracle_with_script.options = opt_log = []
 
     def fake_decode_window(m, mel_segment, o, audio_features=None):
         r = script[min(len(calls), len(script) - 1)]
         calls.append(list(o.prompt or []))
+        opt_log.append(o)
         return wo.DecodingResult(language="en", tokens=list(r["tokens"]), text=wo.render_text(r["tokens"], model.layout.eot).strip(),
-                                 avg_logprob=r["avg_logprob"], no_speech_prob=r["no_speech_prob"], temperature=0.0,
-                                 compression_ratio=1.0, sum_logprob=r["sum_logprob"])
+                                 avg_logprob=r["avg_logprob"], no_speech_prob=r["no_speech_prob"], temperature=o.temperature,
+                                 compression_ratio=wo.compression_ratio(wo.render_text(r["tokens"], model.layout.eot).strip()),
+                                 sum_logprob=r["sum_logprob"])
 
     orig = wo.decode_window
     wo.decode_window = fake_decode_window
@@ -170,6 +174,57 @@ def test_seek_loop_matches_oracle(fake_backend, case):
         for dec, prompt in zip(eng.all_decodes, prompts):
             exp = ([v.sot_prev] + prompt[-223:] if prompt else []) + v.sot_sequence("en", None)
             assert dec["initial"] == exp and dec["initial"][dec["sot_index"]] == v.sot
+
+
+@pytest.mark.parametrize("case", ["accept_first", "logprob_fallback", "repetitive_to_the_top", "silence_is_not_retried",
+                                  "scalar_temperature", "multi_window_prompt_reset"])
+def test_temperature_fallback_ladder_matches_oracle(fake_backend, case):
+    """decode_with_fallback of upstream transcribe.py: which rungs run, with which decoder options, which result is kept,
+    and the prompt reset after a high-temperature window -- backend vs the oracle's restatement on the same script."""
+    v = vocab_for(51865)
+    tb = v.timestamp_begin
+    ladder = (0.0, 0.2, 0.4, 0.6, 0.8, 1.0)
+    good = res([tb, 11, 12, tb + 300], avg=-0.4)
+    low = res([tb, 13, 14, tb + 200], avg=-1.5)
+    rep = res([tb] + [11] * 80 + [tb + 400], avg=-0.3)  # compression ratio of "<11><11>..." is far above 2.4
+    assert wo.compression_ratio(wo.render_text(rep["tokens"], v.eot)) > 2.4
+    cases = {
+        "accept_first": (10.0, ladder, [good], [0.0], 0.0),
+        "logprob_fallback": (10.0, ladder, [low, low, good], [0.0, 0.2, 0.4], 0.4),
+        "repetitive_to_the_top": (10.0, ladder, [rep], list(ladder), 1.0),
+        "silence_is_not_retried": (10.0, ladder, [res([tb, 11, tb + 100], avg=-1.5, nsp=0.9)], [0.0], None),
+        "scalar_temperature": (10.0, 0.4, [low], [0.4], 0.4),
+        # window 1 falls back to T = 0.6 (> 0.5: its tokens are not fed to window 2 as a prompt); window 2 accepted at T = 0
+        "multi_window_prompt_reset": (50.0, (0.0, 0.6), [low, res([tb, 21, tb + 1500], avg=-0.2), good], [0.0, 0.6, 0.0], None),
+    }
+    seconds, temperature, script, want_rungs, want_temperature = cases[case]
+    audio = synth_audio(3, seconds)
+    b, eng = fake_backend(script)
+    opts = {"language": "en", "beam_size": 5, "best_of": 3, "patience": 1.0, "temperature": temperature}
+    got = b.transcribe_raw(audio, _seed=77, **b._normalize_options(opts))
+    want, prompts = _oracle_with_script(script, audio, language="en", beam_size=5, best_of=3, patience=1.0,
+                                        temperature=temperature, sample_seed=77)
+    oracle_opts = _oracle_with_script.options
+    assert [d.get("temperature", 0.0) for d in eng.all_decodes] == want_rungs == [o.temperature for o in oracle_opts]
+    for dec, o in zip(eng.all_decodes, oracle_opts):
+        if o.temperature > 0:  # sampling rung: beam search and patience off, best_of hypotheses, per-attempt seed
+            assert dec["beam"] is None and o.beam_size is None and o.patience is None
+            assert dec["best_of"] == 3 == o.best_of and dec["seed"] == o.sample_seed
+        else:                  # T = 0 rung: beam search, best_of dropped
+            assert dec["beam"] == 5 == o.beam_size and o.best_of is None and "best_of" not in dec
+    assert len({o.sample_seed for o in oracle_opts}) == len(oracle_opts)  # every attempt draws from its own stream
+    key = lambda r: [(s["seek"], s["start"], s["end"], s["tokens"], s["temperature"], round(s["compression_ratio"], 6)) for s in r["segments"]]
+    assert key(got) == key(want)
+    if want_temperature is not None:
+        assert [s["temperature"] for s in got["segments"]] == [want_temperature] * len(got["segments"]) and got["segments"]
+    if case == "silence_is_not_retried":
+        assert got["segments"] == []  # no_speech_prob > threshold and avg_logprob below: window skipped, no retry
+    if case == "multi_window_prompt_reset":
+        assert eng.all_decodes[-1]["initial"][0] == v.sot and prompts[-1] == []
+    with pytest.raises(ValueError):
+        b.transcribe_raw(audio, temperature=-0.1, language="en")
+    with pytest.raises(ValueError):
+        b.transcribe_raw(audio, temperature=0.2, best_of=9, language="en")
 
 
 def test_device_parsing_and_compute_types(monkeypatch):

@@ -49,7 +49,8 @@ class DecodeOptsC(C.Structure):
     _fields_ = [("initial_tokens", c_i32_p), ("n_initial", C.c_int32), ("sot_index", C.c_int32),
                 ("beam_size", C.c_int32), ("patience", C.c_float), ("length_penalty", C.c_float),
                 ("sample_len", C.c_int32), ("without_timestamps", C.c_int32), ("suppress_blank", C.c_int32),
-                ("max_initial_timestamp_index", C.c_int32)]
+                ("max_initial_timestamp_index", C.c_int32), ("temperature", C.c_float), ("best_of", C.c_int32),
+                ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32)]
 
 
 class ResultC(C.Structure):

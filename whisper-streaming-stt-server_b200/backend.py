@@ -7,9 +7,12 @@ same option handling and result mapping as `TorchWhisperBackend`
 The host side keeps upstream `whisper.transcribe`'s seek loop and segment assembly in Python (the
 reference's host language); mel, encoder and the batched decoder run in libb200whisper.so.
 
+Temperature: a scalar or upstream's fallback ladder (tuple) -- `decode_with_fallback` of upstream transcribe.py:
+rungs above 0 sample `best_of` hypotheses on the device (Categorical(logits / T) by Gumbel-max, counter-based
+generator), beam search only runs at temperature 0.  Draws are reproducible for a given seed
+(`B200_WHISPER_SEED`, else one random seed per backend instance), not equal to torch's global generator.
+
 Deviations, all explicit:
-* temperature > 0 / fallback ladders are not implemented (server profiles use scalar 0.0): a warning is
-  logged and the window is decoded at temperature 0;
 * `word_timestamps` (DTW alignment) is accepted and ignored; `initial_prompt` needs the tokenizer rank
   file (`B200_WHISPER_VOCAB_DIR`) and is dropped with a warning without it;
 * like torch_whisper, `without_timestamps` is converted to `word_timestamps` and so does NOT disable
@@ -65,6 +68,12 @@ SUPPORTED_OPTIONS = {  # torch_whisper.py:79-97
 _ENGINES: Dict[tuple, Engine] = {}
 _ENGINES_LOCK = threading.Lock()
 _INSTANCE_COUNTER = itertools.count()
+_M64 = (1 << 64) - 1
+
+
+def window_seed(base_seed: int, seek: int, attempt: int) -> int:
+    """Seed of one decode attempt: window at mel frame `seek`, rung `attempt` of the temperature ladder."""
+    return (base_seed + 0x632BE59BD9B4E019 * (seek + 1) + 0xD1342543DE82EF95 * (attempt + 1)) & _M64
 
 
 def _close_engines() -> None:
@@ -171,6 +180,9 @@ class B200WhisperBackend:
         self.honor_without_timestamps = os.environ.get("B200_WHISPER_HONOR_WITHOUT_TIMESTAMPS", "0") == "1"
         self.report_language_probability = os.environ.get("B200_WHISPER_REPORT_LANGUAGE_PROB", "0") == "1"
         self.last_language_probability: Optional[float] = None
+        env_seed = os.environ.get("B200_WHISPER_SEED")
+        self.base_seed = int(env_seed) & _M64 if env_seed else int.from_bytes(os.urandom(8), "little")
+        self._call_counter = itertools.count()
         LOGGER.info("b200_whisper loaded model=%s device=cuda:%d compute=%s", model_size, self.device_index, self.compute)
 
     # ---- torch_whisper.py:78-110 ----
@@ -273,17 +285,21 @@ class B200WhisperBackend:
             n_in = len(audio) // 2 if isinstance(audio, (bytes, bytearray, memoryview)) else int(np.asarray(audio).size)
         if n_in == 0:
             return {"text": "", "segments": [], "language": language or "", "language_probability": None}
-        if isinstance(temperature, (list, tuple)):
-            if len(temperature) > 1:
-                LOGGER.warning("b200_whisper: temperature fallback ladder not supported; using %s only", temperature[0])
-            temperature = temperature[0] if temperature else 0.0
-        if temperature and float(temperature) > 0:
-            LOGGER.warning("b200_whisper: sampling at temperature %.2f is not supported; decoding at temperature 0", temperature)
-        # scalar temperature 0: best_of is dropped (transcribe.py decode_with_fallback)
+        temperatures = [float(t) for t in temperature] if isinstance(temperature, (list, tuple)) else [float(temperature or 0.0)]
+        if not temperatures:
+            temperatures = [0.0]
+        if any(t < 0 or t != t for t in temperatures):
+            raise ValueError(f"temperature must be >= 0, got {temperature!r}")
+        seed = ignored.pop("_seed", None)
+        # distinct calls of one backend draw from distinct streams; an explicit `_seed` (tests) pins the call
+        call_seed = int(seed) & _M64 if seed is not None else (self.base_seed + 0xA0761D6478BD642F * (next(self._call_counter) + 1)) & _M64
         without_ts = bool(ignored.get("_without_timestamps", False))
         beam = int(beam_size) if beam_size is not None else None
         if beam is not None and not (1 <= beam <= 8):
             raise ValueError(f"beam_size must be in [1, 8], got {beam_size}")
+        n_best = int(best_of) if best_of is not None else None
+        if n_best is not None and not (1 <= n_best <= 8):
+            raise ValueError(f"best_of must be in [1, 8], got {best_of}")
 
         with self.engine.open_call(audio, sample_rate) as call:
             content_frames = call.content_frames
@@ -325,8 +341,29 @@ class B200WhisperBackend:
                     initial = [v.sot_prev] + prompt[-(n_ctx // 2 - 1):] + initial
                 # sample_len: upstream DecodingOptions.sample_len (default n_text_ctx // 2); not reachable through
                 # transcribe() -- torch_whisper.py:78-110 drops it -- but tools use it to bound synthetic decodes
-                res = call.decode(seek, initial, initial.index(v.sot), beam, patience, length_penalty,
-                                  sample_len=int(sample_len or 0), without_timestamps=without_ts)
+                # decode_with_fallback (upstream transcribe.py): walk the temperature ladder until a rung passes the
+                # compression-ratio / log-probability checks; beam search at T = 0, best_of samples above it
+                for attempt, t in enumerate(temperatures):
+                    if t > 0:
+                        res = call.decode(seek, initial, initial.index(v.sot), None, None, length_penalty,
+                                          sample_len=int(sample_len or 0), without_timestamps=without_ts, temperature=t,
+                                          best_of=n_best, seed=window_seed(call_seed, seek, attempt))
+                    else:
+                        res = call.decode(seek, initial, initial.index(v.sot), beam, patience, length_penalty,
+                                          sample_len=int(sample_len or 0), without_timestamps=without_ts)
+                    res["temperature"] = t
+                    text_all = self.detok.decode([tk for tk in res["tokens"] if tk < v.eot]).strip()
+                    res["compression_ratio"] = compression_ratio(text_all)
+                    needs_fallback = False
+                    if compression_ratio_threshold is not None and res["compression_ratio"] > compression_ratio_threshold:
+                        needs_fallback = True  # too repetitive
+                    if logprob_threshold is not None and res["avg_logprob"] < logprob_threshold:
+                        needs_fallback = True  # average log probability is too low
+                    if (no_speech_threshold is not None and res["no_speech_prob"] > no_speech_threshold
+                            and logprob_threshold is not None and res["avg_logprob"] < logprob_threshold):
+                        needs_fallback = False  # silence
+                    if not needs_fallback:
+                        break
                 tokens: List[int] = res["tokens"]
                 if no_speech_threshold is not None:
                     should_skip = res["no_speech_prob"] > no_speech_threshold
@@ -335,13 +372,12 @@ class B200WhisperBackend:
                     if should_skip:
                         seek += segment_size
                         continue
-                text_all = self.detok.decode([t for t in tokens if t < v.eot]).strip()
-                cr = compression_ratio(text_all) if text_all else 0.0
+                cr = res["compression_ratio"]
 
                 def new_segment(start: float, end: float, toks: Sequence[int]) -> dict:
                     return {"seek": seek, "start": start, "end": end,
                             "text": self.detok.decode([t for t in toks if t < v.eot]), "tokens": list(toks),
-                            "temperature": 0.0, "avg_logprob": res["avg_logprob"], "compression_ratio": cr,
+                            "temperature": res["temperature"], "avg_logprob": res["avg_logprob"], "compression_ratio": cr,
                             "no_speech_prob": res["no_speech_prob"]}
 
                 current: List[dict] = []
@@ -377,7 +413,7 @@ class B200WhisperBackend:
                         seg["tokens"] = []
                 all_segments.extend({"id": i, **seg} for i, seg in enumerate(current, start=len(all_segments)))
                 all_tokens.extend(t for seg in current for t in seg["tokens"])
-                if not condition_on_previous_text:
-                    prompt_reset_since = len(all_tokens)
+                if not condition_on_previous_text or res["temperature"] > 0.5:
+                    prompt_reset_since = len(all_tokens)  # do not feed the prompt tokens if a high temperature was used
         return {"text": self.detok.decode(all_tokens[n_initial_prompt:]), "segments": all_segments, "language": language,
                 "language_probability": language_probability}

@@ -1,5 +1,6 @@
 // C ABI (include/b200_whisper.h) + the continuous-batching scheduler thread.
 #include <math.h>
+#include <cmath>
 #include <stdlib.h>
 #include <string.h>
 
@@ -178,9 +179,12 @@ void finalize_decode(bw_engine* e, Request* r, const unsigned char* blob) {
   std::vector<float> cand_lp;
   const int last_pos = std::min(r->cur_len - 1, n_ctx - 1);
   if (r->greedy) {
-    cand.push_back(backtrack(last_pos, 0));
-    cand.back().push_back(eot);
-    cand_lp.push_back(fmisc[1]);
+    // GreedyDecoder.finalize: every hypothesis of the group (1, or best_of samples) padded with one EOT
+    for (int j = 0; j < r->G; ++j) {
+      cand.push_back(backtrack(last_pos, j));
+      cand.back().push_back(eot);
+      cand_lp.push_back(fmisc[1 + j]);
+    }
   } else {
     const int n_fin = misc[0];
     for (int i = 0; i < n_fin; ++i) {
@@ -261,24 +265,27 @@ void admit_batch(bw_engine* e, std::vector<Request*>& fresh) {
   for (int i = 0; i < nb; ++i) engine_cross_kv(e, i, fresh[i]->q);
   for (int i = 0; i < nb; ++i) {
     Request* r = fresh[i];
-    int* rec = e->h_init + i * 12;
+    int* rec = e->h_init + i * kInitRecInts;
     const int n_init = (int)r->initial.size();
     rec[0] = r->q; rec[1] = r->G; rec[2] = r->greedy; rec[3] = n_init; rec[4] = n_init; rec[5] = r->first_seq;
     rec[6] = r->without_ts; rec[7] = r->suppress_blank; rec[8] = r->max_initial_ts;
     rec[9] = std::max(1, (int)lround((double)r->G * (double)r->patience));
-    rec[10] = r->initial.back(); rec[11] = 0;
+    rec[10] = r->initial.back();
+    memcpy(&rec[11], &r->temperature, 4);
+    rec[12] = (int)(unsigned int)(r->seed & 0xffffffffull); rec[13] = (int)(unsigned int)(r->seed >> 32);
+    rec[14] = rec[15] = 0;
     r->cur_len = n_init;
     r->steps = 0;
     r->prefilled = false;
   }
   int* init_dev = e->d_init.as<int>();
-  BW_CUDA(cudaMemcpyAsync(init_dev, e->h_init, (size_t)nb * 12 * 4, cudaMemcpyHostToDevice, e->stream));
+  BW_CUDA(cudaMemcpyAsync(init_dev, e->h_init, (size_t)nb * kInitRecInts * 4, cudaMemcpyHostToDevice, e->stream));
   engine_init_requests(e, init_dev, nb);
   // the pinned control block is rewritten by the next step: make sure the copy has been consumed
   BW_CUDA(cudaStreamSynchronize(e->stream));
   e->stat_windows += nb;
   e->stat_enc_batches += 1;
-  e->stat_h2d += (long long)nb * 48;
+  e->stat_h2d += (long long)nb * kInitRecInts * 4;
   for (Request* r : fresh) { r->t_encoded = Clock::now(); e->live.push_back(r); }
   fresh.clear();
 }
@@ -708,8 +715,8 @@ int bw_engine_finalize(bw_engine* e) {
   BW_CUDA(cudaMemset(e->self_pool.p, 0, e->self_pool.bytes));
   // decoder state
   const size_t n_ctx = d.n_text_ctx;
-  e->st_int.alloc(((size_t)Q * 11 + (size_t)Q * kMaxFinished * 2 + (size_t)S * 4) * 4);
-  e->st_float.alloc(((size_t)Q * kMaxFinished + Q + S) * 4);
+  e->st_int.alloc(((size_t)Q * 13 + (size_t)Q * kMaxFinished * 2 + (size_t)S * 4) * 4);
+  e->st_float.alloc(((size_t)Q * kMaxFinished + 2 * (size_t)Q + S) * 4);
   e->st_anc0.alloc((size_t)S * n_ctx); e->st_anc1.alloc((size_t)S * n_ctx);
   e->st_tok.alloc((size_t)Q * n_ctx * kMaxBeam * 4); e->st_parent.alloc((size_t)Q * n_ctx * kMaxBeam);
   for (DevBuf* b : {&e->st_int, &e->st_float, &e->st_anc0, &e->st_anc1, &e->st_tok, &e->st_parent}) BW_CUDA(cudaMemset(b->p, 0, b->bytes));
@@ -720,12 +727,14 @@ int bw_engine_finalize(bw_engine* e) {
     rs.n_beam = take(Q); rs.greedy = take(Q); rs.sample_begin = take(Q); rs.cur_len = take(Q); rs.first_seq = take(Q);
     rs.without_ts = take(Q); rs.suppress_blank = take(Q); rs.max_initial_ts = take(Q); rs.max_candidates = take(Q);
     rs.n_finished = take(Q); rs.completed = take(Q);
+    rs.seed_lo = reinterpret_cast<unsigned int*>(take(Q)); rs.seed_hi = reinterpret_cast<unsigned int*>(take(Q));
     rs.fin_pos = take((size_t)Q * kMaxFinished); rs.fin_slot = take((size_t)Q * kMaxFinished);
     SeqState& ss = e->ss;
     ss.next_tok = take(S); ss.prev_tok = take(S); ss.last_ts = take(S); ss.seq_first = take(S);
     float* f = e->st_float.as<float>();
     rs.fin_score = f; f += (size_t)Q * kMaxFinished;
     rs.no_speech_prob = f; f += Q;
+    rs.temperature = f; f += Q;
     ss.sum_logprob = f;
     ss.anc[0] = e->st_anc0.as<unsigned char>(); ss.anc[1] = e->st_anc1.as<unsigned char>();
     rs.tok = e->st_tok.as<int>(); rs.parent = e->st_parent.as<unsigned char>();
@@ -739,8 +748,8 @@ int bw_engine_finalize(bw_engine* e) {
       BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->grp[gi].h_ctrl), e->ctrl_ints * 4));
       e->grp[gi].d_ctrl.alloc(e->ctrl_ints * 4);
     }
-    BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_init), (size_t)Q * 12 * 4));
-    e->d_init.alloc((size_t)Q * 12 * 4);
+    BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_init), (size_t)Q * kInitRecInts * 4));
+    e->d_init.alloc((size_t)Q * kInitRecInts * 4);
     BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_flags), (size_t)Q * 4));
     e->h_fin_bytes = fin_blob_bytes(e) * (size_t)Q;
     BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_fin), e->h_fin_bytes));
@@ -984,6 +993,15 @@ int bw_call_decode(bw_call* c, int32_t seek, const bw_decode_opts* o, bw_result*
   r.greedy = o->beam_size == 0;
   r.beam = o->beam_size;
   r.G = r.greedy ? 1 : o->beam_size;
+  if (o->temperature > 0.f) {
+    // upstream DecodingTask: GreedyDecoder(temperature) with n_group = best_of or 1; beam search is a T = 0 decoder
+    BW_CHECK(r.greedy, "temperature > 0 needs beam_size == 0 (decode_with_fallback drops beam_size / patience above T = 0)");
+    BW_CHECK(o->best_of >= 0 && o->best_of <= kMaxBeam, "best_of must be in [0, 8]");
+    BW_CHECK(std::isfinite(o->temperature), "temperature must be finite");
+    r.temperature = o->temperature;
+    r.G = std::max(1, (int)o->best_of);
+    r.seed = ((unsigned long long)o->seed_hi << 32) | (unsigned long long)o->seed_lo;
+  }
   r.patience = o->patience > 0 ? o->patience : 1.f;
   r.length_penalty = o->length_penalty;
   r.sample_len = o->sample_len > 0 ? o->sample_len : e->dims.n_text_ctx / 2;
@@ -1198,11 +1216,12 @@ namespace {
 // Same launches, control upload and per-step completion read-back as the scheduler's decode_step().
 void synthetic_init(bw_engine* e, int n_segments, int n_group, int start_len) {
   for (int i = 0; i < n_segments; ++i) {
-    int* rec = e->h_init + i * 12;
+    int* rec = e->h_init + i * kInitRecInts;
     rec[0] = i; rec[1] = n_group; rec[2] = 0; rec[3] = 3; rec[4] = start_len; rec[5] = i * n_group; rec[6] = 0; rec[7] = 1;
-    rec[8] = 50; rec[9] = kMaxFinished; rec[10] = e->tt.timestamp_begin - 1000; rec[11] = 0;
+    rec[8] = 50; rec[9] = kMaxFinished; rec[10] = e->tt.timestamp_begin - 1000;
+    rec[11] = rec[12] = rec[13] = rec[14] = rec[15] = 0;
   }
-  BW_CUDA(cudaMemcpyAsync(e->d_init.p, e->h_init, (size_t)n_segments * 48, cudaMemcpyHostToDevice, e->stream));
+  BW_CUDA(cudaMemcpyAsync(e->d_init.p, e->h_init, (size_t)n_segments * kInitRecInts * 4, cudaMemcpyHostToDevice, e->stream));
   engine_init_requests(e, e->d_init.as<int>(), n_segments);
   BW_CUDA(cudaStreamSynchronize(e->stream));
 }

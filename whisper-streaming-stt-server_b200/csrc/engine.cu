@@ -17,13 +17,14 @@ namespace {
 
 __global__ void init_requests_kernel(const int* __restrict__ init, int n, ReqState rs, SeqState ss, int anc_cur, int n_ctx) {
   // init record: q, G, greedy, sample_begin, cur_len, first_seq, without_ts, suppress_blank, max_initial_ts,
-  //              max_candidates, last_init_tok, pad
-  const int* r = init + blockIdx.x * 12;
+  //              max_candidates, last_init_tok, temperature (float bits), seed_lo, seed_hi, pad, pad
+  const int* r = init + blockIdx.x * kInitRecInts;
   const int q = r[0], G = r[1], first_seq = r[5];
   if (threadIdx.x == 0) {
     rs.n_beam[q] = G; rs.greedy[q] = r[2]; rs.sample_begin[q] = r[3]; rs.cur_len[q] = r[4]; rs.first_seq[q] = first_seq;
     rs.without_ts[q] = r[6]; rs.suppress_blank[q] = r[7]; rs.max_initial_ts[q] = r[8]; rs.max_candidates[q] = r[9];
     rs.n_finished[q] = 0; rs.completed[q] = 0; rs.no_speech_prob[q] = nanf("");
+    rs.temperature[q] = __int_as_float(r[11]); rs.seed_lo[q] = (unsigned int)r[12]; rs.seed_hi[q] = (unsigned int)r[13];
     for (int j = 0; j < G; ++j) {
       const int s = first_seq + j;
       ss.sum_logprob[s] = 0.f; ss.next_tok[s] = r[10]; ss.prev_tok[s] = -1; ss.last_ts[s] = -1;

@@ -138,6 +138,8 @@ struct Request {
   std::vector<int> initial;
   int sot_index = 0, beam = 0, greedy = 1, sample_len = 224, without_ts = 0, suppress_blank = 1, max_initial_ts = 50;
   float patience = 1.f, length_penalty = -1.f;
+  float temperature = 0.f;          // > 0: GreedyDecoder sampling with G = best_of hypotheses
+  unsigned long long seed = 0;
   // outputs
   bw_result* out = nullptr;
   bw_lang_result* lang_out = nullptr;

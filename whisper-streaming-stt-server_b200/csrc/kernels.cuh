@@ -124,11 +124,15 @@ struct TokenTables {
 constexpr int kMaxBeam = 8;           // beams per request (n_group)
 constexpr int kMaxCand = kMaxBeam + 1;
 constexpr int kMaxFinished = 16;
+constexpr int kInitRecInts = 16;      // admission record (init_requests_kernel input), ints per request
 
 // Per-request decoding state (device, struct of arrays indexed by request slot q)
 struct ReqState {
   int* n_beam;          // G
-  int* greedy;          // GreedyDecoder semantics (G = 1)
+  int* greedy;          // GreedyDecoder semantics (G = 1 at temperature 0, G = best_of samples above it)
+  float* temperature;   // GreedyDecoder temperature; > 0 selects Categorical(logits / T) sampling
+  unsigned int* seed_lo;  // counter-based RNG key of the request (sample_uniform in sampling.cu)
+  unsigned int* seed_hi;
   int* sample_begin;    // index of the first sampled position
   int* cur_len;         // tokens so far (positions [0, cur_len))
   int* first_seq;       // sequence slot of beam 0 (beams are adjacent)

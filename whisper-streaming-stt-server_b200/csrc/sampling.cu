@@ -68,6 +68,19 @@ __device__ void block_ms(float& m, float& s, float* sh_m, float* sh_s) {
 
 __device__ __forceinline__ bool better(float v, int id, float v2, int id2) { return v > v2 || (v == v2 && id < id2); }
 
+// Counter-based generator for temperature sampling: the uniform of (request seed, hypothesis, position, token id)
+// is a pure function of its key (splitmix64 finaliser), so a decode is reproducible whatever batch it runs in and
+// whatever the launch geometry.  23 mantissa bits, u in (0, 1) exactly representable; oracle/whisper_oracle.py
+// `gumbel_noise` restates it bit for bit.
+__device__ __forceinline__ float sample_uniform(unsigned long long seed, int stream, int pos, int id) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(stream + 1);
+  z ^= ((unsigned long long)(unsigned int)pos << 32) | (unsigned long long)(unsigned int)id;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return ((float)(unsigned int)(z >> 41) + 0.5f) * (1.f / 8388608.f);
+}
+
 __global__ void __launch_bounds__(ST)
 sample_topk_kernel(const float* __restrict__ logits, int ld, int V, const int* __restrict__ srow_lrow,
                    const int* __restrict__ lrow_req, const int* __restrict__ lrow_seq, const TokenTables tt, const ReqState rs, const SeqState ss,
@@ -139,6 +152,46 @@ sample_topk_kernel(const float* __restrict__ logits, int ld, int V, const int* _
   else if (ssum == 0.f) lse = tm + logf(tsum);
   else { float m = tm, t = tsum; ms_merge(m, t, sm, ssum); lse = m + logf(t); }
 
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float temperature = rs.temperature[q];
+  if (rs.greedy[q] && temperature > 0.f) {
+    // GreedyDecoder.update at temperature T: next ~ Categorical(logits / T) over the filtered logits, drawn as
+    // argmax(logits / T + Gumbel noise); its log-probability is taken from the un-tempered log-softmax (lse above).
+    // First sampled position: all best_of hypotheses still share this one logits row -> one draw per hypothesis.
+    const unsigned long long seed = ((unsigned long long)rs.seed_hi[q] << 32) | rs.seed_lo[q];
+    const int n_draw = first ? rs.n_beam[q] : 1;
+    for (int k = 0; k < n_draw; ++k) {
+      const int stream = first ? k : s - rs.first_seq[q];
+      float bv = -INFINITY;
+      int bi = INT_MAX;
+      for (int id = threadIdx.x; id < V; id += ST) {
+        if ((mask_text && id < tb) || !allowed(r, id)) continue;
+        const float xv = x[id];
+        if (xv == -INFINITY) continue;
+        const float u = sample_uniform(seed, stream, cur_len, id);
+        const float key = xv / temperature - logf(-logf(u));
+        if (better(key, id, bv, bi)) { bv = key; bi = id; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      __syncthreads();
+      if (lane == 0) { wv[warp] = bv; wi[warp] = bi; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float fv = wv[0]; int fi = wi[0];
+        for (int w = 1; w < ST / 32; ++w)
+          if (better(wv[w], wi[w], fv, fi)) { fv = wv[w]; fi = wi[w]; }
+        cand_tok[lr * kMaxCand + k] = (fi == INT_MAX) ? -1 : fi;
+        cand_lp[lr * kMaxCand + k] = (fi == INT_MAX) ? -INFINITY : x[fi] - lse;
+      }
+    }
+    return;
+  }
+
   // pass B: per-thread sorted top lists, then kMaxCand rounds of block-wide argmax
   float v[kMaxCand];
   int ix[kMaxCand];
@@ -169,7 +222,6 @@ sample_topk_kernel(const float* __restrict__ logits, int ld, int V, const int* _
       }
     }
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = 0; k < K; ++k) {
     float bv = v[0];
     int bi = ix[0];
@@ -229,15 +281,22 @@ beam_update_kernel(const int* __restrict__ active_req, const int* __restrict__ r
     float nsum[kMaxBeam];
     int saved = 0;
     if (rs.greedy[q]) {
-      // GreedyDecoder.update, n_group == 1 (temperature 0): the hypothesis ends at its first EOT
-      const int tok = cand_tok[lr0 * kMaxCand];
-      const float lp = cand_lp[lr0 * kMaxCand];
-      const int last = old_next[0];
-      nsum[0] = old_sum[0] + ((last != tt.eot) ? lp : 0.f);
-      ntok[0] = (last == tt.eot) ? tt.eot : tok;
-      nsrc[0] = 0;
-      saved = 1;
-      if (ntok[0] == tt.eot) rs.completed[q] = 1;
+      // GreedyDecoder.update: n_group == 1 at temperature 0, best_of independent samples above it.  A hypothesis
+      // that has emitted EOT keeps emitting it and stops accumulating; completed once every hypothesis ended.
+      // Before the first sampled token all hypotheses share logits row lr0 (draw j of it belongs to hypothesis j).
+      bool all_eot = true;
+      for (int j = 0; j < G; ++j) {
+        const int c = first ? lr0 * kMaxCand + j : (lr0 + j) * kMaxCand;
+        const int tok = cand_tok[c];
+        const float lp = cand_lp[c];
+        const int last = old_next[j];
+        nsum[j] = old_sum[j] + ((last != tt.eot) ? lp : 0.f);
+        ntok[j] = (last == tt.eot) ? tt.eot : tok;
+        nsrc[j] = first ? 0 : j;
+        all_eot = all_eot && ntok[j] == tt.eot;
+      }
+      saved = G;
+      if (all_eot) rs.completed[q] = 1;
     } else {
       // BeamSearchDecoder.update: candidates (beam j, rank k), stable sort by cumulative logprob
       const int nb = first ? 1 : G;  // all beams are identical before the first sampled token

@@ -54,12 +54,16 @@ class Call:
 
     def decode(self, seek: int, initial: Sequence[int], sot_index: int, beam_size: Optional[int], patience: Optional[float],
                length_penalty: Optional[float], sample_len: int = 0, without_timestamps: bool = False,
-               suppress_blank: bool = True, max_initial_timestamp_index: Optional[int] = 50) -> dict:
+               suppress_blank: bool = True, max_initial_timestamp_index: Optional[int] = 50, temperature: float = 0.0,
+               best_of: Optional[int] = None, seed: int = 0) -> dict:
+        """One 30 s window.  temperature > 0: GreedyDecoder sampling with `best_of` hypotheses (beam_size must be
+        None, as upstream's decode_with_fallback guarantees), reproducible for a given 64-bit `seed`."""
         init = (C.c_int32 * len(initial))(*initial)
         o = L.DecodeOptsC(init, len(initial), sot_index, int(beam_size or 0), float(patience or 0.0),
                           -1.0 if length_penalty is None else float(length_penalty), int(sample_len),
                           int(bool(without_timestamps)), int(bool(suppress_blank)),
-                          -1 if max_initial_timestamp_index is None else int(max_initial_timestamp_index))
+                          -1 if max_initial_timestamp_index is None else int(max_initial_timestamp_index),
+                          float(temperature), int(best_of or 0), int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF)
         r = L.ResultC()
         L.check(self.engine.lib.bw_call_decode(self._h, int(seek), C.byref(o), C.byref(r)), "bw_call_decode")
         return {"tokens": list(r.tokens[: r.n_tokens]), "sum_logprob": r.sum_logprob, "avg_logprob": r.avg_logprob,
