@@ -82,10 +82,6 @@ struct Ctl {
 void enqueue_group_step_eager(bw_engine* e, DecGroup& G, Ctl& c) {
   int* dbase = G.d_ctrl.as<int>();
   auto dev = [&](int* h) { return dbase + (h - c.base); };
-  static const bool prio = getenv("B200W_PRIO") != nullptr;  // see decoder_layers_fused
-  int prio_lo = 0, prio_hi = 0;
-  if (prio) BW_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  PriorityScope chain_prio(prio ? prio_hi : kNoPriority);
   BW_CUDA(cudaMemcpyAsync(dbase, c.base, c.total * 4, cudaMemcpyHostToDevice, G.stream));
   engine_decoder_layers(e, G, c.R, c.NG, c.max_grp, c.LR, dev(c.row_seq), dev(c.row_pos), dev(c.row_tok), dev(c.row_bpos),
                         dev(c.grp_first), dev(c.grp_n), dev(c.grp_x), dev(c.lrow_src));
@@ -100,18 +96,8 @@ void enqueue_group_step_eager(bw_engine* e, DecGroup& G, Ctl& c) {
               G.d_cand_lp.as<float>(), G.stream);
 }
 
-// experiment (B200W_STAGGER_US): hold group g back by g * n microseconds so that the groups' layers interleave
-__global__ void stagger_kernel(unsigned long long ns) {
-  unsigned long long t0, t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < ns);
-}
-
 void enqueue_group_step(bw_engine* e, DecGroup& G, Ctl& c) {
   if (c.R == 0) return;
-  static const int stagger_us = getenv("B200W_STAGGER_US") ? atoi(getenv("B200W_STAGGER_US")) : 0;
-  const int gi = (int)(&G - e->grp);
-  if (stagger_us > 0 && gi > 0) stagger_kernel<<<1, 1, 0, G.stream>>>((unsigned long long)stagger_us * 1000ull * gi);
   e->stat_h2d += (long long)c.total * 4;
   static const bool use_graphs = getenv("B200W_NO_GRAPH") == nullptr;
   if (!use_graphs) return enqueue_group_step_eager(e, G, c);

@@ -211,180 +211,6 @@ dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int
   trace_mark(trace, ttag | 8);
 }
 
-
-// Persistent variant: ONE CTA per SM walks over (head, segment group, T split) items, the TMA ring running ahead across
-// item boundaries.  97 KB of ring per SM keeps ~14 MB of loads in flight (Little: 6.8 TB/s x ~1 us needs ~7 MB), and
-// the other ~110 KB of shared memory per SM stay free for the latency-bound kernels of ANOTHER request group's step
-// (row GEMMs, self-attention), which can then execute underneath this HBM-bound stream instead of queueing behind
-// a grid that fills every SM twice.  The dependent kernel is released only when a CTA starts its last item, so its
-// CTAs do not park in that space while the stream is still running.
-constexpr int XP_RED_FLOATS = 4 * 8 * 66;
-constexpr int XPSM_TOTAL = XSM_RED + 2 * XP_RED_FLOATS * 4 + 1024;
-
-__global__ void __launch_bounds__(160, 1)
-dec_cross_attention_persist_kernel(const __grid_constant__ CUtensorMap tm, const int* __restrict__ group_first_row,
-                                   const int* __restrict__ group_n_rows, const int* __restrict__ group_xslot,
-                                   const float* __restrict__ q, int T_enc, int n_layer, int layer, int d, int n_head,
-                                   int n_groups, int n_split, bf16* __restrict__ out, float* __restrict__ ws) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + XSM_BAR);
-  uint64_t* empty_bar = full_bar + XSTAGES;
-  float* red_base = reinterpret_cast<float*>(smem + XSM_RED);  // 2 x [4 warps][8 rows][66]: m, l, o[64]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = n_head * n_groups * n_split;
-  const int chunk = ((T_enc + n_split - 1) / n_split + XT - 1) / XT * XT;
-  const int last_item = blockIdx.x + ((n_items - 1 - (int)blockIdx.x) / (int)gridDim.x) * (int)gridDim.x;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tm);
-    for (int s = 0; s < XSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
-    fence_barrier_init();
-  }
-  __syncthreads();
-
-  if (warp == 4) {
-    if (lane == 0) {
-      int gt = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int h = item % n_head, g = (item / n_head) % n_groups, sp = item / (n_head * n_groups);
-        const int t0 = sp * chunk, t1 = min(T_enc, t0 + chunk);
-        const int n_tiles = (t1 - t0 + XT - 1) / XT;
-        const int zc = group_xslot[g] * n_layer + layer;
-        for (int it = 0; it < n_tiles; ++it, ++gt) {
-          const int s = gt % XSTAGES;
-          mbar_wait(&empty_bar[s], ((gt / XSTAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], 2 * XTILE_BYTES);
-          uint8_t* ks = smem + s * 2 * XTILE_BYTES;
-          tma_load_3d(ks, &tm, &full_bar[s], h * 64, t0 + it * XT, zc);
-          tma_load_3d(ks + XTILE_BYTES, &tm, &full_bar[s], d + h * 64, t0 + it * XT, zc);
-        }
-        if (item == last_item) pdl_trigger();
-      }
-    }
-    __syncwarp();
-    return;
-  }
-  pdl_wait();
-  const int gid = lane >> 2, tig = lane & 3;
-  const int lrow = lane & 7, lmat = lane >> 3;
-  const float LOG2E = 1.4426950408889634f;
-  int gt = 0, n_done = 0;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
-    const int h = item % n_head, g = (item / n_head) % n_groups, sp = item / (n_head * n_groups);
-    const int row0 = group_first_row[g], nq = group_n_rows[g];
-    const int t0 = sp * chunk, t1 = min(T_enc, t0 + chunk);
-    const int n_tiles = (t1 - t0 + XT - 1) / XT;
-    uint32_t qa[4][2];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-      if (gid < nq) {
-        const float* qr = q + (long long)(row0 + gid) * d + h * 64 + ks * 16 + tig * 2;
-        v0 = qr[0] * 0.125f; v1 = qr[1] * 0.125f; v2 = qr[8] * 0.125f; v3 = qr[9] * 0.125f;
-      }
-      qa[ks][0] = pack_bf16x2(v0, v1);
-      qa[ks][1] = pack_bf16x2(v2, v3);
-    }
-    float m = -INFINITY, l = 0.f;
-    float o[8][4];
-#pragma unroll
-    for (int nd = 0; nd < 8; ++nd) { o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f; }
-    for (int it = 0; it < n_tiles; ++it, ++gt) {
-      const int s = gt % XSTAGES;
-      mbar_wait(&full_bar[s], (gt / XSTAGES) & 1);
-      const uint32_t kbase = smem_u32(smem + s * 2 * XTILE_BYTES);
-      const uint32_t vbase = kbase + XTILE_BYTES;
-      float sc[2][4];
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-        const int krow = warp * 16 + nt * 8 + lrow;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t b0, b1, b2, b3;
-          ldsm_x4(kbase + krow * 128 + (((half * 4 + lmat) ^ (krow & 7)) << 4), b0, b1, b2, b3);
-          mma_bf16(sc[nt], qa[half * 2][0], 0u, qa[half * 2][1], 0u, b0, b1);
-          mma_bf16(sc[nt], qa[half * 2 + 1][0], 0u, qa[half * 2 + 1][1], 0u, b2, b3);
-        }
-      }
-      const int key0 = t0 + it * XT + warp * 16 + tig * 2;
-      float sv[4];
-      sv[0] = (key0 < t1) ? sc[0][0] * LOG2E : -INFINITY;
-      sv[1] = (key0 + 1 < t1) ? sc[0][1] * LOG2E : -INFINITY;
-      sv[2] = (key0 + 8 < t1) ? sc[1][0] * LOG2E : -INFINITY;
-      sv[3] = (key0 + 9 < t1) ? sc[1][1] * LOG2E : -INFINITY;
-      float mx = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      const float m_new = fmaxf(m, mx);
-      float p[4] = {0.f, 0.f, 0.f, 0.f};
-      if (m_new != -INFINITY) {
-        const float alpha = fast_exp2(m - m_new);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) p[i] = fast_exp2(sv[i] - m_new);
-        l = l * alpha + (p[0] + p[1]) + (p[2] + p[3]);
-        if (alpha != 1.f) {
-#pragma unroll
-          for (int nd = 0; nd < 8; ++nd) { o[nd][0] *= alpha; o[nd][1] *= alpha; }
-        }
-        m = m_new;
-      }
-      const uint32_t pa0 = pack_bf16x2(p[0], p[1]), pa2 = pack_bf16x2(p[2], p[3]);
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        const int vrow = warp * 16 + (lmat & 1) * 8 + lrow;
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(vbase + vrow * 128 + (((np * 2 + (lmat >> 1)) ^ (vrow & 7)) << 4), b0, b1, b2, b3);
-        mma_bf16(o[np * 2], pa0, 0u, pa2, 0u, b0, b1);
-        mma_bf16(o[np * 2 + 1], pa0, 0u, pa2, 0u, b2, b3);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-    }
-    l += __shfl_xor_sync(0xffffffffu, l, 1);
-    l += __shfl_xor_sync(0xffffffffu, l, 2);
-    // partials double-buffered by item parity: one 128-thread barrier per item (see the note on reuse above)
-    float* red = red_base + (n_done & 1) * XP_RED_FLOATS;
-    float* mine = red + (warp * 8 + gid) * 66;
-    if (tig == 0) { mine[0] = m; mine[1] = l; }
-#pragma unroll
-    for (int nd = 0; nd < 8; ++nd) { mine[2 + nd * 8 + tig * 2] = o[nd][0]; mine[2 + nd * 8 + tig * 2 + 1] = o[nd][1]; }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const int r = threadIdx.x >> 4, c4 = (threadIdx.x & 15) * 4;
-    if (r < nq) {
-      float M = -INFINITY;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) M = fmaxf(M, red[(w * 8 + r) * 66]);
-      float num[4] = {0.f, 0.f, 0.f, 0.f}, den = 0.f;
-      if (M != -INFINITY) {
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const float* pr = red + (w * 8 + r) * 66;
-          const float e = fast_exp2(pr[0] - M);
-          den = fmaf(e, pr[1], den);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) num[i] = fmaf(e, pr[2 + c4 + i], num[i]);
-        }
-      }
-      const int row = row0 + r;
-      if (n_split == 1) {
-        const float inv = 1.f / den;
-        uint2 t;
-        t.x = pack_bf16x2(num[0] * inv, num[1] * inv);
-        t.y = pack_bf16x2(num[2] * inv, num[3] * inv);
-        *reinterpret_cast<uint2*>(out + (long long)row * d + h * 64 + c4) = t;
-      } else {
-        float* w = ws + (((long long)row * n_head + h) * kMaxSplitX + sp) * 66;
-        if (c4 == 0) { w[0] = (M == -INFINITY) ? -INFINITY : M * 0.6931471805599453f; w[1] = den; }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) w[2 + c4 + i] = num[i];
-      }
-    }
-  }
-}
-
 }  // namespace
 
 void dec_cross_attention_mma(const int* group_first_row, const int* group_n_rows, const int* group_xslot, int n_groups,
@@ -406,21 +232,6 @@ void dec_cross_attention_mma(const int* group_first_row, const int* group_n_rows
     cached_ptr = kv.cache; cached_geo[0] = d; cached_geo[1] = kv.T_enc; cached_geo[2] = kv.n_slots; cached_geo[3] = n_layer;
   }
   const CUtensorMap tm = cached_tm;
-  static const bool persist = getenv("B200W_XATTN_PERSIST") != nullptr;
-  if (persist) {
-    static std::atomic<unsigned long long> pattr_set{0};
-    static int n_sm[64];
-    if (!(pattr_set.load() >> dev & 1ull)) {
-      BW_CUDA(cudaFuncSetAttribute(dec_cross_attention_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XPSM_TOTAL));
-      BW_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
-      pattr_set.fetch_or(1ull << dev);
-    }
-    const int n_items = n_head * n_groups * n_split;
-    launch_kernel(dec_cross_attention_persist_kernel, dim3(std::min(n_items, n_sm[dev])), dim3(160), XPSM_TOTAL, stream, tm,
-                  group_first_row, group_n_rows, group_xslot, q, kv.T_enc, n_layer, layer, d, n_head, n_groups, n_split, out, ws);
-    ++g_kernel_launches;
-    return;
-  }
   dim3 grid(n_head, n_groups, n_split);
   launch_kernel(dec_cross_attention_mma_kernel, grid, dim3(160), XSM_TOTAL, stream, tm, group_first_row, group_n_rows, group_xslot, q,
                 kv.T_enc, n_layer, layer, d, n_split, out, ws, g_trace_dev);

@@ -1,6 +1,5 @@
 // Shared device helpers: error macros, mbarrier / TMA / tcgen05 PTX wrappers (sm_100a).
 #pragma once
-#include <limits.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -43,38 +42,15 @@ struct PdlScope {
   explicit PdlScope(bool on) : prev(tl_pdl) { tl_pdl = on; }
   ~PdlScope() { tl_pdl = prev; }
 };
-// ---- per-launch scheduling priority (decoder step split into request groups on separate streams) ----
-// The latency-bound kernels of a step (row GEMMs, self-attention, sampling) run at the highest priority and the
-// HBM-bound cross-attention grids at a lower, per-group one, so that one group's chain is dispatched into the SM slots
-// another group's cross-attention frees instead of queueing behind its whole grid.  kNoPriority = attribute not set.
-constexpr int kNoPriority = INT_MIN;
-extern thread_local int tl_priority;
-struct PriorityScope {
-  int prev;
-  explicit PriorityScope(int p) : prev(tl_priority) { tl_priority = p; }
-  ~PriorityScope() { tl_priority = prev; }
-};
-// appends the PDL / priority attributes the current scopes ask for; returns the new attribute count
-inline int add_scope_attrs(cudaLaunchAttribute* attr, int n) {
-  if (tl_pdl) {
-    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[n].val.programmaticStreamSerializationAllowed = 1;
-    ++n;
-  }
-  if (tl_priority != kNoPriority) {
-    attr[n].id = cudaLaunchAttributePriority;
-    attr[n].val.priority = tl_priority;
-    ++n;
-  }
-  return n;
-}
 template <typename... KArgs, typename... Args>
 inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = add_scope_attrs(attr, 0);
+  cfg.numAttrs = tl_pdl ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
   if (e != cudaSuccess) throw CudaError(std::string("kernel launch -> ") + cudaGetErrorString(e));
 }

@@ -280,26 +280,14 @@ struct Impl {
     xkv.cache = e->cross_cache.p; xkv.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; xkv.T_enc = d.n_audio_ctx;
     xkv.n_slots = e->Q; xkv.n_layer = L;
     const int Ra = e->R_max;
-    // B200W_PRIO=1 (with B200W_GROUPS >= 2): chain kernels at the highest launch priority, cross-attention of group g at
-    // a lower one that differs per group, so the groups fall out of lockstep and one group's chain runs under another's
-    // cross-attention stream
-    static const bool prio = getenv("B200W_PRIO") != nullptr;
-    int prio_lo = 0, prio_hi = 0;
-    if (prio) BW_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    const int gi = (int)(&G - e->grp);
-    const int x_prio = prio ? std::min(prio_lo, prio_hi + 1 + gi) : kNoPriority;
-    PriorityScope chain_prio(prio ? prio_hi : kNoPriority);
     for (int l = 0; l < L; ++l) {
       const LayerW& w = e->w.dec[l];
       rows_gemm(xb, c.R, Ra, w.wqkv, 3 * dm, dm, w.c2_qkv, nullptr, G.d_qkv.p, false, true, nullptr, nullptr, lst, w.c1_qkv);
       dec_self_attention<bf16>(rows, G.d_qkv.as<float>(), skv, l, dm, H, G.d_att.as<bf16>(), st);
       rows_gemm(G.d_att.p, c.R, Ra, w.wo, dm, dm, w.bo, x, x, false, true, xb, lst, nullptr, nullptr);
       rows_gemm(xb, c.R, Ra, w.wq_x, dm, dm, w.c2_qx, nullptr, G.d_q.p, false, true, nullptr, nullptr, lst, w.c1_qx);
-      {
-        PriorityScope xp(x_prio);
-        dec_cross_attention<bf16>(c.grp_first, c.grp_n, c.grp_x, c.n_groups, c.max_group_rows, c.R, G.d_q.as<float>(), xkv, l, dm, H,
-                                  G.d_att.as<bf16>(), G.d_ws.as<float>(), st);
-      }
+      dec_cross_attention<bf16>(c.grp_first, c.grp_n, c.grp_x, c.n_groups, c.max_group_rows, c.R, G.d_q.as<float>(), xkv, l, dm, H,
+                                G.d_att.as<bf16>(), G.d_ws.as<float>(), st);
       rows_gemm(G.d_att.p, c.R, Ra, w.wo_x, dm, dm, w.bo_x, x, x, false, true, xb, lst, nullptr, nullptr);
       rows_gemm(xb, c.R, Ra, w.w1, 4 * dm, dm, w.c2_w1, nullptr, G.d_h.p, true, false, nullptr, nullptr, lst, w.c1_w1);
       rows_gemm(G.d_h.p, c.R, Ra, w.w2, dm, 4 * dm, w.b2, x, x, false, true, xb, lst, nullptr, nullptr);

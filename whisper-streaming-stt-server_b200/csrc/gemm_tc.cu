@@ -21,7 +21,6 @@ namespace bw {
 
 std::atomic<long long> g_kernel_launches{0};
 thread_local bool tl_pdl = false;
-thread_local int tl_priority = kNoPriority;
 unsigned long long* g_trace_dev = nullptr;
 
 namespace {
@@ -1023,11 +1022,13 @@ void launch_splitk(const GemmArgs& g, cudaStream_t stream) {
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[3];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = KS;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = add_scope_attrs(attr, 1);
+  cfg.numAttrs = tl_pdl ? 2 : 1;
   BW_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   ++g_kernel_launches;
 }
@@ -1062,11 +1063,13 @@ void launch_rows(const GemmArgs& g, cudaStream_t stream) {
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = R_SMEM_TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[3];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = KS;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = add_scope_attrs(attr, 1);
+  cfg.numAttrs = tl_pdl ? 2 : 1;
   BW_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   ++g_kernel_launches;
 }
