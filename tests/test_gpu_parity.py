@@ -296,6 +296,31 @@ def test_concurrent_sessions_batch_and_match_serial():
         assert got == [(round(x, 3), round(y, 3), t) for x, y, t in ref_segs], f"session {i}"
 
 
+def test_sampling_is_batch_invariant():
+    """Sampling windows decoded next to arg-max and beam-search windows of other sessions (one continuous batch, shared
+    decoder steps) return what they return alone: the draw depends on (seed, hypothesis, position, token) only."""
+    kw = dict(eot_bias=4.0)
+    b = backend("test-tiny", "float32", **kw)
+    audios = [synth_audio(200 + i, 3.0 + 0.5 * i) for i in range(9)]
+    plans = [dict(REALTIME, language="en", temperature=0.6, best_of=4), dict(REALTIME, language="en"),
+             dict(ACCURATE, language="en"), dict(REALTIME, language="en", temperature=(0.0, 0.5, 1.0), logprob_threshold=10.0, best_of=2)]
+
+    def run(i):
+        return _raw_key(b.transcribe_raw(audios[i], _seed=500 + i, **b._normalize_options(plans[i % len(plans)])))
+
+    serial = [run(i) for i in range(len(audios))]
+    out = [None] * len(audios)
+
+    def work(i):
+        out[i] = run(i)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(audios))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert out == serial
+    assert any(k[4] > 0 for r in serial for k in r), "no sampled segment in the mix"
+
+
 def test_errors_and_edge_cases():
     b = backend("test-tiny", "float32")
     segs, info = b.transcribe(np.zeros(0, np.float32), dict(REALTIME, language="en"))
