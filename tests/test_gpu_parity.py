@@ -138,6 +138,21 @@ def test_transcribe_eot_and_multiwindow_fp32():
     _check_transcribe(b, "test-tiny", synth_audio(10, 7.0), dict(ACCURATE, language="en"), **kw)
 
 
+@pytest.mark.parametrize("beam,patience,length_penalty", [(8, 1.0, 1.0), (5, 2.0, None), (3, 1.6, 0.6), (2, 0.5, 1.0)])
+def test_beam_patience_and_length_penalty_fp32(beam, patience, length_penalty):
+    """BeamSearchDecoder corners outside the two server profiles: the widest beam, patience != 1 (finished pool of
+    round(beam * patience) candidates, larger or smaller than the beam), length normalisation instead of the GNMT
+    penalty.  EOT-biased weights so that hypotheses do finish and the pool / ranker paths are taken."""
+    opts = dict(ACCURATE, language="en", beam_size=beam, best_of=beam, patience=patience)
+    if length_penalty is None:
+        opts.pop("length_penalty")
+    else:
+        opts["length_penalty"] = length_penalty
+    for seed, seconds, eot_bias in ((71, 5.0, 4.0), (72, 9.0, 5.0), (73, 3.0, 4.5)):
+        kw = dict(eot_bias=eot_bias)
+        _check_transcribe(backend("test-tiny", "float32", **kw), "test-tiny", synth_audio(seed, seconds), opts, **kw)
+
+
 def test_transcribe_bf16_first_divergence():
     """bf16 product mode: report where the token stream first leaves the fp32 oracle's (north_star)."""
     b = backend("test-tiny", "bfloat16")
