@@ -46,6 +46,7 @@ struct GemmDev {
   const float* c1;        // consumer: row sums of the folded weight
   int st_in_tiles;
   float ln_eps;
+  int vec8 = 0;           // pair kernel: C / residual rows are 32-byte aligned -> 256-bit epilogue loads and stores
 };
 
 template <int BN, int STAGES>
@@ -682,6 +683,24 @@ gemm_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // 6-stage TMA ring, two 256-column TMEM accumulators per SM: the epilogue of tile i overlaps the main
 // loop of tile i+1.  warp 0 = TMA producer (both CTAs; bytes are credited to the leader's barrier),
 // warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..11 = epilogue.
+// 256-bit global accesses (LDG / STG .256 on sm_100): an epilogue thread owns one accumulator ROW, so every access of a warp
+// touches 32 different lines; with 32 bytes per thread each instruction moves whole sectors (a float4 is half a sector, which
+// doubles the LSU transactions and makes every store a partial-sector write for L2 to merge).
+__device__ __forceinline__ void ldg256(const float* ptr, float* v) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(ptr));
+}
+__device__ __forceinline__ void stg256(float* ptr, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void stg256_bf16x16(bf16* ptr, const float* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(ptr), "r"(pack_bf16x2(v[0], v[1])), "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])),
+                  "r"(pack_bf16x2(v[6], v[7])), "r"(pack_bf16x2(v[8], v[9])), "r"(pack_bf16x2(v[10], v[11])),
+                  "r"(pack_bf16x2(v[12], v[13])), "r"(pack_bf16x2(v[14], v[15])) : "memory");
+}
+
 constexpr int P_STAGES = 6;
 constexpr int P_STAGE_BYTES = 2 * BM * BK * 2;  // A half + B half
 constexpr int P_BAR_OFF = P_STAGES * P_STAGE_BYTES;
@@ -819,7 +838,13 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (row_ok) {
         if (res) {
           const float* rr = res + (long long)i * p.ldres + j0;
-          if (full && ((p.ldres & 3) == 0)) {
+          if (full && p.vec8) {
+            float q[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) ldg256(rr + j, q + j);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += q[j];
+          } else if (full && ((p.ldres & 3) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 q = *reinterpret_cast<const float4*>(rr + j);
@@ -833,7 +858,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (p.out_fp32) {
           float* o = reinterpret_cast<float*>(p.C) + (long long)z * p.c_zstride + (long long)i * p.ldc + j0;
-          if (full && ((p.ldc & 3) == 0)) {
+          if (full && p.vec8) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) stg256(o + j, v + j);
+          } else if (full && ((p.ldc & 3) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
@@ -843,7 +871,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         } else {
           bf16* o = reinterpret_cast<bf16*>(p.C) + (long long)z * p.c_zstride + (long long)i * p.ldc + j0;
-          if (full && ((p.ldc & 7) == 0)) {
+          if (full && p.vec8) {
+            stg256_bf16x16(o, v);
+            stg256_bf16x16(o + 16, v + 16);
+          } else if (full && ((p.ldc & 7) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint4 q;
@@ -1093,6 +1124,13 @@ void launch_pair(const GemmArgs& g, cudaStream_t stream) {
   p.gelu = g.gelu; p.out_fp32 = g.out_fp32; p.transposed = 0; p.accumulate = 0; p.ksplit = 1;
   p.trace = nullptr;
   p.xb = nullptr; p.st_out = nullptr; p.st_in = nullptr; p.c1 = nullptr; p.st_in_tiles = 0; p.ln_eps = 0.f;
+  {
+    static const bool no_vec8 = getenv("B200W_NO_VEC8") != nullptr;
+    const long long c_elems = g.out_fp32 ? 8 : 16;  // elements per 32 bytes of C
+    auto aligned32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+    p.vec8 = !no_vec8 && aligned32(g.C) && g.ldc % c_elems == 0 && g.c_zstride % c_elems == 0 &&
+             (!g.residual || (aligned32(g.residual) && g.ldres % 8 == 0 && g.res_zstride % 8 == 0));
+  }
   const int m_pairs = (g.M + 255) / 256, n_tiles = (g.N + 255) / 256;
   const int total = m_pairs * n_tiles * g.Z;
   static int sm_count = 0;
