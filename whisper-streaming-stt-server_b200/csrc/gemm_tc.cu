@@ -47,6 +47,7 @@ struct GemmDev {
   int st_in_tiles;
   float ln_eps;
   int vec8 = 0;           // pair kernel: C / residual rows are 32-byte aligned -> 256-bit epilogue loads and stores
+  int res_prefetch = 0;   // pair kernel: L2-prefetch the residual rows of a tile before waiting for its accumulator
 };
 
 template <int BN, int STAGES>
@@ -805,6 +806,13 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool row_ok = i < p.M;
       const float* bias = p.bias ? p.bias + (long long)z * p.bias_zstride : nullptr;
       const float* res = p.residual ? p.residual + (long long)z * p.res_zstride : nullptr;
+      if (res && row_ok && p.res_prefetch) {
+        // the residual rows this thread will add come from HBM: ask for them while the main loop of the tile still runs
+        const float* rr = res + (long long)i * p.ldres + n0 + chalf * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (n0 + chalf * 128 + k * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" :: "l"(rr + k * 32));
+      }
       mbar_wait(&tmem_full_bar[a], (ti >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -1130,6 +1138,8 @@ void launch_pair(const GemmArgs& g, cudaStream_t stream) {
     auto aligned32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
     p.vec8 = !no_vec8 && aligned32(g.C) && g.ldc % c_elems == 0 && g.c_zstride % c_elems == 0 &&
              (!g.residual || (aligned32(g.residual) && g.ldres % 8 == 0 && g.res_zstride % 8 == 0));
+    static const bool no_prefetch = getenv("B200W_NO_RES_PREFETCH") != nullptr;
+    p.res_prefetch = !no_prefetch && g.residual != nullptr;
   }
   const int m_pairs = (g.M + 255) / 256, n_tiles = (g.N + 255) / 256;
   const int total = m_pairs * n_tiles * g.Z;
