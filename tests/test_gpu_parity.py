@@ -25,7 +25,8 @@ def backend(name="test-tiny", compute="float32", **kw):
 
 
 @pytest.mark.parametrize("name,n_mels", [("test-tiny", 80), ("test-v3", 128)])
-@pytest.mark.parametrize("seconds,padding", [(30.0, 480000), (3.96, 480000), (1.0, 480000), (0.3, 480000), (2.5, 0), (10.01, 137)])
+@pytest.mark.parametrize("seconds,padding", [(30.0, 480000), (3.96, 480000), (1.0, 480000), (0.3, 480000), (2.5, 0), (10.01, 137),
+                                             (15.0, 480000), (20.3, 480000)])  # 4, 8 and 16 frames per CTA
 def test_log_mel(name, n_mels, seconds, padding):
     eng = backend(name).engine
     audio = synth_audio(int(seconds * 10), seconds)

@@ -13,7 +13,8 @@
 namespace bw {
 namespace {
 
-constexpr int FT = 16;        // frames per CTA
+// frames per CTA (FT): 16 for long calls; 8 / 4 when a call has too few frames to give every SM a CTA (a 6 s streaming partial
+// is 600 frames = 38 CTAs of 16)
 constexpr int NBIN = 201;
 constexpr int MEL_THREADS = 224;
 constexpr int PSTRIDE = 209;  // odd stride: conflict-free column reads of the power tile
@@ -25,6 +26,7 @@ __device__ __forceinline__ float sample_at(const float* __restrict__ pcm, long l
   return (idx < n) ? __ldg(pcm + idx) : 0.f;
 }
 
+template <int FT>
 __global__ void __launch_bounds__(MEL_THREADS)
 mel_power_kernel(const float* __restrict__ pcm, long long n, long long L, int n_real, int total_frames,
                  const float* __restrict__ tables,   // cos[425] sin[425] win[201]
@@ -186,17 +188,26 @@ void mel_power(const float* pcm_dev, long long n, long long padding, const float
                cudaStream_t stream) {
   BW_CUDA(cudaMemsetAsync(gmax_bits, 0, sizeof(int), stream));
   if (n_real <= 0) return;
-  const size_t smem = sizeof(float) * ((FT * 160 + 240) + 2 * NBIN * FT + 850 + FT * PSTRIDE);
+  static int n_sm[64];
   static std::atomic<unsigned long long> attr_set{0};
   int dev = 0;
   BW_CUDA(cudaGetDevice(&dev));
+  auto smem_of = [](int ft) { return sizeof(float) * ((size_t)(ft * 160 + 240) + 2 * NBIN * ft + 850 + ft * PSTRIDE); };
   if (!(attr_set.load() >> dev & 1ull)) {
-    BW_CUDA(cudaFuncSetAttribute(mel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BW_CUDA(cudaFuncSetAttribute(mel_power_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(16)));
+    BW_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set.fetch_or(1ull << dev);
   }
-  const int grid = (n_real + FT - 1) / FT;
-  mel_power_kernel<<<grid, MEL_THREADS, smem, stream>>>(pcm_dev, n, n + padding, n_real, total_frames, tables, filters,
-                                                          ranges, n_mels, logmel, ld, gmax_bits);
+  static const int forced = getenv("B200W_MEL_FT") ? atoi(getenv("B200W_MEL_FT")) : 0;
+  const int ft = forced ? forced : (n_real >= 16 * n_sm[dev] ? 16 : n_real >= 8 * n_sm[dev] ? 8 : 4);
+  const int grid = (n_real + ft - 1) / ft;
+  auto launch = [&](auto kern) {
+    kern<<<grid, MEL_THREADS, smem_of(ft), stream>>>(pcm_dev, n, n + padding, n_real, total_frames, tables, filters, ranges, n_mels,
+                                                     logmel, ld, gmax_bits);
+  };
+  if (ft == 16) launch(mel_power_kernel<16>);
+  else if (ft == 8) launch(mel_power_kernel<8>);
+  else launch(mel_power_kernel<4>);
   BW_CUDA(cudaGetLastError());
   ++g_kernel_launches;
 }
