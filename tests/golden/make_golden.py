@@ -50,6 +50,18 @@ def main():
             dec[f"{name}_{pname}_tokens"] = np.array(w.tokens, dtype=np.int32)
             dec[f"{name}_{pname}_stats"] = np.array([w.sum_logprob, w.avg_logprob, w.no_speech_prob, w.min_margin], dtype=np.float64)
             dec[f"{name}_{pname}_segments"] = np.array([[s[0], s[1]] for s in segs], dtype=np.float64)
+    # temperature > 0: seeded Gumbel-max draws (OUR counter-based generator, restated on the device) and the fallback ladder
+    for name in ("test-tiny", "test-v3"):
+        dims = MODEL_DIMS[name]
+        model = wo.Whisper(wo.ModelDimensions(**dims.__dict__), random_state_dict(dims, 0, emb_std=0.1, eot_bias=4.0))
+        audio = synth_audio(51, 6.0)
+        for tag, temperature, extra in (("t07", 0.7, {}), ("ladder", (0.0, 0.4, 0.8), {"logprob_threshold": 10.0})):
+            opts = dict(ACCURATE, best_of=3, temperature=temperature, **extra)
+            segs, info, raw = wo.backend_transcribe(model, audio, opts, sample_seed=11)
+            w = raw["windows"][0]
+            dec[f"{name}_sample_{tag}_tokens"] = np.array(w.tokens, dtype=np.int32)
+            dec[f"{name}_sample_{tag}_stats"] = np.array([w.sum_logprob, w.avg_logprob, w.temperature, w.min_margin], dtype=np.float64)
+    dec["gumbel_seed123_stream2_pos7"] = wo.gumbel_noise(123, 2, 7, 64)
     np.savez_compressed(os.path.join(OUT, "decode.npz"), **dec)
     with open(os.path.join(OUT, "META.txt"), "w") as fh:
         for k, v in meta.items():
