@@ -227,6 +227,32 @@ def test_temperature_fallback_ladder_matches_oracle(fake_backend, case):
         b.transcribe_raw(audio, temperature=0.2, best_of=9, language="en")
 
 
+def test_sampling_seeds(fake_backend, monkeypatch):
+    """Every call of a backend draws from its own stream; B200_WHISPER_SEED makes a process reproducible; `_seed` pins a call."""
+    v = vocab_for(51865)
+    script = [res([v.timestamp_begin, 11, v.timestamp_begin + 100])]
+    audio = synth_audio(4, 3.0)
+    monkeypatch.setenv("B200_WHISPER_SEED", "42")
+    b1, eng1 = fake_backend(script)
+    b2, eng2 = fake_backend(script)
+    for b in (b1, b2):
+        for _ in range(2):
+            b.transcribe(audio, {"language": "en", "temperature": 0.5, "best_of": 2})
+    s1 = [d["seed"] for d in eng1.all_decodes]
+    s2 = [d["seed"] for d in eng2.all_decodes]
+    assert s1 == s2 and s1[0] != s1[1] and all(0 <= s < 2 ** 64 for s in s1)
+    monkeypatch.delenv("B200_WHISPER_SEED")
+    b3, eng3 = fake_backend(script)
+    b3.transcribe(audio, {"language": "en", "temperature": 0.5})
+    assert eng3.all_decodes[0]["seed"] != s1[0] and eng3.all_decodes[0]["best_of"] is None
+    b3.transcribe_raw(audio, language="en", temperature=0.5, _seed=7)
+    b3.transcribe_raw(audio, language="en", temperature=0.5, _seed=7)
+    assert eng3.all_decodes[1]["seed"] == eng3.all_decodes[2]["seed"] == bk.window_seed(7, 0, 0) == wo.window_seed(7, 0, 0)
+    # temperature 0 never asks the engine to sample
+    b3.transcribe(audio, {"language": "en", "temperature": 0.0, "best_of": 5})
+    assert "temperature" not in eng3.all_decodes[-1]
+
+
 def test_device_parsing_and_compute_types(monkeypatch):
     assert bk.parse_device("cuda", 3) == 0 and bk.parse_device("cuda:5", 0) == 5
     monkeypatch.setattr(bk, "get_engine", lambda *a, **k: FakeEngine())
