@@ -85,3 +85,46 @@ def test_encoder_decoder_match_hf_whisper():
     assert (xa - enc_hf).abs().max() < 2e-4
     assert (logits - logits_hf).abs().max() < 2e-3
     assert logits.argmax(-1).tolist() == logits_hf.argmax(-1).tolist()
+
+
+@pytest.mark.parametrize("n_vocab", [51864, 51865, 51866])
+def test_logit_filters_match_hf_logits_processors(n_vocab):
+    """SuppressBlank + SuppressTokens + ApplyTimestampRules of the oracle (`_Filters`, restating upstream decoding.py) against
+    HF's ports of the same three filters (generation/logits_process.py) on random logits and token histories that reach every
+    branch: first sampled position, text after a timestamp, a closed pair, an open timestamp, non-decreasing timestamps,
+    timestamp mass above / below the best text token."""
+    from types import SimpleNamespace
+
+    from transformers.generation.logits_process import (SuppressTokensAtBeginLogitsProcessor, SuppressTokensLogitsProcessor,
+                                                        WhisperTimeStampLogitsProcessor)
+
+    lay = layout_for_vocab(n_vocab)
+    tb, V = lay.timestamp_begin, lay.n_vocab
+    initial = list(lay.sot_sequence("en", "transcribe"))
+    begin = len(initial)
+    cfg = SimpleNamespace(no_timestamps_token_id=lay.no_timestamps, eos_token_id=lay.eot, bos_token_id=lay.eot,
+                          max_initial_timestamp_index=50, _detect_timestamp_from_logprob=True)
+    hf = [SuppressTokensAtBeginLogitsProcessor([lay.blank, lay.eot], begin), SuppressTokensLogitsProcessor(list(lay.suppress_tokens())),
+          WhisperTimeStampLogitsProcessor(cfg, begin_index=begin)]
+    f = wo._Filters(lay, begin, wo.DecodingOptions(), n_audio_ctx=1500)
+    assert f.max_initial_timestamp_index == 50
+    rng = np.random.default_rng(n_vocab)
+    text = lambda: int(rng.integers(0, lay.eot))
+    histories = [[], [tb + 3], [tb + 3, text()], [tb + 3, text(), text()], [tb + 3, text(), tb + 40], [tb + 3, text(), tb + 40, tb + 40],
+                 [tb, text(), tb + 10, tb + 10, text(), text(), tb + 700], [text()], [text(), text(), tb + 1499], [tb + 1500],
+                 [tb + 5, tb + 5], [tb + 20, text(), tb + 20, tb + 20, text()]]
+    for hist in histories:
+        for trial in range(6):
+            logits = torch.from_numpy(rng.normal(size=(2, V)).astype(np.float32)) * 3.0
+            if trial % 3 == 1:
+                logits[:, text()] += 40.0          # text mass wins the last rule
+            if trial % 3 == 2:
+                logits[:, tb + 800 : tb + 900] += 6.0  # timestamp mass wins it
+            tokens = torch.tensor([initial + hist, initial + hist])
+            want = logits.clone()
+            for proc in hf:
+                want = proc(tokens, want)
+            got = logits.clone()
+            f.apply(got, tokens)
+            assert torch.equal(torch.isfinite(got), torch.isfinite(want)), (hist, trial)
+            assert torch.equal(torch.where(torch.isfinite(got), got, torch.zeros(())), torch.where(torch.isfinite(want), want, torch.zeros(())))
