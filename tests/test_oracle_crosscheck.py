@@ -128,3 +128,50 @@ def test_logit_filters_match_hf_logits_processors(n_vocab):
             f.apply(got, tokens)
             assert torch.equal(torch.isfinite(got), torch.isfinite(want)), (hist, trial)
             assert torch.equal(torch.where(torch.isfinite(got), got, torch.zeros(())), torch.where(torch.isfinite(want), want, torch.zeros(())))
+
+
+def test_greedy_decode_matches_hf_model_with_hf_cache_and_processors():
+    """The whole greedy loop in composition: HF's model code with HF's own KV cache and HF's logits processors, driven by a
+    plain arg-max loop, must emit the oracle's token stream (`decode_window`: upstream DecodingTask + GreedyDecoder)."""
+    from types import SimpleNamespace
+
+    from transformers.generation.logits_process import (SuppressTokensAtBeginLogitsProcessor, SuppressTokensLogitsProcessor,
+                                                        WhisperTimeStampLogitsProcessor)
+
+    dims = MODEL_DIMS["test-tiny"]
+    n_steps = 48
+    for seed, eot_bias in ((6, 0.0), (8, 4.0)):
+        state = random_state_dict(dims, 0, emb_std=0.1, eot_bias=eot_bias)
+        model = wo.Whisper(wo.ModelDimensions(**dims.__dict__), state)
+        hf = _to_hf(state, dims)
+        lay = layout_for_vocab(dims.n_vocab)
+        mel = wo.pad_or_trim(wo.log_mel_spectrogram(synth_audio(seed, 5.0), 80, padding=480000), 3000)
+        want = wo.decode_window(model, mel, wo.DecodingOptions(language="en", sample_len=n_steps))
+        assert want.min_margin > 1e-3
+        initial = list(lay.sot_sequence("en", "transcribe"))
+        cfg = SimpleNamespace(no_timestamps_token_id=lay.no_timestamps, eos_token_id=lay.eot, bos_token_id=lay.eot,
+                              max_initial_timestamp_index=50, _detect_timestamp_from_logprob=True)
+        procs = [SuppressTokensAtBeginLogitsProcessor([lay.blank, lay.eot], len(initial)), SuppressTokensLogitsProcessor(list(lay.suppress_tokens())),
+                 WhisperTimeStampLogitsProcessor(cfg, begin_index=len(initial))]
+        with torch.no_grad():
+            enc = hf.encoder(mel[None]).last_hidden_state
+            tokens = torch.tensor([initial])
+            past = None
+            sum_logprob = 0.0
+            for i in range(n_steps):
+                out = hf.decoder(input_ids=tokens if past is None else tokens[:, -1:], encoder_hidden_states=enc,
+                                 past_key_values=past, use_cache=True)
+                past = out.past_key_values
+                logits = (out.last_hidden_state[:, -1] @ hf.decoder.embed_tokens.weight.t()).float()
+                for proc in procs:
+                    logits = proc(tokens, logits)
+                nxt = int(logits.argmax(-1))
+                sum_logprob += float(torch.log_softmax(logits, -1)[0, nxt])
+                tokens = torch.cat([tokens, torch.tensor([[nxt]])], dim=-1)
+                if nxt == lay.eot:
+                    break
+        got = tokens[0, len(initial):].tolist()
+        if got and got[-1] == lay.eot:
+            got = got[:-1]
+        assert got == want.tokens, (seed, eot_bias)
+        assert abs(sum_logprob - want.sum_logprob) < 2e-3 * max(1.0, abs(want.sum_logprob))
