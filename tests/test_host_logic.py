@@ -253,6 +253,46 @@ def test_sampling_seeds(fake_backend, monkeypatch):
     assert "temperature" not in eng3.all_decodes[-1]
 
 
+def test_server_option_surface_from_the_reference(fake_backend, caplog):
+    """The option dicts that really reach `transcribe` -- the server's shipped decode profiles and every key a client may send
+    (fixture generated from the real reference by tests/golden/make_golden_server_options.py): the parity tests' REALTIME /
+    ACCURATE constants ARE those profiles, and each allowed key is either honoured or warned about and dropped, never an error
+    (torch_whisper.py:78-110 precedent), with the caller's dict left untouched."""
+    import json
+    import logging
+    import os
+
+    from tests._util import ACCURATE, REALTIME
+
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "server_options.json")))
+    assert fx["decode_profiles"]["realtime"] == REALTIME and fx["decode_profiles"]["accurate"] == ACCURATE
+    assert fx["default_decode_profile"] == REALTIME and fx["default_task"] == "transcribe"
+    v = vocab_for(51865)
+    b, eng = fake_backend([res([v.timestamp_begin, 11, v.timestamp_begin + 100])])
+    audio = synth_audio(5, 2.0)
+    samples = {"append_punctuations": ".", "prepend_punctuations": "(", "chunk_length": 30, "clip_timestamps": "0", "hotwords": "x",
+               "initial_prompt": "hello", "language": "en", "max_initial_timestamp": 1.0, "no_repeat_ngram_size": 2, "prefix": "x",
+               "prompt_reset_on_temperature": 0.5, "repetition_penalty": 1.1, "suppress_blank": True, "suppress_tokens": [-1],
+               "task": "transcribe", "temperature_increment_on_fallback": 0.2, "vad_filter": True, "vad_parameters": {},
+               "word_timestamps": False, "condition_on_previous_text": False}
+    honoured = bk.SUPPORTED_OPTIONS | {"log_prob_threshold", "without_timestamps"}
+    for key in fx["allowed_decode_option_keys"]:
+        for profile in ("realtime", "accurate"):
+            opts = dict(fx["decode_profiles"][profile], task=fx["default_task"])
+            if key not in opts:
+                opts[key] = samples[key]
+            frozen = json.dumps(opts, sort_keys=True, default=str)
+            caplog.clear()
+            with caplog.at_level(logging.WARNING, logger="stt_server.model_backend"):
+                segs, info = b.transcribe(audio, opts)
+            assert json.dumps(opts, sort_keys=True, default=str) == frozen
+            assert isinstance(segs, list) and info.language_probability == -1.0
+            dropped = any("Dropping unsupported" in r.getMessage() and f" {key}=" in r.getMessage() for r in caplog.records)
+            assert dropped == (key not in honoured), key
+    # the profiles decode with the decoder upstream would pick: beam search with 1 / 5 beams, best_of dropped at temperature 0
+    assert {d["beam"] for d in eng.all_decodes} == {1, 5} and all("best_of" not in d for d in eng.all_decodes)
+
+
 def test_device_parsing_and_compute_types(monkeypatch):
     assert bk.parse_device("cuda", 3) == 0 and bk.parse_device("cuda:5", 0) == 5
     monkeypatch.setattr(bk, "get_engine", lambda *a, **k: FakeEngine())
