@@ -1,0 +1,93 @@
+"""Wire-level load test: the UNMODIFIED reference server (started through b200_whisper.launcher) under the reference's own
+load generator `tools/bench/grpc_load_test.py`, run unchanged.
+
+  python tools/wire_bench.py [--fake-engine] [--channels 64] [--seconds 10] [--pool-size 16] [--model random:large-v3]
+                             [--server-root /root/reference] [-- extra grpc_load_test.py arguments]
+
+--fake-engine replaces the engine below the backend by the host-logic fake (tests/_ref_server_driver.py): no GPU needed; what
+is measured then is the ceiling of the server's Python control plane in front of a zero-cost backend.  Without it the real
+engine runs (needs a B200 and the reference checkout on the same box)."""
+import argparse
+import os
+import runpy
+import socket
+import subprocess
+import sys
+import tempfile
+import time
+import wave
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+
+def free_port() -> int:
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--fake-engine", action="store_true")
+    ap.add_argument("--channels", type=int, default=64)
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--pool-size", type=int, default=16)
+    ap.add_argument("--model", default="random:large-v3")
+    ap.add_argument("--decode-profile", default="realtime")
+    ap.add_argument("--server-root", default=os.environ.get("STT_SERVER_ROOT", "/root/reference"))
+    args, extra = ap.parse_known_args()
+    extra = [a for a in extra if a != "--"]
+    sys.path.append(args.server_root)
+
+    from b200_whisper import protostubs
+    from b200_whisper.synth import synth_audio
+
+    tmp = tempfile.mkdtemp(prefix="wire_bench_")
+    wav = os.path.join(tmp, "speech.wav")
+    pcm = (np.clip(synth_audio(11, args.seconds), -1, 1) * 32767).astype(np.int16)
+    with wave.open(wav, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(pcm.tobytes())
+    port, mport, wport = free_port(), free_port(), free_port()
+    cfg = os.path.join(tmp, "server.yaml")
+    with open(cfg, "w") as fh:
+        fh.write(open(os.path.join(args.server_root, "config", "server.yaml")).read())
+        fh.write(f"\nws_host: 127.0.0.1\nws_port: {wport}\nmax_sessions: {max(256, 2 * args.channels)}\n"
+                 "max_sessions_per_ip: 0\nmax_sessions_per_api_key: 0\ncreate_session_rps: 0\nmax_audio_bytes_per_sec: 0\n"
+                 "max_audio_bytes_per_sec_burst: 0\n")  # one load generator = one client IP: lift the per-IP limits
+    entry = [os.path.join(REPO, "tests", "_ref_server_driver.py")] if args.fake_engine else ["-m", "b200_whisper.launcher"]
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([REPO, args.server_root, os.environ.get("PYTHONPATH", "")]))
+    server = subprocess.Popen([sys.executable, *entry, "--config", cfg, "--model-backend", "b200_whisper", "--model", args.model,
+                               "--device", "cuda:0", "--port", str(port), "--metrics-port", str(mport), "--vad-threshold", "0",
+                               "--model-pool-size", str(args.pool_size), "--language", "en", "--log-level", "WARNING"],
+                              cwd=REPO, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+    try:
+        import grpc
+
+        protostubs.install(os.path.join(args.server_root, "proto", "stt.proto"))
+        grpc.channel_ready_future(grpc.insecure_channel(f"127.0.0.1:{port}")).result(timeout=600)
+        sys.argv = ["grpc_load_test.py", "--target", f"127.0.0.1:{port}", "--channels", str(args.channels), "--iterations", "1",
+                    "--audio", wav, "--chunk-ms", "100", "--realtime", "--decode-profile", args.decode_profile, "--language", "en",
+                    "--vad-mode", "continue", *extra]
+        t0 = time.time()
+        try:
+            runpy.run_path(os.path.join(args.server_root, "tools", "bench", "grpc_load_test.py"), run_name="__main__")
+        except SystemExit as exc:
+            print(f"grpc_load_test.py exited with {exc.code}")
+        wall = time.time() - t0
+        print(f"wire_bench: {args.channels} channels x {args.seconds:.0f} s of audio in {wall:.1f} s wall "
+              f"({args.channels * args.seconds / wall:.1f} audio-s/s through the wire), engine = {'fake' if args.fake_engine else 'B200'}")
+    finally:
+        server.terminate()
+        try:
+            server.wait(timeout=40)
+        except subprocess.TimeoutExpired:
+            server.kill()
+
+
+if __name__ == "__main__":
+    main()
