@@ -41,6 +41,10 @@ class _Parser:
         self.i = 0
         self.fd = descriptor_pb2.FileDescriptorProto(name=file_name, syntax="proto3")
         self.package = ""
+        # filled while parsing, finished in parse_proto(): fields whose type is a message / enum name, and proto3 `optional`
+        # fields (each gets a synthetic one-field oneof placed after the real ones, as protoc does)
+        self.unresolved: List[descriptor_pb2.FieldDescriptorProto] = []
+        self.synthetic: List[Tuple[descriptor_pb2.DescriptorProto, descriptor_pb2.FieldDescriptorProto, str]] = []
 
     def peek(self) -> Optional[str]:
         return self.t[self.i] if self.i < len(self.t) else None
@@ -169,13 +173,11 @@ class _Parser:
                 fd.oneof_index = oneof_index
             if proto3_optional:  # proto3 `optional` = a synthetic one-field oneof (what protoc emits)
                 fd.proto3_optional = True
-                self._synthetic.append((md, fd, name))
+                self.synthetic.append((md, fd, name))
         if self.peek() == "[":
             while self.take() != "]":
                 pass
         self.take(";")
-
-    _synthetic: List[Tuple[descriptor_pb2.DescriptorProto, descriptor_pb2.FieldDescriptorProto, str]] = []
 
     def _typed(self, fd: descriptor_pb2.FieldDescriptorProto, type_name: str) -> None:
         if type_name in SCALARS:
@@ -183,9 +185,7 @@ class _Parser:
         else:
             # resolved after parsing (enum vs message); proto3 files in scope here use package-level names
             fd.type_name = type_name
-            self._unresolved.append(fd)
-
-    _unresolved: List[descriptor_pb2.FieldDescriptorProto] = []
+            self.unresolved.append(fd)
 
     def service(self) -> None:
         sd = self.fd.service.add(name=self.take())
@@ -232,7 +232,6 @@ def _json_name(name: str) -> str:
 def parse_proto(text: str, file_name: str = "stt.proto") -> descriptor_pb2.FileDescriptorProto:
     """proto3 text -> FileDescriptorProto (the subset described in the module docstring)."""
     p = _Parser(text, file_name)
-    p._unresolved, p._synthetic = [], []
     fd = p.parse()
     # type names: look them up among the declared messages / enums (outermost scope first, then nested)
     enums: Dict[str, str] = {}
@@ -261,9 +260,9 @@ def parse_proto(text: str, file_name: str = "stt.proto") -> descriptor_pb2.FileD
                 return c, _F.TYPE_ENUM
         raise ValueError(f".proto: unknown type {name!r}")
 
-    for f in p._unresolved:
+    for f in p.unresolved:
         f.type_name, f.type = resolve(f.type_name)
-    for md, f, name in p._synthetic:  # synthetic oneofs go after the real ones
+    for md, f, name in p.synthetic:  # synthetic oneofs go after the real ones
         f.oneof_index = len(md.oneof_decl)
         md.oneof_decl.add(name=f"_{name}")
     return fd
