@@ -195,9 +195,14 @@ def cpu_oracle_window(state, model_name: str, seconds: float, sample_len=None, t
     return time.perf_counter() - t0, cores
 
 
+def workload_name(model: str, sessions: int) -> str:
+    return (f"{model} realtime profile (beam_size=1), {sessions} concurrent sessions per GPU, one 2-10 s "
+            f"partial window per session per step (configs[4] per-GPU shard)")
+
+
 def run_reference(args):
-    rank, world, local, dist = dist_setup(args.gpus)
-    if rank != 0:
+    # the CPU arm needs no process group: under torchrun rank 0 alone runs and prints, the other ranks exit 0 without work
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     from b200_whisper.synth import MODEL_DIMS, random_state_dict
 
@@ -217,8 +222,9 @@ def run_reference(args):
         "impl": "reference", "metric": "RTFx (audio-seconds transcribed per second)", "value": value, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic audio, random-init weights",
-        "config": {"workload": f"{args.model} realtime profile (beam_size=1), partial windows 2-10 s, one window per step on host cores",
-                   "note": "warm-up steps decode 4 tokens only; timed steps are full windows"},
+        "config": {"workload": workload_name(args.model, args.sessions),
+                   "sample": "bounded sample of that workload: ONE of its windows per step (6 s partial) on the host cores, fp32 torch",
+                   "note": "warm-up steps decode 4 tokens only; timed steps are full windows (224 decoder steps)"},
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -327,8 +333,7 @@ def run_b200(args):
         "metric": "RTFx (audio-seconds transcribed per second)", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic audio, random-init weights (no EOT: 224 decoder steps per window)",
-        "config": {"workload": f"{args.model} realtime profile (beam_size=1), {S} concurrent sessions per GPU, one 2-10 s "
-                               f"partial window per session per step (configs[4] per-GPU shard)",
+        "config": {"workload": workload_name(args.model, S),
                    "sessions_per_gpu": S, "audio_s_per_step_per_gpu": audio_sec, "decoder_steps_per_window": n_steps,
                    "l2": "inputs larger than L2 (cross-KV cache %.1f GB per step)" % (S * dims.n_text_layer * 1500 * 2 * dims.n_text_state * 2 / 1e9),
                    "timing": "CUDA events on the engine stream inside libb200whisper.so, max over ranks", "peaks": pk["source"]},
