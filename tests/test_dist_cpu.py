@@ -56,6 +56,17 @@ def test_reference_arm_is_rank0_only(monkeypatch):
 
     called = []
     monkeypatch.setattr(bench, "cpu_oracle_window", lambda *a, **k: called.append(1) or (1.0, 1))
-    monkeypatch.setattr(bench, "dist_setup", lambda n: (1, 2, 1, None))
-    bench.run_reference(type("A", (), {"gpus": 2, "steps": 1, "warmup": 0, "model": "test-tiny", "cpu_threads": 1})())
+    monkeypatch.setattr(bench, "emit", lambda line: called.append(line))
+    args = type("A", (), {"gpus": 2, "steps": 1, "warmup": 0, "model": "test-tiny", "cpu_threads": 1, "sessions": 128})()
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    bench.run_reference(args)
     assert called == []
+    monkeypatch.setenv("RANK", "0")  # rank 0 runs it alone, with no process group, and prints one line on our arm's workload
+    bench.run_reference(args)
+    assert called[0] == 1 and len(called) == 2
+    import json
+
+    line = json.loads(called[1])
+    assert line["impl"] == "reference" and line["config"]["workload"] == bench.workload_name("test-tiny", 128) and line["n_gpus"] == 2
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
