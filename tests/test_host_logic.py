@@ -253,6 +253,26 @@ def test_sampling_seeds(fake_backend, monkeypatch):
     assert "temperature" not in eng3.all_decodes[-1]
 
 
+def test_wrapper_matches_the_real_torch_whisper_wrapper(fake_backend):
+    """Option normalisation and result mapping against outputs of the REAL `TorchWhisperBackend` methods
+    (stt_server/model/backends/torch_whisper.py:49-110, run in the build container by make_golden_server_options.py)."""
+    import json
+    import os
+
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "server_options.json")))
+    b, _ = fake_backend([res([])])
+    norm = fx["torch_whisper_normalize_options"]
+    for given, want in zip(norm["inputs"], norm["outputs"]):
+        frozen = json.dumps(given, sort_keys=True)
+        assert b._normalize_options(given) == want, given
+        assert json.dumps(given, sort_keys=True) == frozen
+    mapping = fx["torch_whisper_result_mapping"]
+    for given, want in zip(mapping["inputs"], mapping["outputs"]):
+        segs, info = b._to_segments(given)
+        assert [[s.start, s.end, s.text] for s in segs] == want["segments"]
+        assert (info.language, info.language_probability) == (want["language"], want["language_probability"])
+
+
 def test_server_option_surface_from_the_reference(fake_backend, caplog):
     """The option dicts that really reach `transcribe` -- the server's shipped decode profiles and every key a client may send
     (fixture generated from the real reference by tests/golden/make_golden_server_options.py): the parity tests' REALTIME /

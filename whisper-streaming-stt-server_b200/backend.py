@@ -256,9 +256,20 @@ class B200WhisperBackend:
 
     def _to_segments(self, result: dict) -> Tuple[List[Segment], BackendInfo]:
         segments: List[Segment] = []
-        for seg in result.get("segments", []):
-            segments.append(Segment(float(seg.get("start", 0.0)), float(seg.get("end", 0.0)), str(seg.get("text", "") or "")))
+        for seg in result.get("segments", []):  # same defensive mapping as torch_whisper.py:56-75
+            if not isinstance(seg, dict):
+                continue
+
+            def as_float(value: Any) -> float:
+                try:
+                    return float(value)
+                except (TypeError, ValueError):
+                    return 0.0
+
+            segments.append(Segment(as_float(seg.get("start", 0.0)), as_float(seg.get("end", 0.0)), str(seg.get("text", "") or "")))
         language = result.get("language") or ""
+        if not isinstance(language, str):
+            language = str(language)
         # parity with torch_whisper.py:76: the probability is reported as -1.0 ("unknown"); the detected
         # value stays available as `last_language_probability` (B200_WHISPER_REPORT_LANGUAGE_PROB=1 returns it)
         self.last_language_probability = result.get("language_probability")
