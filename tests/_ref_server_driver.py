@@ -1,5 +1,9 @@
 """Test driver (not product): starts the REAL reference server through `b200_whisper.launcher` with the engine below the
-backend replaced by the host-logic fake (this container has no GPU).  argv is passed to stt_server.main unchanged."""
+backend replaced by the host-logic fake (this container has no GPU).  argv is passed to stt_server.main unchanged.
+
+B200_TEST_ENERGY_VAD=1 also provides a stand-in for the `silero_vad` package (absent here, weights not vendored): a frame is
+speech when its RMS exceeds 0.01.  It only exists so that the server's own VAD gate, endpointing and partial-decode
+schedule run (--vad-threshold > 0); it says nothing about Silero's decisions."""
 import os
 import sys
 
@@ -14,6 +18,23 @@ v = vocab_for(51865)
 tb = v.timestamp_begin
 ENGINE = FakeEngine(51865, [res([tb, 11, 12, tb + 100])])
 bk.get_engine = lambda *a, **k: ENGINE
+
+if os.environ.get("B200_TEST_ENERGY_VAD") == "1":
+    import types
+
+    import torch
+
+    class EnergyVAD:
+        def __call__(self, audio_tensor, sample_rate):
+            rms = float(torch.sqrt(torch.mean(audio_tensor.float() ** 2)))
+            return torch.tensor(1.0 if rms > 0.01 else 0.0)
+
+        def reset_states(self):
+            pass
+
+    stub = types.ModuleType("silero_vad")
+    stub.load_silero_vad = lambda onnx=False: EnergyVAD()
+    sys.modules["silero_vad"] = stub
 
 from b200_whisper.launcher import main  # noqa: E402
 

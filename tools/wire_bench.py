@@ -4,7 +4,8 @@ load generator `tools/bench/grpc_load_test.py`, run unchanged (SURVEY.md section
   python tools/wire_bench.py [--fake-engine] [--channels 64] [--seconds 10] [--pool-size 16] [--model random:large-v3]
                              [--server-root /root/reference] [-- extra grpc_load_test.py arguments]
 
---fake-engine replaces the engine below the backend by the host-logic fake (tests/_ref_server_driver.py): no GPU needed; what
+--energy-vad (with --fake-engine) turns the server's VAD gate on over an energy stand-in for silero_vad, so that its endpointing and
+partial-decode schedule run.  --fake-engine replaces the engine below the backend by the host-logic fake (tests/_ref_server_driver.py): no GPU needed; what
 is measured then is the ceiling of the server's Python control plane in front of a zero-cost backend.  Without it the real
 engine runs (needs a B200 and the reference checkout on the same box)."""
 import argparse
@@ -34,6 +35,7 @@ def free_port() -> int:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--fake-engine", action="store_true")
+    ap.add_argument("--energy-vad", action="store_true", help="with --fake-engine: energy stand-in for silero_vad, VAD gate on")
     ap.add_argument("--channels", type=int, default=64)
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--pool-size", type=int, default=16)
@@ -61,8 +63,11 @@ def main() -> None:
                  "max_audio_bytes_per_sec_burst: 0\n")  # one load generator = one client IP: lift the per-IP limits
     entry = [os.path.join(REPO, "tests", "_ref_server_driver.py")] if args.fake_engine else ["-m", "b200_whisper.launcher"]
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([REPO, args.server_root, os.environ.get("PYTHONPATH", "")]))
+    if args.energy_vad:
+        env["B200_TEST_ENERGY_VAD"] = "1"
+    vad_threshold = "0.5" if args.energy_vad else "0"
     server = subprocess.Popen([sys.executable, *entry, "--config", cfg, "--model-backend", "b200_whisper", "--model", args.model,
-                               "--device", "cuda:0", "--port", str(port), "--metrics-port", str(mport), "--vad-threshold", "0",
+                               "--device", "cuda:0", "--port", str(port), "--metrics-port", str(mport), "--vad-threshold", vad_threshold,
                                "--model-pool-size", str(args.pool_size), "--language", "en", "--log-level", "WARNING"],
                               cwd=REPO, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
     try:
