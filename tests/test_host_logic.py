@@ -372,6 +372,52 @@ def test_registration_wraps_reference_get_backend(monkeypatch):
     assert "faster_whisper" in sys.modules  # stubbed when absent so the registry's eager import works
 
 
+def _write_synthetic_rank_file(path, n_ranks):
+    """A tiktoken rank file of the real SIZE (the special-token ids depend on it) with made-up merges: 256 bytes, a chain that
+    turns " hello" / " world" into single tokens, then filler sequences of non-ASCII bytes."""
+    import base64
+
+    toks = [bytes([b]) for b in range(256)]
+    toks += [b"he", b"ll", b"hell", b"hello", b" hello", b"wo", b"rl", b"worl", b"world", b" world"]
+    a = 128
+    while len(toks) < n_ranks:
+        for b in range(128, 256):
+            for c in range(128, 256):
+                if len(toks) < n_ranks:
+                    toks.append(bytes([a, b, c]))
+        a += 1
+    with open(path, "w") as fh:
+        for rank, tok in enumerate(toks):
+            fh.write(f"{base64.b64encode(tok).decode()} {rank}\n")
+    return {tok: rank for rank, tok in enumerate(toks)}
+
+
+def test_text_rendering_and_initial_prompt_with_a_rank_file(fake_backend, tmp_path, monkeypatch):
+    """With B200_WHISPER_VOCAB_DIR the backend renders real text and honours `initial_prompt` (upstream transcribe.py: the
+    prompt is encoded with a leading space and fed as [sot_prev] + tokens in front of the sot sequence).  The real asset ships
+    with openai-whisper; a synthetic rank file of the real size stands in for it here."""
+    ranks = _write_synthetic_rank_file(tmp_path / "multilingual.tiktoken", 50257)
+    monkeypatch.setenv("B200_WHISPER_VOCAB_DIR", str(tmp_path))
+    v = vocab_for(51865)
+    d = Detokenizer(v)
+    assert d.has_text and d.encoding.n_vocab == 51865
+    hello, world = ranks[b" hello"], ranks[b" world"]
+    assert d.encode(" hello world") == [hello, world] and d.decode([hello, world, v.timestamp_begin + 7]) == " hello world"
+    # special tokens sit where the engine's token tables expect them
+    for name, tok in (("<|endoftext|>", v.eot), ("<|startoftranscript|>", v.sot), ("<|en|>", v.language_token("en")),
+                      ("<|transcribe|>", v.transcribe), ("<|startofprev|>", v.sot_prev), ("<|nospeech|>", v.no_speech),
+                      ("<|notimestamps|>", v.no_timestamps), ("<|0.00|>", v.timestamp_begin), ("<|30.00|>", v.timestamp_begin + 1500)):
+        assert d.encoding.encode(name, allowed_special="all") == [tok], name
+    tb = v.timestamp_begin
+    b, eng = fake_backend([res([tb, hello, world, tb + 100])])
+    segs, info = b.transcribe(synth_audio(6, 3.0), {"language": "en", "beam_size": 1, "initial_prompt": "hello"})
+    assert [(s.start, s.end, s.text) for s in segs] == [(0.0, 2.0, " hello world")]
+    assert eng.all_decodes[-1]["initial"] == [v.sot_prev, hello] + v.sot_sequence("en", None)
+    assert eng.all_decodes[-1]["initial"][eng.all_decodes[-1]["sot_index"]] == v.sot
+    raw = b.transcribe_raw(synth_audio(6, 3.0), language="en", initial_prompt="hello")
+    assert raw["text"] == " hello world" and raw["segments"][0]["compression_ratio"] == bk.compression_ratio("hello world")
+
+
 def test_detokenizer_placeholder():
     d = Detokenizer(vocab_for(51865))
     v = vocab_for(51865)
