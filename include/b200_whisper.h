@@ -100,6 +100,9 @@ typedef struct bw_decode_opts {
   float temperature;              /* 0 -> arg-max (fields below ignored) */
   int32_t best_of;
   uint32_t seed_lo, seed_hi;
+  /* BeamSearchDecoder.max_candidates = round(beam_size * patience) as the HOST rounds it (Python: half to even);
+   * 0 -> computed here with nearbyint (same rule under the default rounding mode). */
+  int32_t max_candidates;
 } bw_decode_opts;
 
 #define BW_MAX_TOKENS 448
@@ -130,8 +133,10 @@ int bw_engine_load_weights(bw_engine*, const bw_tensor_desc* tensors, int32_t n)
 int bw_engine_set_tables(bw_engine*, const bw_token_tables* tables);
 int bw_engine_set_mel_filters(bw_engine*, const float* filters /* [n_mels, 201] */);
 int bw_engine_finalize(bw_engine*);  /* packs weights, sizes the KV pools, starts the scheduler */
-int bw_engine_destroy(bw_engine*);
-int bw_engine_retain(bw_engine*);    /* refcount: one weight copy per (GPU, model, dtype) shared by pool handles */
+int bw_engine_destroy(bw_engine*);   /* drops one reference; the engine goes away with the last one */
+/* refcount: one weight copy per (GPU, model, dtype) shared by pool handles.  Every open bw_call holds a reference
+ * too, so destroying the engine while calls are open only defers the teardown to the last bw_call_close. */
+int bw_engine_retain(bw_engine*);
 int bw_engine_stats(bw_engine*, int64_t* out, int32_t n); /* see BW_STAT_* */
 
 enum {
@@ -158,6 +163,13 @@ int bw_resample_pcm16(bw_engine*, const int16_t* pcm, int64_t n_samples, int32_t
 int bw_call_content_frames(bw_call*, int32_t* out);
 /* Encoder + batched decoder for the 30 s window starting at mel frame `seek`. Blocking. */
 int bw_call_decode(bw_call*, int32_t seek, const bw_decode_opts* opts, bw_result* out);
+/* Explicit cross-session batch (what the reference declares as decode_batch_window_ms /
+ * max_decode_batch_size, config/server.yaml:48-49, and never implements): n windows -- calls[i] at seeks[i] with
+ * opts[i] -- are handed to the scheduler together by ONE host thread and share encoder launches and every decoder
+ * step.  Blocking until all are done; statuses[i] (may be NULL) gets each window's bw_status, the return value is the
+ * first non-zero one.  The same call may appear more than once (different seeks). */
+int bw_decode_many(bw_call* const* calls, const int32_t* seeks, const bw_decode_opts* opts, bw_result* results,
+                   int32_t* statuses, int32_t n);
 /* upstream decoding.detect_language on the window at `seek`. Blocking. */
 int bw_call_detect_language(bw_call*, int32_t seek, bw_lang_result* out);
 int bw_call_close(bw_call*);
@@ -170,41 +182,6 @@ int bw_encode(bw_engine*, const float* mel, int32_t batch, float* out);
 /* AudioEncoder + TextDecoder.forward (no cache) for one already-normalised mel window [n_mels, 3000]:
  * tokens [n] -> logits [n, V] f32.  Goes through the scheduler like any other request. */
 int bw_decode_logits(bw_engine*, const float* mel_window, const int32_t* tokens, int32_t n, float* out_logits);
-
-/* ---- kernel-level entry points (device pointers; used by tests/bench for roofline timing) ---- */
-/* C[M,N] = act(A[M,K] . B[N,K]^T + bias) (+ residual); bf16 in, fp32 accumulate. impl 0 = tcgen05, 1 = SIMT,
- * 2 = tcgen05 swap-AB (the decoder's skinny-GEMM path) */
-int bw_gemm_bf16(int impl, const void* A, const void* B, void* C, const float* bias, const float* residual,
-                 int32_t M, int32_t N, int32_t K, int32_t gelu, int32_t out_fp32, void* stream);
-/* Encoder self-attention on qkv [batch*T, 3*64*n_head] bf16 -> out [batch*T, 64*n_head] bf16. impl 0 = tcgen05, 1 = SIMT */
-int bw_attention_bf16(int impl, const void* qkv, void* out, int32_t batch, int32_t T_len, int32_t n_head, void* stream);
-/* Times `iters` launches of the decoder cross-attention kernel on synthetic resident data and returns
- * avg ms per launch (CUDA events on the launch stream); bytes_out = algorithmic bytes per launch. */
-int bw_bench_cross_attention(bw_engine*, int32_t n_segments, int32_t n_group, int32_t iters, float* ms_out, double* bytes_out);
-int bw_bench_encoder(bw_engine*, int32_t batch, int32_t iters, float* ms_out, double* flops_out);
-int bw_bench_mel(bw_engine*, int64_t n_samples, int32_t iters, float* ms_out, double* bytes_out);
-int bw_bench_decoder_step(bw_engine*, int32_t n_segments, int32_t n_group, int32_t context_len, int32_t iters,
-                          float* ms_out, double* bytes_out);
-
-/* Whole hot path on device-resident PCM (mel -> encoder -> cross-KV -> n_steps batched decoder steps), one
- * CUDA-event pair on the engine stream; returns total ms. */
-int bw_bench_pipeline(bw_engine*, const float* pcm_host, const int64_t* offsets, const int64_t* lengths,
-                      int32_t n_segments, int32_t n_group, int32_t n_steps, float* ms_out);
-
-/* Test hook for the decoder LayerNorm fusion (device pointers): producer row GEMM x = res + A.Wp^T + bp (also
- * emits bf16(x) and per-row LayerNorm partials) then consumer row GEMM out = [gelu](LayerNorm(x; gamma, beta).Wc^T + bc)
- * with gamma folded into Wc.  A == NULL skips the producer (x = res).  A bf16 [M, Kp], Wp bf16 [d, Kp], Wc fp32 [N, d];
- * x_out fp32 [M, d], out fp32 [M, N]; d % 64 == 0, N % 64 == 0. */
-int bw_test_ln_chain(const void* A, const void* Wp, const float* bp, const float* res, const float* gamma, const float* beta,
-                     const float* Wc, const float* bc, int32_t M, int32_t d, int32_t Kp, int32_t N, int32_t gelu, float* x_out,
-                     float* out, void* stream);
-
-/* Debug timeline of the decoder step: enable != 0 arms a device buffer that the step's kernels append
- * (tag, globaltimer ns) records to; enable == 0 disarms it and copies up to `cap` records (2 x uint64 each:
- * smid << 32 | kernel id << 24 | grid.x << 8 | phase, then the timestamp) to `out`, count in *n_out.
- * enable == 2 dumps the raw buffer instead (kernels that store into fixed slots).
- * Run with B200W_NO_GRAPH=1 (captured graphs keep the pointer they were captured with). */
-int bw_debug_trace(bw_engine*, int32_t enable, uint64_t* out, int32_t cap, int32_t* n_out);
 
 #ifdef __cplusplus
 }

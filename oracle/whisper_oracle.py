@@ -275,6 +275,9 @@ class DecodingResult:
     min_margin: float = float("inf")
 
 
+HAS_TEXT = False  # no tokenizer rank file in this image: text is a placeholder, see render_text
+
+
 def render_text(tokens: Sequence[int], eot: int) -> str:
     """Placeholder detokeniser (vocab assets absent): text tokens as `<id>`."""
     return "".join(f"<{t}>" for t in tokens if t < eot)
@@ -559,7 +562,9 @@ def transcribe(
                 audio_features = model.encode(segment[None].float())  # upstream re-encodes every rung: same numbers
             decode_result = decode_window(model, segment, opts, audio_features)
             needs_fallback = False
-            if compression_ratio_threshold is not None and decode_result.compression_ratio > compression_ratio_threshold:
+            # The repetitiveness check needs real text.  This restatement has no tokenizer assets and renders `<id>`
+            # placeholders (render_text), so -- like the product's placeholder mode -- it leaves the check out.
+            if HAS_TEXT and compression_ratio_threshold is not None and decode_result.compression_ratio > compression_ratio_threshold:
                 needs_fallback = True  # too repetitive
             if logprob_threshold is not None and decode_result.avg_logprob < logprob_threshold:
                 needs_fallback = True  # average log probability is too low

@@ -11,23 +11,33 @@ import pytest
 from b200_whisper import _lib as L
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HEADER = os.path.join(ROOT, "include", "b200_whisper.h")
+HEADERS = [os.path.join(ROOT, "include", "b200_whisper.h"), os.path.join(ROOT, "include", "b200_whisper_hooks.h")]
 
 
-def declared_symbols():
-    src = open(HEADER).read()
+def declared_symbols(header):
+    src = open(header).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(bw_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
     lib = L.load()
-    names = declared_symbols()
-    assert len(names) >= 25
-    for n in names:
-        assert hasattr(lib, n), f"{n} declared in include/b200_whisper.h but not exported"
+    boundary, hooks = declared_symbols(HEADERS[0]), declared_symbols(HEADERS[1])
+    assert len(boundary) >= 22 and len(hooks) >= 10
+    for n in boundary + hooks:
+        assert hasattr(lib, n), f"{n} declared in include/ but not exported"
         assert n in L.SIGNATURES, f"{n} has no ctypes signature in _lib.py"
+    # the drop-in boundary carries no bench / test / debug entry point
+    assert not [n for n in boundary if n.startswith(("bw_bench_", "bw_test_", "bw_debug_"))]
+    assert sorted(L.SIGNATURES) == sorted(set(boundary + hooks)), "ctypes signatures without a declaration in include/"
     assert lib.bw_version() >= 100
+
+
+def test_hooks_header_compiles_as_c(tmp_path):
+    prog = tmp_path / "hooks.c"
+    prog.write_text('#include "b200_whisper_hooks.h"\nint main(void){return 0;}\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(prog), "-o", str(tmp_path / "h.o")],
+                   check=True)
 
 
 def test_struct_layouts_match_c(tmp_path):

@@ -139,11 +139,12 @@ def test_transcribe_eot_and_multiwindow_fp32():
     _check_transcribe(b, "test-tiny", synth_audio(10, 7.0), dict(ACCURATE, language="en"), **kw)
 
 
-@pytest.mark.parametrize("beam,patience,length_penalty", [(8, 1.0, 1.0), (5, 2.0, None), (3, 1.6, 0.6), (2, 0.5, 1.0)])
+@pytest.mark.parametrize("beam,patience,length_penalty", [(8, 1.0, 1.0), (5, 2.0, None), (3, 1.6, 0.6), (2, 0.5, 1.0),
+                                                          (5, 0.5, 1.0), (3, 0.5, None), (5, 0.3, 1.0)])  # x.5 products: round-half-even
 def test_beam_patience_and_length_penalty_fp32(beam, patience, length_penalty):
     """BeamSearchDecoder corners outside the two server profiles: the widest beam, patience != 1 (finished pool of
-    round(beam * patience) candidates, larger or smaller than the beam), length normalisation instead of the GNMT
-    penalty.  EOT-biased weights so that hypotheses do finish and the pool / ranker paths are taken."""
+    round(beam * patience) candidates, larger or smaller than the beam -- Python's round(): 5 * 0.5 -> 2, 3 * 0.5 -> 2,
+    5 * 0.3 -> 2 (1.5 -> 2) -- ), length normalisation instead of the GNMT penalty.  EOT-biased weights so that hypotheses do finish and the pool / ranker paths are taken."""
     opts = dict(ACCURATE, language="en", beam_size=beam, best_of=beam, patience=patience)
     if length_penalty is None:
         opts.pop("length_penalty")

@@ -22,8 +22,8 @@ class FakeCall:
         self.content_frames = (len(audio) + 480000) // 160 - 3000
         self.decodes = []
 
-    def decode(self, seek, initial, sot_index, beam, patience, length_penalty, **kw):
-        self.decodes.append({"seek": seek, "initial": list(initial), "sot_index": sot_index, "beam": beam, **kw})
+    def decode(self, seek, initial, sot_index, beam_size, patience, length_penalty, **kw):
+        self.decodes.append({"seek": seek, "initial": list(initial), "sot_index": sot_index, "beam": beam_size, **kw})
         self.engine.all_decodes.append(self.decodes[-1])
         return dict(self.engine.script[min(len(self.engine.all_decodes) - 1, len(self.engine.script) - 1)])
 
@@ -50,6 +50,10 @@ class FakeEngine:
     def open_call(self, audio, sample_rate=None):
         self.last_sample_rate = sample_rate
         return FakeCall(self, audio)
+
+    def decode_many(self, items):
+        self.batches = getattr(self, "batches", []) + [len(items)]
+        return [call.decode(seek, **kw) for call, seek, kw in items]
 
 
 @pytest.fixture
@@ -178,7 +182,7 @@ def test_seek_loop_matches_oracle(fake_backend, case):
 
 @pytest.mark.parametrize("case", ["accept_first", "logprob_fallback", "repetitive_to_the_top", "silence_is_not_retried",
                                   "scalar_temperature", "multi_window_prompt_reset"])
-def test_temperature_fallback_ladder_matches_oracle(fake_backend, case):
+def test_temperature_fallback_ladder_matches_oracle(fake_backend, monkeypatch, case):
     """decode_with_fallback of upstream transcribe.py: which rungs run, with which decoder options, which result is kept,
     and the prompt reset after a high-temperature window -- backend vs the oracle's restatement on the same script."""
     v = vocab_for(51865)
@@ -200,6 +204,9 @@ def test_temperature_fallback_ladder_matches_oracle(fake_backend, case):
     seconds, temperature, script, want_rungs, want_temperature = cases[case]
     audio = synth_audio(3, seconds)
     b, eng = fake_backend(script)
+    # the repetitiveness check is off in placeholder-text mode (product and oracle alike); switch it on for this host-logic test
+    b.check_compression_ratio = True
+    monkeypatch.setattr(wo, "HAS_TEXT", True)
     opts = {"language": "en", "beam_size": 5, "best_of": 3, "patience": 1.0, "temperature": temperature}
     got = b.transcribe_raw(audio, _seed=77, **b._normalize_options(opts))
     want, prompts = _oracle_with_script(script, audio, language="en", beam_size=5, best_of=3, patience=1.0,
@@ -418,6 +425,58 @@ def test_text_rendering_and_initial_prompt_with_a_rank_file(fake_backend, tmp_pa
     assert raw["text"] == " hello world" and raw["segments"][0]["compression_ratio"] == bk.compression_ratio("hello world")
 
 
+def test_real_checkpoint_without_rank_file_is_refused(monkeypatch, tmp_path):
+    """a real checkpoint served with `<id>` placeholder text is a silent failure -- the backend must refuse to load
+    unless the model is random-init or the operator opts in; and the rank file is found under B200_WHISPER_VOCAB_DIR or in an
+    installed openai-whisper's assets."""
+    from b200_whisper.vocab import find_rank_file
+
+    monkeypatch.delenv("B200_WHISPER_VOCAB_DIR", raising=False)
+    monkeypatch.delenv("B200_WHISPER_ALLOW_PLACEHOLDER_TEXT", raising=False)
+    assert find_rank_file("multilingual") is None
+    with pytest.raises(RuntimeError, match="tiktoken"):
+        Detokenizer(vocab_for(51865), allow_placeholders=False)
+    eng = FakeEngine()
+    monkeypatch.setattr(bk, "get_engine", lambda *a, **k: eng)
+    with pytest.raises(RuntimeError, match="placeholder"):
+        B200WhisperBackend("/models/large-v3.pt", "cuda:0", "bfloat16")
+    monkeypatch.setenv("B200_WHISPER_ALLOW_PLACEHOLDER_TEXT", "1")
+    assert not B200WhisperBackend("/models/large-v3.pt", "cuda:0", "bfloat16").detok.has_text
+    # auto-location: a package called `whisper` with assets/<name>.tiktoken on the import path
+    pkg = tmp_path / "whisper"
+    (pkg / "assets").mkdir(parents=True)
+    (pkg / "__init__.py").write_text("")
+    (pkg / "assets" / "gpt2.tiktoken").write_text("")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    import importlib
+
+    importlib.invalidate_caches()
+    assert find_rank_file("gpt2") == str(pkg / "assets" / "gpt2.tiktoken")
+
+
+def test_placeholder_mode_skips_the_repetitiveness_check(fake_backend):
+    v = vocab_for(51865)
+    tb = v.timestamp_begin
+    rep = res([tb] + [11] * 80 + [tb + 400], avg=-0.3)
+    b, eng = fake_backend([rep])
+    assert not b.detok.has_text and not b.check_compression_ratio
+    got = b.transcribe_raw(synth_audio(3, 10.0), language="en", beam_size=5, temperature=(0.0, 0.4, 0.8))
+    assert len(eng.all_decodes) == 1 and got["segments"][0]["temperature"] == 0.0
+
+
+def test_compute_type_remap_is_logged(fake_backend, caplog):
+    import logging
+
+    bk._REMAP_WARNED.clear()
+    with caplog.at_level(logging.WARNING, logger="stt_server.model_backend"):
+        b, _ = fake_backend([res([])])
+        assert B200WhisperBackend("random:test-tiny", "cuda:0", "int8").compute == "bf16"
+        assert B200WhisperBackend("random:test-tiny", "cuda:0", "float16").compute == "bf16"
+        assert B200WhisperBackend("random:test-tiny", "cuda:0", "float32").compute == "fp32"
+    msgs = [r.getMessage() for r in caplog.records]
+    assert any("compute_type=int8 runs as bfloat16" in m for m in msgs) and any("compute_type=float16" in m for m in msgs)
+
+
 def test_detokenizer_placeholder():
     d = Detokenizer(vocab_for(51865))
     v = vocab_for(51865)
@@ -441,8 +500,14 @@ def test_side_doors_route_through_the_same_seek_loop(fake_backend):
     audios = [np.zeros(16000 * (i + 1), np.float32) for i in range(3)]
     out = b.transcribe_many(audios + [pcm], {"language": "en"}, [None, None, None, 48000])
     assert len(out) == 4 and all(len(s) == 1 for s, _ in out)
+    assert eng.batches == [4], "one bw_decode_many for the whole batch (one window each), not a thread per item"
     out2 = b.transcribe_many(audios, [{"language": "en"}, {"language": "de"}, {"language": "en"}])
     assert [i.language for _, i in out2] == ["en", "de", "en"]
+    # items with several windows stay in lockstep: round k carries the k-th window of every item that still has one
+    eng.batches = []
+    long_audios = [np.zeros(16000 * 70, np.float32), np.zeros(16000 * 5, np.float32), np.zeros(16000 * 40, np.float32)]
+    b.transcribe_many(long_audios, {"language": "en"})
+    assert eng.batches == [3, 2, 1]
     with pytest.raises(ValueError):
         b.transcribe_many(audios, {"language": "en", "beam_size": 99})  # every call fails on the option check
     with pytest.raises(ValueError):

@@ -50,7 +50,7 @@ class DecodeOptsC(C.Structure):
                 ("beam_size", C.c_int32), ("patience", C.c_float), ("length_penalty", C.c_float),
                 ("sample_len", C.c_int32), ("without_timestamps", C.c_int32), ("suppress_blank", C.c_int32),
                 ("max_initial_timestamp_index", C.c_int32), ("temperature", C.c_float), ("best_of", C.c_int32),
-                ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32)]
+                ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("max_candidates", C.c_int32)]
 
 
 class ResultC(C.Structure):
@@ -63,7 +63,8 @@ class LangResultC(C.Structure):
     _fields_ = [("language_token", C.c_int32), ("n_languages", C.c_int32), ("probs", C.c_float * 128)]
 
 
-# name -> (restype, argtypes); every symbol include/b200_whisper.h declares
+# name -> (restype, argtypes); every symbol include/b200_whisper.h (the drop-in boundary) and
+# include/b200_whisper_hooks.h (bench / test hooks) declare
 SIGNATURES = {
     "bw_last_error": (C.c_char_p, []),
     "bw_version": (C.c_int, []),
@@ -82,6 +83,7 @@ SIGNATURES = {
     "bw_resample_pcm16": (C.c_int, [C.c_void_p, C.POINTER(C.c_int16), C.c_int64, C.c_int32, c_f32_p, C.POINTER(C.c_int64)]),
     "bw_call_content_frames": (C.c_int, [C.c_void_p, c_i32_p]),
     "bw_call_decode": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(DecodeOptsC), C.POINTER(ResultC)]),
+    "bw_decode_many": (C.c_int, [C.POINTER(C.c_void_p), c_i32_p, C.POINTER(DecodeOptsC), C.POINTER(ResultC), c_i32_p, C.c_int32]),
     "bw_call_detect_language": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(LangResultC)]),
     "bw_call_close": (C.c_int, [C.c_void_p]),
     "bw_mel": (C.c_int, [C.c_void_p, c_f32_p, C.c_int64, C.c_int32, c_f32_p, c_i32_p]),
@@ -99,6 +101,11 @@ SIGNATURES = {
                                         C.POINTER(C.c_double)]),
     "bw_test_ln_chain": (C.c_int, [C.c_void_p] * 8 + [C.c_int32] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bw_debug_trace": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64), C.c_int32, c_i32_p]),
+    "bw_call_decode_forced": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(DecodeOptsC), c_i32_p, C.c_int32, c_f32_p, C.POINTER(ResultC)]),
+    "bw_test_dec_cross_attention": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]),
+    "bw_test_dec_self_attention": (C.c_int, [C.c_int32] + [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p] +
+                                   [C.c_int32] * 3 + [C.c_void_p, C.c_void_p]),
+    "bw_test_sample_topk": (C.c_int, [C.c_void_p, c_f32_p, C.c_int32, c_i32_p, c_i32_p, c_f32_p]),
 }
 
 _lib = None

@@ -57,7 +57,11 @@ N_FRAMES = 3000
 HOP_LENGTH = 160
 SAMPLE_RATE = 16000
 FP32_ALIASES = {"float32", "fp32"}
-BF16_ALIASES = {"bfloat16", "bf16", "float16", "fp16", "half", "int8", "int8_float16", "int8_bfloat16", "default", "auto"}
+BF16_ALIASES = {"bfloat16", "bf16", "default", "auto"}
+# compute types the reference's backends give another meaning to (torch_whisper.py:36-47: fp16 aliases -> .half(), int8* ->
+# float32; faster_whisper: CTranslate2 quantisation).  This engine has exactly two modes, so they run as bfloat16 -- loudly.
+REMAPPED_TO_BF16 = {"float16", "fp16", "half", "int8", "int8_float16", "int8_bfloat16", "int8_float32"}
+_REMAP_WARNED: set = set()
 
 SUPPORTED_OPTIONS = {  # torch_whisper.py:79-97
     "temperature", "compression_ratio_threshold", "logprob_threshold", "no_speech_threshold",
@@ -132,7 +136,9 @@ def load_checkpoint(model_size: str) -> Tuple[ModelDims, Dict[str, Any], str]:
         if os.path.isfile(path):
             import torch
 
-            ckpt = torch.load(path, map_location="cpu", weights_only=False)
+            # {"dims": dict, "model_state_dict": tensors}: nothing that needs unpickling arbitrary objects (upstream
+            # whisper.load_model passes weights_only=True as well)
+            ckpt = torch.load(path, map_location="cpu", weights_only=True)
             dims = ModelDims(**{k: int(v) for k, v in ckpt["dims"].items()})
             return dims, ckpt["model_state_dict"], os.path.abspath(path)
     raise RuntimeError(
@@ -169,14 +175,24 @@ class B200WhisperBackend:
         if ct in FP32_ALIASES:
             self.compute = "fp32"
         else:
-            if ct not in BF16_ALIASES:
+            if ct in REMAPPED_TO_BF16:
+                if ct not in _REMAP_WARNED:
+                    _REMAP_WARNED.add(ct)
+                    LOGGER.warning("b200_whisper: compute_type=%s runs as bfloat16 (bf16 storage, fp32 accumulate); the engine has "
+                                   "no fp16 / int8 mode -- pass float32 for the validation mode", compute_type)
+            elif ct not in BF16_ALIASES:
                 LOGGER.warning("Unsupported compute_type=%s for b200_whisper; using bfloat16", compute_type)
             self.compute = "bf16"
         self._instance = next(_INSTANCE_COUNTER)
         self.device_index = parse_device(device, self._instance)
         self.engine = get_engine(model_size, self.device_index, self.compute, **engine_kwargs)
         self.vocab: Vocab = self.engine.vocab
-        self.detok = Detokenizer(self.vocab)
+        # A real checkpoint without its tokenizer rank file would hand `<id>` placeholders to clients: refuse to load.
+        # Random-init models (tests / bench) and an explicit opt-in keep the placeholder renderer.
+        allow_placeholders = model_size.startswith("random:") or os.environ.get("B200_WHISPER_ALLOW_PLACEHOLDER_TEXT", "0") == "1"
+        self.detok = Detokenizer(self.vocab, allow_placeholders=allow_placeholders)
+        # decode_with_fallback's repetitiveness check (compression ratio of the TEXT) is meaningless on `<id>` placeholders
+        self.check_compression_ratio = self.detok.has_text
         self.honor_without_timestamps = os.environ.get("B200_WHISPER_HONOR_WITHOUT_TIMESTAMPS", "0") == "1"
         self.report_language_probability = os.environ.get("B200_WHISPER_REPORT_LANGUAGE_PROB", "0") == "1"
         self.last_language_probability: Optional[float] = None
@@ -233,22 +249,40 @@ class B200WhisperBackend:
             raise ValueError("options / sample_rates must match audios in length")
         results: List[Any] = [None] * n
         errors: List[Optional[BaseException]] = [None] * n
+        gens: List[Any] = [None] * n
+        pending: Dict[int, tuple] = {}
 
-        def work(i: int) -> None:
+        def advance(i: int, step) -> None:
+            """run item i's seek loop up to its next window; `step` starts / resumes the generator"""
             try:
-                if rates[i] is None:
-                    results[i] = self.transcribe(audios[i], opt_list[i])
-                else:
-                    results[i] = self.transcribe_pcm16(audios[i], rates[i], opt_list[i])
-            except BaseException as exc:  # noqa: BLE001 - re-raised below
+                pending[i] = step()
+            except StopIteration as stop:
+                pending.pop(i, None)
+                results[i] = self._to_segments(stop.value)
+            except Exception as exc:  # noqa: BLE001 - re-raised below, after every item has finished
+                pending.pop(i, None)
                 errors[i] = exc
 
-        # blocking C calls release the GIL; the engine's scheduler coalesces whatever is pending into one batch
-        threads = [threading.Thread(target=work, args=(i,), name=f"b200w-many-{i}") for i in range(n)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
+        for i in range(n):
+            def start(i=i):
+                opts = self._normalize_options(opt_list[i])
+                if rates[i] is not None:
+                    if int(rates[i]) != rates[i] or int(rates[i]) <= 0:
+                        raise ValueError(f"sample_rate must be a positive integer, got {rates[i]!r}")
+                    opts["_sample_rate"] = int(rates[i])
+                gens[i] = self._transcribe_steps(audios[i], **opts)
+                return next(gens[i])
+            advance(i, start)
+        # One host thread: every round hands the next window of every unfinished item to the engine in ONE blocking
+        # bw_decode_many, so the windows share encoder launches and every decoder step (no thread per item).
+        while pending:
+            idx = sorted(pending)
+            outs = self.engine.decode_many([pending[i] for i in idx])
+            for i, out in zip(idx, outs):
+                if isinstance(out, BaseException):
+                    advance(i, lambda i=i, out=out: gens[i].throw(out))
+                else:
+                    advance(i, lambda i=i, out=out: gens[i].send(out))
         for exc in errors:
             if exc is not None:
                 raise exc
@@ -278,13 +312,24 @@ class B200WhisperBackend:
             prob = float(self.last_language_probability)
         return segments, BackendInfo(language, prob)
 
-    # ---- upstream whisper/transcribe.py seek loop over the engine ----
-    def transcribe_raw(self, audio: Any, *, temperature: Any = 0.0, compression_ratio_threshold: Optional[float] = 2.4,
+    def transcribe_raw(self, audio: Any, **opts) -> dict:
+        """upstream whisper.transcribe() over the engine: one blocking bw_call_decode per window"""
+        gen = self._transcribe_steps(audio, **opts)
+        try:
+            call, seek, kw = next(gen)
+            while True:
+                call, seek, kw = gen.send(call.decode(seek, **kw))
+        except StopIteration as stop:
+            return stop.value
+
+    # ---- upstream whisper/transcribe.py seek loop; a generator that yields one (call, seek, decode arguments) per window
+    # and is sent the window's result, so that one thread can drive many calls in lockstep (transcribe_many) ----
+    def _transcribe_steps(self, audio: Any, *, temperature: Any = 0.0, compression_ratio_threshold: Optional[float] = 2.4,
                        logprob_threshold: Optional[float] = -1.0, no_speech_threshold: Optional[float] = 0.6,
                        condition_on_previous_text: bool = True, initial_prompt: Optional[str] = None,
                        language: Optional[str] = None, task: Optional[str] = None, beam_size: Optional[int] = None,
                        best_of: Optional[int] = None, patience: Optional[float] = None,
-                       length_penalty: Optional[float] = None, sample_len: Optional[int] = None, **ignored) -> dict:
+                          length_penalty: Optional[float] = None, sample_len: Optional[int] = None, **ignored):
         v = self.vocab
         sample_rate = ignored.pop("_sample_rate", None)  # not None: `audio` is PCM16 at that rate (transcribe_pcm16)
         if sample_rate is None:
@@ -332,8 +377,8 @@ class B200WhisperBackend:
             all_tokens: List[int] = []
             if initial_prompt is not None:
                 enc = self.detok.encode(" " + initial_prompt.strip())
-                if enc is None:
-                    LOGGER.warning("b200_whisper: initial_prompt dropped (no tokenizer rank file)")
+                if enc is None:  # placeholder mode only (random-init models / explicit opt-in): there is no text codec
+                    LOGGER.warning("b200_whisper: initial_prompt dropped (placeholder text mode, no tokenizer rank file)")
                 else:
                     all_tokens.extend(enc)
             n_initial_prompt = len(all_tokens)
@@ -355,18 +400,18 @@ class B200WhisperBackend:
                 # decode_with_fallback (upstream transcribe.py): walk the temperature ladder until a rung passes the
                 # compression-ratio / log-probability checks; beam search at T = 0, best_of samples above it
                 for attempt, t in enumerate(temperatures):
+                    kw = dict(initial=initial, sot_index=initial.index(v.sot), beam_size=beam, patience=patience,
+                              length_penalty=length_penalty, sample_len=int(sample_len or 0), without_timestamps=without_ts)
                     if t > 0:
-                        res = call.decode(seek, initial, initial.index(v.sot), None, None, length_penalty,
-                                          sample_len=int(sample_len or 0), without_timestamps=without_ts, temperature=t,
-                                          best_of=n_best, seed=window_seed(call_seed, seek, attempt))
-                    else:
-                        res = call.decode(seek, initial, initial.index(v.sot), beam, patience, length_penalty,
-                                          sample_len=int(sample_len or 0), without_timestamps=without_ts)
+                        kw.update(beam_size=None, patience=None, temperature=t, best_of=n_best, seed=window_seed(call_seed, seek, attempt))
+                    res = dict((yield call, seek, kw))
                     res["temperature"] = t
                     text_all = self.detok.decode([tk for tk in res["tokens"] if tk < v.eot]).strip()
                     res["compression_ratio"] = compression_ratio(text_all)
                     needs_fallback = False
-                    if compression_ratio_threshold is not None and res["compression_ratio"] > compression_ratio_threshold:
+                    # (placeholder renderer: `<id>` strings say nothing about repetitiveness -- the check needs real text)
+                    if (compression_ratio_threshold is not None and self.check_compression_ratio
+                            and res["compression_ratio"] > compression_ratio_threshold):
                         needs_fallback = True  # too repetitive
                     if logprob_threshold is not None and res["avg_logprob"] < logprob_threshold:
                         needs_fallback = True  # average log probability is too low

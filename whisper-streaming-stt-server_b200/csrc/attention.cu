@@ -520,7 +520,7 @@ void launch_cross(const int* gfr, const int* gnr, const int* gx, int n_groups, c
 template <typename T>
 void dec_cross_attention(const int* group_first_row, const int* group_n_rows, const int* group_xslot, int n_groups,
                          int max_group_rows, int n_rows, const float* q, const CrossKV& kv, int layer, int d, int n_head, T* out,
-                         float* workspace, cudaStream_t stream) {
+                         float* workspace, cudaStream_t stream, int force_split) {
   if (n_groups <= 0) return;
   BW_CHECK(max_group_rows <= 8, "at most 8 hypotheses per segment");
   BW_CHECK(kv.T_enc <= 1504, "n_audio_ctx > 1504 unsupported");
@@ -528,6 +528,7 @@ void dec_cross_attention(const int* group_first_row, const int* group_n_rows, co
   int n_split = 1;
   const long long base = (long long)n_head * n_groups;
   while (n_split < kMaxSplit && base * n_split < 4 * 148) n_split *= 2;
+  if (force_split > 0) n_split = std::min(force_split, (int)kMaxSplit);  // tests: any split count, not just powers of two
   if constexpr (std::is_same<T, bf16>::value) {
     static const bool simt = getenv("B200W_XATTN_SIMT") != nullptr;
     if (!simt && kv.n_slots > 0) {
@@ -552,7 +553,7 @@ void dec_cross_attention(const int* group_first_row, const int* group_n_rows, co
     ++g_kernel_launches;
   }
 }
-template void dec_cross_attention<float>(const int*, const int*, const int*, int, int, int, const float*, const CrossKV&, int, int, int, float*, float*, cudaStream_t);
-template void dec_cross_attention<bf16>(const int*, const int*, const int*, int, int, int, const float*, const CrossKV&, int, int, int, bf16*, float*, cudaStream_t);
+template void dec_cross_attention<float>(const int*, const int*, const int*, int, int, int, const float*, const CrossKV&, int, int, int, float*, float*, cudaStream_t, int);
+template void dec_cross_attention<bf16>(const int*, const int*, const int*, int, int, int, const float*, const CrossKV&, int, int, int, bf16*, float*, cudaStream_t, int);
 
 }  // namespace bw

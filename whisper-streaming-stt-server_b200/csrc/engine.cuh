@@ -89,14 +89,17 @@ struct StepGraphKeyHash {
 };
 struct StepGraph {
   int seen = 0;
+  unsigned long long last_use = 0;
   cudaGraphExec_t exec = nullptr;
 };
+constexpr size_t kMaxStepGraphs = 128;  // per group; least recently used half is dropped beyond this
 
 struct DecGroup {
   cudaStream_t stream = nullptr;
   // CUDA graphs of the whole decoder step, keyed by its shape: while the set of live requests is unchanged only the
   // control block's CONTENTS change from step to step, so ~360 launches collapse into one cudaGraphLaunch.
   std::unordered_map<StepGraphKey, StepGraph, StepGraphKeyHash> graphs;
+  unsigned long long graph_clock = 0;
   DevBuf d_x, d_xn, d_qkv, d_att, d_q, d_h, d_lnrows, d_logits, d_ws, d_cand_tok, d_cand_lp, d_ctrl;
   DevBuf d_xb, d_lnst;  // LayerNorm fusion: bf16 copy of the residual stream, per-row / per-64-column partials
   int* h_ctrl = nullptr;  // pinned host copy of the control block
@@ -140,6 +143,11 @@ struct Request {
   float patience = 1.f, length_penalty = -1.f;
   float temperature = 0.f;          // > 0: GreedyDecoder sampling with G = best_of hypotheses
   unsigned long long seed = 0;
+  int max_candidates = 1;           // BeamSearchDecoder: round(beam_size * patience), computed by the caller's rounding rule
+  // test hook (bw_call_decode_forced): teacher forcing -- step k feeds forced[k] whatever was sampled, and the
+  // step's raw logits row goes to step_logits_out + k * V
+  std::vector<int> forced;
+  float* step_logits_out = nullptr;
   // outputs
   bw_result* out = nullptr;
   bw_lang_result* lang_out = nullptr;

@@ -109,7 +109,7 @@ struct CrossKV {
 template <typename T>
 void dec_cross_attention(const int* group_first_row, const int* group_n_rows, const int* group_xslot, int n_groups,
                          int max_group_rows, int n_rows, const float* q, const CrossKV& kv, int layer, int d, int n_head, T* out,
-                         float* workspace, cudaStream_t stream);
+                         float* workspace, cudaStream_t stream, int force_split = 0);
 size_t dec_cross_workspace_floats(int n_rows, int n_head);
 
 // ---- sampling.cu ----
@@ -164,8 +164,10 @@ void sample_topk(const float* logits, int ld, int V, const int* srow_lrow, const
                  const TokenTables& tt, const ReqState& rs, const SeqState& ss, int anc_cur, int* cand_tok, float* cand_lp,
                  cudaStream_t stream);
 // Beam bookkeeping (BeamSearchDecoder.update / GreedyDecoder.update) for each active request.
-void beam_update(const int* active_req, const int* req_first_lrow, int n_active, const TokenTables& tt, const ReqState& rs,
-                 const SeqState& ss, int anc_cur, int n_ctx, const int* cand_tok, const float* cand_lp, cudaStream_t stream);
+// active_force[i] >= 0 (greedy requests only): the token to feed next instead of the sampled one (teacher forcing).
+void beam_update(const int* active_req, const int* req_first_lrow, const int* active_force, int n_active, const TokenTables& tt,
+                 const ReqState& rs, const SeqState& ss, int anc_cur, int n_ctx, const int* cand_tok, const float* cand_lp,
+                 cudaStream_t stream);
 // probs_at_sot.softmax()[no_speech] for requests in their first step
 void no_speech_prob(const float* logits, int ld, int V, const int* lrows, const int* reqs, int n, int no_speech_id,
                     float* out_prob, cudaStream_t stream);

@@ -251,7 +251,8 @@ sample_topk_kernel(const float* __restrict__ logits, int ld, int V, const int* _
 }
 
 __global__ void __launch_bounds__(32)
-beam_update_kernel(const int* __restrict__ active_req, const int* __restrict__ req_first_lrow, const TokenTables tt,
+beam_update_kernel(const int* __restrict__ active_req, const int* __restrict__ req_first_lrow,
+                   const int* __restrict__ active_force, const TokenTables tt,
                    const ReqState rs, const SeqState ss, int anc_cur, int n_ctx, const int* __restrict__ cand_tok,
                    const float* __restrict__ cand_lp) {
   pdl_trigger();
@@ -287,7 +288,8 @@ beam_update_kernel(const int* __restrict__ active_req, const int* __restrict__ r
       bool all_eot = true;
       for (int j = 0; j < G; ++j) {
         const int c = first ? lr0 * kMaxCand + j : (lr0 + j) * kMaxCand;
-        const int tok = cand_tok[c];
+        const int force = active_force ? active_force[blockIdx.x] : -1;
+        const int tok = force >= 0 ? force : cand_tok[c];
         const float lp = cand_lp[c];
         const int last = old_next[j];
         nsum[j] = old_sum[j] + ((last != tt.eot) ? lp : 0.f);
@@ -416,10 +418,12 @@ void sample_topk(const float* logits, int ld, int V, const int* srow_lrow, const
   ++g_kernel_launches;
 }
 
-void beam_update(const int* active_req, const int* req_first_lrow, int n_active, const TokenTables& tt, const ReqState& rs,
-                 const SeqState& ss, int anc_cur, int n_ctx, const int* cand_tok, const float* cand_lp, cudaStream_t stream) {
+void beam_update(const int* active_req, const int* req_first_lrow, const int* active_force, int n_active, const TokenTables& tt,
+                 const ReqState& rs, const SeqState& ss, int anc_cur, int n_ctx, const int* cand_tok, const float* cand_lp,
+                 cudaStream_t stream) {
   if (n_active <= 0) return;
-  launch_kernel(beam_update_kernel, dim3(n_active), dim3(32), 0, stream, active_req, req_first_lrow, tt, rs, ss, anc_cur, n_ctx, cand_tok, cand_lp);
+  launch_kernel(beam_update_kernel, dim3(n_active), dim3(32), 0, stream, active_req, req_first_lrow, active_force, tt, rs, ss, anc_cur,
+                n_ctx, cand_tok, cand_lp);
   ++g_kernel_launches;
 }
 

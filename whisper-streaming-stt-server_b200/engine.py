@@ -31,6 +31,29 @@ def _as_i16(pcm) -> np.ndarray:
     return np.ascontiguousarray(a.reshape(-1))
 
 
+def decode_opts(initial: Sequence[int], sot_index: int, beam_size: Optional[int], patience: Optional[float],
+                length_penalty: Optional[float], sample_len: int = 0, without_timestamps: bool = False,
+                suppress_blank: bool = True, max_initial_timestamp_index: Optional[int] = 50, temperature: float = 0.0,
+                best_of: Optional[int] = None, seed: int = 0):
+    """bw_decode_opts for one window; returns (struct, objects that must outlive it)."""
+    init = (C.c_int32 * len(initial))(*initial)
+    beam = int(beam_size or 0)
+    # BeamSearchDecoder.max_candidates = round(beam_size * patience) with Python's own round() (half to even), as upstream
+    max_cand = max(1, round(beam * float(patience or 1.0))) if beam else 0
+    o = L.DecodeOptsC(init, len(initial), sot_index, beam, float(patience or 0.0),
+                      -1.0 if length_penalty is None else float(length_penalty), int(sample_len),
+                      int(bool(without_timestamps)), int(bool(suppress_blank)),
+                      -1 if max_initial_timestamp_index is None else int(max_initial_timestamp_index),
+                      float(temperature), int(best_of or 0), int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF, max_cand)
+    return o, init
+
+
+def result_dict(r: "L.ResultC") -> dict:
+    return {"tokens": list(r.tokens[: r.n_tokens]), "sum_logprob": r.sum_logprob, "avg_logprob": r.avg_logprob,
+            "no_speech_prob": r.no_speech_prob, "n_steps": r.n_steps, "t_queue": r.t_queue, "t_encode": r.t_encode,
+            "t_decode": r.t_decode}
+
+
 class Call:
     """One `transcribe()` call: PCM resident on the device + its whole-call log-mel."""
 
@@ -58,17 +81,24 @@ class Call:
                best_of: Optional[int] = None, seed: int = 0) -> dict:
         """One 30 s window.  temperature > 0: GreedyDecoder sampling with `best_of` hypotheses (beam_size must be
         None, as upstream's decode_with_fallback guarantees), reproducible for a given 64-bit `seed`."""
-        init = (C.c_int32 * len(initial))(*initial)
-        o = L.DecodeOptsC(init, len(initial), sot_index, int(beam_size or 0), float(patience or 0.0),
-                          -1.0 if length_penalty is None else float(length_penalty), int(sample_len),
-                          int(bool(without_timestamps)), int(bool(suppress_blank)),
-                          -1 if max_initial_timestamp_index is None else int(max_initial_timestamp_index),
-                          float(temperature), int(best_of or 0), int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF)
+        o, _keep = decode_opts(initial, sot_index, beam_size, patience, length_penalty, sample_len, without_timestamps,
+                               suppress_blank, max_initial_timestamp_index, temperature, best_of, seed)
         r = L.ResultC()
         L.check(self.engine.lib.bw_call_decode(self._h, int(seek), C.byref(o), C.byref(r)), "bw_call_decode")
-        return {"tokens": list(r.tokens[: r.n_tokens]), "sum_logprob": r.sum_logprob, "avg_logprob": r.avg_logprob,
-                "no_speech_prob": r.no_speech_prob, "n_steps": r.n_steps, "t_queue": r.t_queue, "t_encode": r.t_encode,
-                "t_decode": r.t_decode}
+        return result_dict(r)
+
+    def decode_forced(self, seek: int, initial: Sequence[int], sot_index: int, forced: Sequence[int], want_logits: bool = True,
+                      without_timestamps: bool = False):
+        """Test hook (bw_call_decode_forced): teacher-forced greedy decode through the scheduler; returns
+        (result dict, logits [len(forced), V] or None) -- logits[k] is the row step k sampled from."""
+        o, _keep = decode_opts(initial, sot_index, None, None, None, 0, without_timestamps, True, 50, 0.0, None, 0)
+        f = (C.c_int32 * len(forced))(*forced)
+        logits = np.empty((len(forced), self.engine.dims.n_vocab), dtype=np.float32) if want_logits else None
+        r = L.ResultC()
+        L.check(self.engine.lib.bw_call_decode_forced(self._h, int(seek), C.byref(o), f, len(forced),
+                                                      logits.ctypes.data_as(L.c_f32_p) if want_logits else None, C.byref(r)),
+                "bw_call_decode_forced")
+        return result_dict(r), logits
 
     def detect_language(self, seek: int = 0):
         r = L.LangResultC()
@@ -187,6 +217,35 @@ class Engine:
 
     def open_call(self, audio, sample_rate: Optional[int] = None) -> Call:
         return Call(self, audio, sample_rate)
+
+    def decode_many(self, items: Sequence[tuple]) -> list:
+        """One blocking bw_decode_many for a batch of windows.  items[i] = (call, seek, kwargs of decode_opts); returns a
+        list of result dicts, or the B200WhisperError of the window that failed, in input order."""
+        n = len(items)
+        if n == 0:
+            return []
+        calls = (C.c_void_p * n)(*[it[0]._h for it in items])
+        seeks = (C.c_int32 * n)(*[int(it[1]) for it in items])
+        opts = (L.DecodeOptsC * n)()
+        keep = []
+        for i, it in enumerate(items):
+            o, k = decode_opts(**it[2])
+            opts[i] = o
+            keep.append(k)
+        results = (L.ResultC * n)()
+        statuses = (C.c_int32 * n)()
+        st = self.lib.bw_decode_many(calls, seeks, opts, results, statuses, n)
+        if st != 0 and all(s == 0 for s in statuses):
+            L.check(st, "bw_decode_many")
+        out = []
+        for i in range(n):
+            if statuses[i] != 0:
+                msg = self.lib.bw_last_error()
+                out.append(L.B200WhisperError(f"bw_decode_many window {i} failed (bw_status {statuses[i]}): "
+                                              f"{msg.decode('utf-8', 'replace') if msg else ''}"))
+            else:
+                out.append(result_dict(results[i]))
+        return out
 
     def stats(self) -> Dict[str, int]:
         buf = (C.c_int64 * len(L.STAT_NAMES))()

@@ -129,16 +129,42 @@ def normalize_language(language: Optional[str]) -> Optional[str]:
 _WARNED: set = set()
 
 
-class Detokenizer:
-    """tiktoken-backed text codec when the rank file is available, `<id>` placeholders otherwise."""
+def find_rank_file(name: str) -> Optional[str]:
+    """`<name>.tiktoken`: under $B200_WHISPER_VOCAB_DIR, else in the assets of an installed openai-whisper (the package
+    the reference's torch_whisper backend imports; located without importing it)."""
+    roots = []
+    if os.environ.get("B200_WHISPER_VOCAB_DIR"):
+        roots.append(os.environ["B200_WHISPER_VOCAB_DIR"])
+    try:
+        import importlib.util
 
-    def __init__(self, vocab: Vocab):
+        spec = importlib.util.find_spec("whisper")
+        if spec is not None and spec.submodule_search_locations:
+            roots.extend(os.path.join(loc, "assets") for loc in spec.submodule_search_locations)
+    except (ImportError, ValueError):
+        pass
+    for root in roots:
+        path = os.path.join(root, f"{name}.tiktoken")
+        if os.path.isfile(path):
+            return path
+    return None
+
+
+class Detokenizer:
+    """tiktoken-backed text codec.  Without the rank file: `<id>` placeholders if `allow_placeholders` (random-init models,
+    tests, bench), else a RuntimeError -- a real checkpoint must never hand placeholder strings to clients."""
+
+    def __init__(self, vocab: Vocab, allow_placeholders: bool = True):
         self.vocab = vocab
         self.encoding = None
-        vdir = os.environ.get("B200_WHISPER_VOCAB_DIR")
         name = "multilingual" if vocab.multilingual else "gpt2"
-        path = os.path.join(vdir, f"{name}.tiktoken") if vdir else None
-        if path and os.path.exists(path):
+        path = find_rank_file(name)
+        if path is None and not allow_placeholders:
+            raise RuntimeError(
+                f"b200_whisper: tokenizer rank file {name}.tiktoken not found (set B200_WHISPER_VOCAB_DIR to the directory that "
+                "holds it -- it ships in openai-whisper's whisper/assets/ -- or install openai-whisper next to this backend). "
+                "Refusing to serve a real checkpoint with placeholder text; B200_WHISPER_ALLOW_PLACEHOLDER_TEXT=1 overrides.")
+        if path:
             import tiktoken
 
             with open(path) as fh:
