@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- RTFx (audio-seconds transcribed per wall-second) of the Whisper hot path on B200.
 
-Workload (BASELINE.json configs[4], the per-GPU shard of the config the metric is quoted on):
+Default workload (BASELINE.json configs[4], the per-GPU shard of the config the metric is quoted on):
 large-v3 (128 mel bins), realtime decode profile (beam_size=1), 128 concurrent streaming sessions
 per GPU, each submitting one partial-decode window of its last 2-10 s of audio per step (seeded
 lengths; every window is a full 30 s encoder pass, as in the reference).  Random-init weights of the
 named architecture and synthetic audio (no network) -> hypotheses never reach EOT and every window
 runs the full 224 decoder steps: the worst case.  One "step" = one such batch of 128 windows.
+`--config N` selects another BASELINE.json configs[N] (table CONFIGS below): the same line, per config.
 
   value : whole-job RTFx with the PCM already resident in HBM, timed with CUDA events on the engine
           stream around mel -> encoder -> cross-KV -> 224 batched decoder steps (max over ranks)
@@ -38,9 +39,28 @@ if ROOT not in sys.path:
 ENC_BATCH = 16  # windows admitted per encoder pass (8 is 5 % more efficient per window, but the 128-session burst of the
                 # e2e leg then needs 16 admission rounds interleaved with decoder steps: e2e 351 vs 373 audio-s/s)
 
+# the server's two decode profiles (reference config/model.yaml:42-65, stt_server/config/default/model.py:17-27)
 REALTIME = {"beam_size": 1, "best_of": 1, "patience": 1.0, "temperature": 0.0, "length_penalty": 1.0,
             "without_timestamps": True, "compression_ratio_threshold": 2.4, "no_speech_threshold": 0.6,
             "log_prob_threshold": -1.0, "language": "en", "task": "transcribe"}
+ACCURATE = dict(REALTIME, beam_size=5, best_of=5)
+
+# BASELINE.json `configs`, as this bench drives them at the ModelWorker.decode_sync boundary.
+# windows: "partial" = one 2-10 s partial window per session per step; "utterance" = one VAD-endpointed utterance of
+# 1-8 s per session per step (finals only); "chunk30" = one 30 s chunk per session per step.
+CONFIGS = {
+    0: dict(model="tiny.en", sessions=1, profile="realtime", windows="chunk30", gpus=(1,),
+            label="configs[0]: tiny.en, batch client, single 30 s synthetic chunk (the reference's CPU int8 case; this arm runs it on the GPU)"),
+    1: dict(model="base", sessions=16, profile="realtime", windows="partial", gpus=(1,),
+            label="configs[1]: base multilingual (language fixed to en), realtime profile, 16 concurrent streaming sessions, 1 B200"),
+    2: dict(model="small", sessions=64, profile="realtime", windows="utterance", gpus=(1, 2, 4),
+            label="configs[2]: small, 64 concurrent sessions per GPU, VAD-endpointed utterances (finals only), realtime profile"),
+    3: dict(model="large-v3", sessions=64, profile="accurate", windows="chunk30", gpus=(1,),
+            label="configs[3]: large-v3 (128 mel bins), accurate profile (beam 5), 64 back-to-back 30 s chunks per step, 1 B200"),
+    4: dict(model="large-v3", sessions=128, profile="realtime", windows="partial", gpus=(1, 2, 4, 8),
+            label="configs[4] per-GPU shard: large-v3 realtime profile (beam_size=1), 128 concurrent sessions per GPU, one 2-10 s "
+                  "partial window per session per step"),
+}
 
 
 def parse_args():
@@ -49,14 +69,23 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="large-v3")
-    ap.add_argument("--sessions", type=int, default=128, help="concurrent sessions per GPU")
+    ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS), help="BASELINE.json configs[N] (default 4)")
+    ap.add_argument("--model", default=None, help="override the config's model")
+    ap.add_argument("--sessions", type=int, default=0, help="override the config's concurrent sessions per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streaming-seconds", type=float, default=10.0,
                     help="length of the real-time streaming-session run reported under `streaming` (0 = skip)")
     ap.add_argument("--streaming-sessions", type=int, default=0, help="sessions per GPU in that run (0 = 3 x --sessions)")
     ap.add_argument("--cpu-threads", type=int, default=0)
-    return ap.parse_args()
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.model = args.model or cfg["model"]
+    args.sessions = args.sessions or cfg["sessions"]
+    args.profile = dict(ACCURATE if cfg["profile"] == "accurate" else REALTIME)
+    args.n_group = 5 if cfg["profile"] == "accurate" else 1
+    args.windows = cfg["windows"]
+    args.cfg = cfg
+    return args
 
 
 def peaks():
@@ -79,9 +108,22 @@ def ncu_traffic(sessions: int):
     return None
 
 
-def window_lengths(rank: int, sessions: int):
+def window_lengths(rank: int, sessions: int, kind: str = "partial"):
     rng = np.random.default_rng(4242 + rank)
-    return [float(np.round(rng.uniform(2.0, 10.0), 2)) for _ in range(sessions)]
+    if kind == "chunk30":
+        return [30.0] * sessions
+    lo, hi = (2.0, 10.0) if kind == "partial" else (1.0, 8.0)  # utterance: the burst lengths of tools/stream_bench.py
+    return [float(np.round(rng.uniform(lo, hi), 2)) for _ in range(sessions)]
+
+
+def faster_whisper_row():
+    """the reference's other baseline (stt_server/model/backends/faster_whisper.py:14-39, CTranslate2 int8 on the CPU):
+    probed at run time, never estimated"""
+    try:
+        import faster_whisper  # noqa: F401
+    except Exception as exc:  # noqa: BLE001
+        return f"not runnable: {type(exc).__name__}: {exc} (module absent from this image, no network to install it)"
+    return "importable, but no pretrained CTranslate2 checkpoint is available offline: not run"
 
 
 class ClockSampler:
@@ -175,7 +217,7 @@ def whole_job_rtfx(dist, local, audio_sec_local: float, seconds_local: float) ->
     return sum_over_ranks(dist, local, audio_sec_local) / barrier_max(dist, local, seconds_local)
 
 
-def cpu_oracle_window(state, model_name: str, seconds: float, sample_len=None, threads: int = 0):
+def cpu_oracle_window(state, model_name: str, seconds: float, sample_len=None, threads: int = 0, profile=None):
     """One window through the CPU oracle (reference torch_whisper path restated); returns (elapsed s, cores)."""
     import torch
 
@@ -187,7 +229,7 @@ def cpu_oracle_window(state, model_name: str, seconds: float, sample_len=None, t
     dims = MODEL_DIMS[model_name]
     model = wo.Whisper(wo.ModelDimensions(**dims.__dict__), state)
     audio = synth_audio(999, seconds)
-    opts = wo.normalize_options(dict(REALTIME))  # the wrapper's option handling (torch_whisper.py:78-110)
+    opts = wo.normalize_options(dict(profile or REALTIME))  # the wrapper's option handling (torch_whisper.py:78-110)
     if sample_len:
         opts["sample_len"] = sample_len
     t0 = time.perf_counter()
@@ -195,9 +237,15 @@ def cpu_oracle_window(state, model_name: str, seconds: float, sample_len=None, t
     return time.perf_counter() - t0, cores
 
 
-def workload_name(model: str, sessions: int) -> str:
-    return (f"{model} realtime profile (beam_size=1), {sessions} concurrent sessions per GPU, one 2-10 s "
-            f"partial window per session per step (configs[4] per-GPU shard)")
+def workload_name(args) -> str:
+    name = args.cfg["label"]
+    if args.model != args.cfg["model"] or args.sessions != args.cfg["sessions"]:
+        name += f" [overridden: model {args.model}, {args.sessions} sessions per GPU]"
+    return name
+
+
+def cpu_sample_seconds(args) -> float:
+    return 30.0 if args.windows == "chunk30" else 6.0
 
 
 def run_reference(args):
@@ -207,25 +255,27 @@ def run_reference(args):
     from b200_whisper.synth import MODEL_DIMS, random_state_dict
 
     state = random_state_dict(MODEL_DIMS[args.model], 0, emb_std=0.1)
-    seconds = 6.0
+    seconds = cpu_sample_seconds(args)
     for _ in range(args.warmup):  # nothing to warm on the CPU but threads/allocator: short decodes
-        cpu_oracle_window(state, args.model, seconds, sample_len=4, threads=args.cpu_threads)
+        cpu_oracle_window(state, args.model, seconds, sample_len=4, threads=args.cpu_threads, profile=args.profile)
     times = []
     cores = 1
     for _ in range(args.steps):
-        dt, cores = cpu_oracle_window(state, args.model, seconds, threads=args.cpu_threads)
+        dt, cores = cpu_oracle_window(state, args.model, seconds, threads=args.cpu_threads, profile=args.profile)
         times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = seconds / (ms / 1e3)
-    sample = f"1 session x 1 partial window ({seconds:.0f} s audio -> full 30 s encoder pass + 224 decoder steps) per step"
+    sample = (f"1 session x 1 window ({seconds:.0f} s audio -> full 30 s encoder pass + 224 decoder steps, "
+              f"beam {args.profile['beam_size']}) per step")
     emit(json.dumps({
         "impl": "reference", "metric": "RTFx (audio-seconds transcribed per second)", "value": value, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic audio, random-init weights",
-        "config": {"workload": workload_name(args.model, args.sessions),
-                   "sample": "bounded sample of that workload: ONE of its windows per step (6 s partial) on the host cores, fp32 torch",
+        "config": {"workload": workload_name(args),
+                   "sample": f"bounded sample of that workload: ONE of its windows per step ({seconds:.0f} s) on the host cores, fp32 torch",
                    "note": "warm-up steps decode 4 tokens only; timed steps are full windows (224 decoder steps)"},
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "faster_whisper_int8": faster_whisper_row(),
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -244,24 +294,25 @@ def run_b200(args):
     spec = f"random:{args.model}:0:0.1"
     # the engine materialises the seeded random checkpoint one tensor at a time (backend.load_checkpoint); only the CPU
     # baseline at the end (rank 0, N = 1) needs the whole fp32 state dict on the host
-    handles = [B200WhisperBackend(spec, f"cuda:{local}", "bfloat16", max_segments=S, max_sequences=max(2 * S, 8),
+    NG = args.n_group
+    handles = [B200WhisperBackend(spec, f"cuda:{local}", "bfloat16", max_segments=S, max_sequences=max(2 * S, NG * S, 320 if args.config == 4 and S >= 64 else 8),
                                   max_encoder_batch=min(ENC_BATCH, S)) for _ in range(S)]
     eng = handles[0].engine
-    lengths = window_lengths(rank, S)
+    lengths = window_lengths(rank, S, args.windows)
     audios = [synth_audio(rank * 100000 + i, lengths[i]) for i in range(S)]
     audio_sec = float(sum(a.size for a in audios)) / 16000.0
     n_steps = dims.n_text_ctx // 2  # 224: random weights never emit EOT (worst case)
 
     # ---- value: device-timed pipeline on resident PCM ----
     for _ in range(args.warmup):
-        eng.bench_pipeline(audios, 1, n_steps)
+        eng.bench_pipeline(audios, NG, n_steps)
     barrier_max(dist, local, 0.0)
     torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = eng.stats()["kernel_launches"]
     total_ms = 0.0
     for _ in range(args.steps):
-        total_ms += eng.bench_pipeline(audios, 1, n_steps)
+        total_ms += eng.bench_pipeline(audios, NG, n_steps)
     torch.cuda.synchronize()
     launches = eng.stats()["kernel_launches"] - l0
     value = whole_job_rtfx(dist, local, audio_sec * args.steps, total_ms / 1e3)
@@ -275,7 +326,7 @@ def run_b200(args):
     def e2e_step(record: bool):
         def work(i):
             t0 = time.perf_counter()
-            handles[i].transcribe(audios[i], REALTIME)
+            handles[i].transcribe(audios[i], args.profile)
             if record:
                 lat.append(time.perf_counter() - t0)
 
@@ -300,40 +351,49 @@ def run_b200(args):
 
     # ---- streaming sessions in real time (tools/stream_bench.py): the orchestrator's partial / final schedule ----
     streaming = None
-    if args.streaming_seconds > 0:
+    if args.streaming_seconds > 0 and args.windows != "chunk30":
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         from stream_bench import run_stream_sim
 
-        n_stream = args.streaming_sessions or 3 * S
+        # configs[4]: 3 x the per-GPU shard (how many streams one GPU carries); configs[1] / [2]: the named session count
+        n_stream = args.streaming_sessions or (3 * S if args.config == 4 else S)
         while len(handles) < n_stream:
             handles.append(B200WhisperBackend(spec, f"cuda:{local}", "bfloat16"))
         barrier_max(dist, local, 0.0)
-        streaming = run_stream_sim(handles[:n_stream], args.streaming_seconds, seed=rank)
+        streaming = run_stream_sim(handles[:n_stream], args.streaming_seconds, seed=rank, opts=args.profile,
+                                   finals_only=args.windows == "utterance")
         streaming["note"] = ("real-time pacing; decodes bounded by DecodingOptions.sample_len = 3.5 tokens per audio second + 4 "
                              "(random weights never emit EOT); per GPU, rank 0 shown")
 
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (decoder cross-attention, HBM-bound), timed live ----
-    xa_ms, xa_bytes = eng.bench_cross_attention(S, 1, 64)
+    xa_ms, xa_bytes = eng.bench_cross_attention(S, NG, 64)
     achieved = xa_bytes / (xa_ms * 1e-3) / 1e9
     stages = {}
     enc_b = min(ENC_BATCH, S)
     ems, eflops = eng.bench_encoder(enc_b, 3)
     stages["encoder"] = {"batch": enc_b, "ms": ems, "tflops": eflops / (ems * 1e-3) / 1e12,
                          "frac_of_bf16_sustained": eflops / (ems * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]}
-    eng.bench_decoder_step(S, 1, 60, 6)  # the step graph of this shape is captured at its third sighting: not in the timed run
-    dms, dbytes = eng.bench_decoder_step(S, 1, 100, 20)
-    stages["decoder_step"] = {"segments": S, "context": 100, "ms": dms, "gbs": dbytes / (dms * 1e-3) / 1e9,
+    eng.bench_decoder_step(S, NG, 60, 6)  # the step graph of this shape is captured at its third sighting: not in the timed run
+    dms, dbytes = eng.bench_decoder_step(S, NG, 100, 20)
+    stages["decoder_step"] = {"segments": S, "hypotheses_per_segment": NG, "context": 100, "ms": dms, "gbs": dbytes / (dms * 1e-3) / 1e9,
                               "frac_of_hbm": dbytes / (dms * 1e-3) / 1e9 / pk["hbm_gbs"]}
-    mms, mbytes = eng.bench_mel(96000, 20)
-    stages["mel"] = {"audio_s": 6.0, "ms": mms, "gbs": mbytes / (mms * 1e-3) / 1e9}
+    if args.config == 4 and S >= 64:  # the other headline shape (configs[3]: 64 windows x beam 5) on the same engine
+        eng.bench_decoder_step(64, 5, 60, 6)
+        bms, bbytes = eng.bench_decoder_step(64, 5, 100, 20)
+        stages["decoder_step_beam5"] = {"segments": 64, "hypotheses_per_segment": 5, "context": 100, "ms": bms,
+                                        "gbs": bbytes / (bms * 1e-3) / 1e9, "frac_of_hbm": bbytes / (bms * 1e-3) / 1e9 / pk["hbm_gbs"]}
+    mel_n = int(cpu_sample_seconds(args) * 16000)
+    mms, mbytes = eng.bench_mel(mel_n, 20)
+    stages["mel"] = {"audio_s": mel_n / 16000.0, "ms": mms, "gbs": mbytes / (mms * 1e-3) / 1e9, "frac_of_hbm": mbytes / (mms * 1e-3) / 1e9 / pk["hbm_gbs"]}
 
     out = {
         "metric": "RTFx (audio-seconds transcribed per second)", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic audio, random-init weights (no EOT: 224 decoder steps per window)",
-        "config": {"workload": workload_name(args.model, S),
+        "impl": "b200",
+        "config": {"workload": workload_name(args), "baseline_config_index": args.config,
                    "sessions_per_gpu": S, "audio_s_per_step_per_gpu": audio_sec, "decoder_steps_per_window": n_steps,
                    "l2": "inputs larger than L2 (cross-KV cache %.1f GB per step)" % (S * dims.n_text_layer * 1500 * 2 * dims.n_text_state * 2 / 1e9),
                    "timing": "CUDA events on the engine stream inside libb200whisper.so, max over ranks", "peaks": pk["source"]},
@@ -344,7 +404,7 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": {"kernel": "dec_cross_attention_mma_kernel (decoder cross-attention over the cached encoder K/V)", "bound": "hbm",
                      "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                     "traffic": ncu_traffic(S), "ms_per_launch": xa_ms,
+                     "traffic": ncu_traffic(S) if args.config == 4 else None, "ms_per_launch": xa_ms,
                      "algorithmic_bytes_per_launch": xa_bytes},
         "stages": stages,
     }
@@ -352,10 +412,12 @@ def run_b200(args):
         out["streaming"] = streaming
     if world == 1 and not args.no_cpu_baseline:
         state = random_state_dict(dims, 0, emb_std=0.1)
-        dt, cores = cpu_oracle_window(state, args.model, 6.0, threads=args.cpu_threads)
-        out["cpu_baseline"] = {"value": 6.0 / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                               "sample": "1 session x 1 partial window (6 s audio, full 30 s encoder pass + 224 decoder steps), "
-                                         f"fp32 torch on {cores} threads, {dt:.1f} s"}
+        cs = cpu_sample_seconds(args)
+        dt, cores = cpu_oracle_window(state, args.model, cs, threads=args.cpu_threads, profile=args.profile)
+        out["cpu_baseline"] = {"value": cs / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                               "sample": f"1 session x 1 window ({cs:.0f} s audio, full 30 s encoder pass + 224 decoder steps, beam "
+                                         f"{args.profile['beam_size']}), fp32 torch on {cores} threads, {dt:.1f} s"}
+    out["faster_whisper_int8"] = faster_whisper_row()
     emit(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -140,18 +140,30 @@ def test_bf16_decode_is_deterministic_and_batch_invariant():
         th = [threading.Thread(target=work, args=(i,)) for i in range(len(audios))]
         [t.start() for t in th]
         [t.join() for t in th]
-        return [[(s["tokens"], round(s["avg_logprob"], 6)) for s in r["segments"]] for r in out]
+        return [[(s["tokens"], s["avg_logprob"]) for s in r["segments"]] for r in out]
+
+    def toks(r):
+        return [t for t, _ in r]
+
+    def lp_diff(a, c):
+        return max([abs(x[1] - y[1]) for x, y in zip(a, c)] + [0.0]) if toks(a) == toks(c) else float("nan")
 
     first = run_batch()
     again = run_batch()
-    # scheduling (which requests share a step) is timing dependent; the arithmetic of a row is not
-    same = sum(a == c for a, c in zip(first, again))
-    alone = [[(s["tokens"], round(s["avg_logprob"], 6)) for s in
+    # Which requests share a step is timing dependent, and with it the T-split / K-split choice of a launch: the
+    # arithmetic of a row changes only in its fp32 summation order.  Token streams must survive that; log-probabilities
+    # may move in their last bits.
+    same = sum(toks(a) == toks(c) for a, c in zip(first, again))
+    alone = [[(s["tokens"], s["avg_logprob"]) for s in
               b.transcribe_raw(a, **b._normalize_options(opts if i % 4 else dict(ACCURATE, language="en")))["segments"]]
              for i, a in enumerate(audios)]
-    same_alone = sum([t for t, _ in a] == [t for t, _ in c] for a, c in zip(first, alone))
-    _report("r2_bf16_batch_invariance.json", {"sessions": len(audios), "identical_batch_vs_batch": same, "identical_batch_vs_alone": same_alone})
-    assert same >= len(audios) - 1 and same_alone >= len(audios) - 1
+    same_alone = sum(toks(a) == toks(c) for a, c in zip(first, alone))
+    diffs = [lp_diff(a, c) for a, c in zip(first, again)] + [lp_diff(a, c) for a, c in zip(first, alone)]
+    rep = {"sessions": len(audios), "identical_tokens_batch_vs_batch": same, "identical_tokens_batch_vs_alone": same_alone,
+           "max_avg_logprob_difference": float(np.nanmax(diffs))}
+    _report("r2_bf16_batch_invariance.json", rep)
+    assert same >= len(audios) - 1 and same_alone >= len(audios) - 1, rep
+    assert rep["max_avg_logprob_difference"] < 2e-3, rep
 
 
 @pytest.mark.parametrize("name,n_utt,sample_len", [("test-tiny", 12, 224), ("tiny.en", 10, 224), ("base", 6, 224), ("small", 4, 96)])

@@ -39,8 +39,9 @@ def nearest_rank(values, q):
 
 
 def run_stream_sim(handles, seconds: float, seed: int = 0, partial_every: float = 1.5, window_s: float = 10.0, opts=None,
-                   tokens_per_s: float = 3.5):
-    """handles[i] serves session i.  Returns a dict of latency / throughput statistics."""
+                   tokens_per_s: float = 3.5, finals_only: bool = False):
+    """handles[i] serves session i.  Returns a dict of latency / throughput statistics.
+    finals_only: VAD endpointing without interim results (BASELINE configs[2]): one decode per burst, at its end."""
     from b200_whisper.synth import synth_audio
 
     opts = dict(opts or REALTIME)
@@ -75,7 +76,7 @@ def run_stream_sim(handles, seconds: float, seed: int = 0, partial_every: float 
         h = handles[i]
         for (b0, b1) in plans[i]:
             k = 1
-            while True:
+            while not finals_only:
                 due = b0 + k * partial_every
                 if due >= b1:
                     break

@@ -21,7 +21,14 @@ def ensure_proto_stubs() -> None:
         return
     from .protostubs import install
 
-    install(os.path.join(root, "proto", "stt.proto"))
+    # a checkout keeps proto/ next to the packages; an installed server (pip --target) does not ship it: $B200_WHISPER_PROTO,
+    # or the `_tree/` directory tools/install_reference.sh puts next to the packages
+    candidates = [os.environ.get("B200_WHISPER_PROTO"), os.path.join(root, "proto", "stt.proto"), os.path.join(root, "_tree", "proto", "stt.proto")]
+    for path in candidates:
+        if path and os.path.isfile(path):
+            install(path)
+            return
+    raise RuntimeError(f"stt.proto not found (looked at {[c for c in candidates if c]}); set B200_WHISPER_PROTO")
 
 
 def main() -> None:
