@@ -53,9 +53,13 @@ typedef struct bw_engine_config {
   int32_t cuda_device;       /* ordinal */
   int32_t compute;           /* bw_compute */
   int32_t max_segments;      /* concurrent decode windows resident on the GPU (cross-KV slots); 0 = auto */
-  int32_t max_sequences;     /* concurrent hypotheses (beams) resident (self-KV units); 0 = auto */
+  int32_t max_sequences;     /* concurrent hypotheses (beams) resident (state slots); 0 = auto */
   int32_t max_encoder_batch; /* windows per encoder launch; 0 = auto */
   int32_t flags;             /* BW_FLAG_* */
+  /* self-attention KV pool, in pages of 16 positions of one hypothesis (all layers, k and v); 0 = auto
+   * (16 pages per hypothesis slot).  Pages are handed out as hypotheses grow and shared by beams over their common
+   * prefix, so the pool follows the tokens in use; a window is admitted once its worst case is reservable. */
+  int32_t max_kv_pages;
 } bw_engine_config;
 
 #define BW_FLAG_FORCE_SIMT_GEMM 1  /* debugging: use the SIMT GEMM/attention even in bf16 mode */
@@ -142,7 +146,8 @@ int bw_engine_stats(bw_engine*, int64_t* out, int32_t n); /* see BW_STAT_* */
 enum {
   BW_STAT_KERNEL_LAUNCHES = 0, BW_STAT_DECODE_STEPS, BW_STAT_ROWS, BW_STAT_WINDOWS,
   BW_STAT_MAX_SEGMENTS, BW_STAT_MAX_SEQUENCES, BW_STAT_ENCODER_BATCHES, BW_STAT_H2D_BYTES,
-  BW_STAT_D2H_BYTES, BW_STAT_COUNT
+  BW_STAT_D2H_BYTES, BW_STAT_KV_PAGES_TOTAL, BW_STAT_KV_PAGES_IN_USE, BW_STAT_KV_PAGES_PEAK, BW_STAT_KV_PAGE_BYTES,
+  BW_STAT_COUNT
 };
 
 /* ---- the hot call, split so the host keeps upstream's seek loop (transcribe.py) ---- */

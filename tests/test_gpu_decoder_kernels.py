@@ -100,9 +100,26 @@ def test_cross_attention_mma_short_encoder_context():
 
 
 # ------------------------------------------------------------------------------------------------- self attention
-def _self_ref(qkv, pool_before, rows, seq_first, anc, layer, d, n_head, n_ctx):
+P = 16  # kPageTokens
+
+
+def _paged_pool(S, n_layer, n_ctx, d, gen, seed):
+    """pool [n_pages][L][2][P][d] bf16 + a page table [S][n_blocks] that scatters every (slot, block) onto a random page"""
+    nb = (n_ctx + P - 1) // P
+    n_pages = S * nb + 5
+    pool = (torch.randn((n_pages, n_layer, 2, P, d), device=DEV, generator=gen) * 1.3).bfloat16()
+    perm = torch.randperm(n_pages, generator=torch.Generator().manual_seed(seed))[: S * nb].reshape(S, nb).to(torch.int32)
+    return pool, perm, nb
+
+
+def _kv_at(pool, pt, u, layer, kv, t):
+    return pool[int(pt[u, t // P]), layer, kv, t % P]
+
+
+def _self_ref(qkv, pool_before, pt, rows, seq_first, anc, layer, d, n_head):
     """fp32 reference of one decoder self-attention step over the paged pool: row r attends positions [0, pos_r]; positions
-    < bpos come from the pool through the ancestry table, the others from this step's qkv rows (bf16-rounded like the append)"""
+    < bpos come from the pool through the ancestry table + page table, the others from this step's qkv rows (bf16-rounded
+    like the append)"""
     R = qkv.shape[0]
     out = torch.empty((R, d), device=DEV)
     kb = qkv[:, d:2 * d].bfloat16().float()
@@ -114,8 +131,8 @@ def _self_ref(qkv, pool_before, rows, seq_first, anc, layer, d, n_head, n_ctx):
         for t in range(pos + 1):
             if t < bpos:
                 u = first + int(anc[s, t])
-                ks.append(pool_before[u, layer, 0, t].float())
-                vs.append(pool_before[u, layer, 1, t].float())
+                ks.append(_kv_at(pool_before, pt, u, layer, 0, t).float())
+                vs.append(_kv_at(pool_before, pt, u, layer, 1, t).float())
             else:
                 rr = r - (pos - t)
                 ks.append(kb[rr])
@@ -128,18 +145,19 @@ def _self_ref(qkv, pool_before, rows, seq_first, anc, layer, d, n_head, n_ctx):
     return out
 
 
-def _run_self(rows, qkv, pool, seq_first_dev_vals, anc, layer, d, n_head, n_ctx, n_layer):
+def _run_self(rows, qkv, pool, pt, seq_first_dev_vals, anc, layer, d, n_head, n_ctx, n_layer):
     lib = L.load()
     R = qkv.shape[0]
     out = torch.full((R, d), float("nan"), device=DEV, dtype=torch.bfloat16)
     rs, rp, rb = _i32(rows["seq"]), _i32(rows["pos"]), _i32(rows["bpos"])
+    rpage = _i32([int(pt[s, t // P]) for s, t in zip(rows["seq"], rows["pos"])])  # the row's k / v goes to its slot's page
     sf = _i32(seq_first_dev_vals)
     anc_d = anc.to(torch.uint8).to(DEV).contiguous()
-    unit_stride = n_layer * 2 * n_ctx * d
+    pt_d = pt.to(DEV).contiguous()
     torch.cuda.synchronize()
-    L.check(lib.bw_test_dec_self_attention(R, rs.data_ptr(), rp.data_ptr(), rb.data_ptr(), qkv.data_ptr(), pool.data_ptr(), unit_stride,
-                                           n_ctx, sf.data_ptr(), anc_d.data_ptr(), layer, d, n_head, out.data_ptr(), None),
-            "bw_test_dec_self_attention")
+    L.check(lib.bw_test_dec_self_attention(R, rs.data_ptr(), rp.data_ptr(), rb.data_ptr(), rpage.data_ptr(), qkv.data_ptr(), pool.data_ptr(),
+                                           n_layer, n_ctx, pt.shape[0], pt_d.data_ptr(), sf.data_ptr(), anc_d.data_ptr(), layer, d, n_head,
+                                           out.data_ptr(), None), "bw_test_dec_self_attention")
     torch.cuda.synchronize()
     return out
 
@@ -148,13 +166,14 @@ def _run_self(rows, qkv, pool, seq_first_dev_vals, anc, layer, d, n_head, n_ctx,
 @pytest.mark.parametrize("G", [1, 5, 8])
 def test_self_attention_bf16_cached_decode_through_ancestry(ctx, G):
     """one new token per hypothesis at position `ctx` (the step's row), `ctx` cached positions behind it.  G > 1: every
-    cached position of every hypothesis lives in a RANDOM beam slot of its request (what beam reordering leaves behind)."""
+    cached position of every hypothesis lives in a RANDOM beam slot of its request (what beam reordering leaves behind);
+    every (slot, block) sits on a random page of the pool."""
     n_head, n_layer, layer, n_ctx = 6, 3, 1, 448
     d = 64 * n_head
     n_req = 3
     S = n_req * G + 2
     g = torch.Generator(device=DEV).manual_seed(ctx * 17 + G)
-    pool = (torch.randn((S, n_layer, 2, n_ctx, d), device=DEV, generator=g) * 1.3).bfloat16()
+    pool, pt, nb = _paged_pool(S, n_layer, n_ctx, d, g, ctx + 31 * G)
     pool_before = pool.clone()
     cg = torch.Generator().manual_seed(ctx + G)
     anc = torch.randint(0, G, (S, n_ctx), generator=cg)
@@ -170,19 +189,20 @@ def test_self_attention_bf16_cached_decode_through_ancestry(ctx, G):
     if G == 1:
         anc.zero_()
     qkv = torch.randn((len(seq), 3 * d), device=DEV, generator=g) * 1.5
-    out = _run_self(rows, qkv, pool, [f | flag for f in seq_first], anc, layer, d, n_head, n_ctx, n_layer)
-    ref = _self_ref(qkv, pool_before, rows, seq_first, anc, layer, d, n_head, n_ctx)
+    out = _run_self(rows, qkv, pool, pt, [f | flag for f in seq_first], anc, layer, d, n_head, n_ctx, n_layer)
+    ref = _self_ref(qkv, pool_before, pt, rows, seq_first, anc, layer, d, n_head)
     assert torch.isfinite(out.float()).all()
     r = _rel(out, ref)
     assert r < 5e-3, f"ctx {ctx} G {G}: rel-L2 {r}"  # fp32 math on bf16 K/V; only the bf16 output rounding is left
     per_row = (out.float() - ref).norm(dim=1) / ref.norm(dim=1)
     assert per_row.max().item() < 2.5e-2
-    # fused append: this step's k / v rows landed in the hypothesis' OWN unit at position ctx, nothing else changed
-    for i, s in enumerate(seq):
-        assert torch.equal(pool[s, layer, 0, ctx], qkv[i, d:2 * d].bfloat16()) and torch.equal(pool[s, layer, 1, ctx], qkv[i, 2 * d:].bfloat16())
+    # fused append: this step's k / v rows landed on the hypothesis' OWN page at position ctx, nothing else changed
     changed = (pool != pool_before)
-    changed[seq, layer, :, ctx] = False
-    assert not changed.any(), "the kernel wrote outside this step's (unit, layer, position) rows"
+    for i, s in enumerate(seq):
+        pg = int(pt[s, ctx // P])
+        assert torch.equal(pool[pg, layer, 0, ctx % P], qkv[i, d:2 * d].bfloat16()) and torch.equal(pool[pg, layer, 1, ctx % P], qkv[i, 2 * d:].bfloat16())
+        changed[pg, layer, :, ctx % P] = False
+    assert not changed.any(), "the kernel wrote outside this step's (page, layer, position) rows"
 
 
 def test_self_attention_bf16_prefill_rows():
@@ -192,15 +212,15 @@ def test_self_attention_bf16_prefill_rows():
     d = 64 * n_head
     g = torch.Generator(device=DEV).manual_seed(9)
     S = 4
-    pool = (torch.randn((S, n_layer, 2, n_ctx, d), device=DEV, generator=g)).bfloat16()
+    pool, pt, nb = _paged_pool(S, n_layer, n_ctx, d, g, 77)
     pool_before = pool.clone()
-    n_init = 11
+    n_init = 19  # spans two pages
     rows = {"seq": [2] * n_init + [0] * 3, "pos": list(range(n_init)) + [130, 131, 132], "bpos": [0] * n_init + [130] * 3}
     anc = torch.zeros((S, n_ctx), dtype=torch.int64)
     flag = 0x40000000
     qkv = torch.randn((n_init + 3, 3 * d), device=DEV, generator=g)
-    out = _run_self(rows, qkv, pool, [s | flag for s in range(S)], anc, layer, d, n_head, n_ctx, n_layer)
-    ref = _self_ref(qkv, pool_before, rows, list(range(S)), anc, layer, d, n_head, n_ctx)
+    out = _run_self(rows, qkv, pool, pt, [s | flag for s in range(S)], anc, layer, d, n_head, n_ctx, n_layer)
+    ref = _self_ref(qkv, pool_before, pt, rows, list(range(S)), anc, layer, d, n_head)
     r = _rel(out, ref)
     assert r < 5e-3, f"prefill rel-L2 {r}"
 

@@ -1,0 +1,81 @@
+"""Paged self-attention KV cache (north_star (3)): pages of 16 positions per hypothesis slot behind a device page table,
+handed out by the scheduler as hypotheses grow, shared by the beams of a request over their common prefix (pages no
+surviving hypothesis references go back to the pool after every step), reserved per window at admission.
+
+Checked here: results are unchanged (fp32 validation mode token-exact vs the oracle) when the pool is so small that
+windows queue for pages; pages in use follow the tokens in use and return to zero; beam search holds far fewer pages
+than beams x blocks; the smallest pool still admits the widest window."""
+import threading
+
+import pytest
+
+from tests._util import ACCURATE, REALTIME, model_spec, oracle_model
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+torch = pytest.importorskip("torch")
+
+from b200_whisper.backend import B200WhisperBackend  # noqa: E402
+from b200_whisper.synth import synth_audio  # noqa: E402
+from oracle import whisper_oracle as wo  # noqa: E402
+
+
+def _segments(res):
+    return [(round(s.start, 3), round(s.end, 3), s.text) for s in res]
+
+
+def test_small_pool_queues_windows_and_results_do_not_change():
+    """12 concurrent windows (every third one beam 5) through a pool of 40 pages: a beam-5 window reserves 5 x 15 pages,
+    so at most one of them plus a few greedy ones fit at a time and the rest wait for pages.  Same answers as the oracle."""
+    name, seed = "test-tiny", 11
+    b = B200WhisperBackend(model_spec(name, seed=seed), "cuda:0", "float32", max_segments=16, max_sequences=48, max_kv_pages=40)
+    st0 = b.engine.stats()
+    assert st0["kv_pages_total"] == 28 * 8 and st0["kv_pages_in_use"] == 0  # never below one worst-case window (n_text_ctx x 8 beams)
+    b = B200WhisperBackend(model_spec(name, seed=seed + 1), "cuda:0", "float32", max_segments=16, max_sequences=48, max_kv_pages=230)
+    model = oracle_model(name, seed=seed + 1)
+    audios = [synth_audio(700 + i, 2.0 + 0.5 * i) for i in range(12)]
+    opts = [dict(ACCURATE if i % 3 == 0 else REALTIME, language="en") for i in range(12)]
+    out = [None] * 12
+
+    def work(i):
+        out[i] = b.transcribe(audios[i], opts[i])
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(12)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(12):
+        ref, _, raw = wo.backend_transcribe(model, audios[i], opts[i])
+        if min(w.min_margin for w in raw["windows"]) < 2e-4:
+            continue
+        assert _segments(out[i][0]) == [(round(a, 3), round(e, 3), t) for a, e, t in ref], f"window {i}"
+    st = b.engine.stats()
+    assert st["kv_pages_in_use"] == 0, "pages leaked"
+    assert 0 < st["kv_pages_peak"] <= st["kv_pages_total"] == 230
+    # 4 beam-5 windows + 8 greedy ones would hold 4 * 75 + 8 * 15 = 420 pages if every window kept its worst case
+
+
+def test_beam_search_shares_prefix_pages():
+    """one beam-5 window decoded to 224 tokens: 5 hypotheses x 15 blocks = 75 pages without sharing; with the page
+    collector the request holds the common-prefix blocks once and only the recent blocks five times"""
+    b = B200WhisperBackend(model_spec("test-tiny", seed=21), "cuda:0", "float32", max_segments=4, max_sequences=16)
+    b.transcribe(synth_audio(800, 5.0), dict(ACCURATE, language="en"))
+    st = b.engine.stats()
+    assert st["kv_pages_in_use"] == 0
+    assert st["kv_pages_peak"] <= 40, f"beam 5 held {st['kv_pages_peak']} pages at its peak (75 without prefix sharing)"
+    assert st["kv_page_bytes"] == 2 * 2 * 16 * 128 * 4  # [L = 2][k | v][16 positions][d = 128] fp32
+
+
+def test_minimum_pool_holds_the_widest_window():
+    """max_kv_pages is clamped to one worst-case window (28 blocks x 8 hypotheses), so every request the API accepts can be
+    admitted: the widest beam runs in the smallest pool and gives the pool back"""
+    b = B200WhisperBackend(model_spec("test-tiny", seed=31), "cuda:0", "float32", max_segments=4, max_sequences=16, max_kv_pages=1)
+    assert b.engine.stats()["kv_pages_total"] == 224
+    out = [None] * 3
+
+    def work(i):
+        out[i] = b.transcribe(synth_audio(801 + i, 3.0), dict(REALTIME, language="en", beam_size=8, best_of=8))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(3)]  # 3 x (8 x 15) pages reserved > 224: they take turns
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert all(isinstance(o[0], list) for o in out) and b.engine.stats()["kv_pages_in_use"] == 0

@@ -16,7 +16,7 @@ BW_COMPUTE_BF16, BW_COMPUTE_FP32 = 0, 1
 BW_F32, BW_F16, BW_BF16 = 0, 1, 2
 BW_FLAG_FORCE_SIMT_GEMM, BW_FLAG_NO_SCHEDULER, BW_FLAG_SIMT_ATTENTION = 1, 2, 4
 STAT_NAMES = ("kernel_launches", "decode_steps", "rows", "windows", "max_segments", "max_sequences",
-              "encoder_batches", "h2d_bytes", "d2h_bytes")
+              "encoder_batches", "h2d_bytes", "d2h_bytes", "kv_pages_total", "kv_pages_in_use", "kv_pages_peak", "kv_page_bytes")
 
 c_i32_p = C.POINTER(C.c_int32)
 c_f32_p = C.POINTER(C.c_float)
@@ -30,7 +30,7 @@ class ModelDimsC(C.Structure):
 
 class EngineConfigC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
-        "cuda_device", "compute", "max_segments", "max_sequences", "max_encoder_batch", "flags")]
+        "cuda_device", "compute", "max_segments", "max_sequences", "max_encoder_batch", "flags", "max_kv_pages")]
 
 
 class TensorDescC(C.Structure):
@@ -103,7 +103,7 @@ SIGNATURES = {
     "bw_debug_trace": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64), C.c_int32, c_i32_p]),
     "bw_call_decode_forced": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(DecodeOptsC), c_i32_p, C.c_int32, c_f32_p, C.POINTER(ResultC)]),
     "bw_test_dec_cross_attention": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]),
-    "bw_test_dec_self_attention": (C.c_int, [C.c_int32] + [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p] +
+    "bw_test_dec_self_attention": (C.c_int, [C.c_int32] + [C.c_void_p] * 6 + [C.c_int32] * 3 + [C.c_void_p] * 3 +
                                    [C.c_int32] * 3 + [C.c_void_p, C.c_void_p]),
     "bw_test_sample_topk": (C.c_int, [C.c_void_p, c_f32_p, C.c_int32, c_i32_p, c_i32_p, c_f32_p]),
 }

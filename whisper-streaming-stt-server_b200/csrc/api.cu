@@ -185,32 +185,41 @@ int bw_engine_finalize(bw_engine* e) {
   const size_t ts = e->fp32 ? 4 : 2;
   const size_t dm = d.n_audio_state;
   const size_t cross_slot = (size_t)d.n_text_layer * d.n_audio_ctx * 2 * dm * ts;
-  const size_t unit = (size_t)d.n_text_layer * 2 * d.n_text_ctx * dm * ts;
+  // self-KV pool: pages of kPageTokens positions for one hypothesis slot, every layer ([L][2][kPageTokens][d]).
+  // Default budget: 256 positions (16 pages) per hypothesis slot -- a decode holds at most n_initial + sample_len
+  // (<= 3 + 224 without a prompt) positions per hypothesis, and beam hypotheses share the pages of their common
+  // prefix -- but never less than one worst-case request (n_text_ctx positions x kMaxBeam hypotheses).
+  e->n_blocks = (d.n_text_ctx + kPageTokens - 1) / kPageTokens;
+  BW_CHECK(e->n_blocks <= kMaxBlocks, "n_text_ctx too large for the page table");
+  e->page_bytes = (size_t)d.n_text_layer * 2 * kPageTokens * dm * ts;
   int Q = e->cfg.max_segments > 0 ? e->cfg.max_segments : 64;
   int S = e->cfg.max_sequences > 0 ? e->cfg.max_sequences : std::max(2 * Q, kMaxBeam);
   int Be = e->cfg.max_encoder_batch > 0 ? e->cfg.max_encoder_batch : 8;
+  const int min_pages = e->n_blocks * kMaxBeam;
+  auto pages_for = [&](int s) { return e->cfg.max_kv_pages > 0 ? std::max(e->cfg.max_kv_pages, min_pages) : std::max(s * 16, min_pages); };
   size_t free_b = 0, total_b = 0;
   BW_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const size_t enc_per = (size_t)(3000 * 3 * d.n_mels + 3000 * dm + 1500 * 3 * dm + 1500 * dm * 2 + 1500 * 3 * dm + 1500 * dm +
                                   1500 * 4 * dm + 1500 * dm) * 4;  // upper bound (fp32 sizes)
   for (int guard = 0; guard < 64; ++guard) {
-    if (!((double)Q * cross_slot + (double)S * unit + (double)Be * enc_per > 0.80 * (double)free_b && (Q > 1 || S > kMaxBeam || Be > 1))) break;
+    const double need = (double)Q * cross_slot + (double)pages_for(S) * e->page_bytes + (double)Be * enc_per;
+    if (!(need > 0.80 * (double)free_b && (Q > 1 || S > kMaxBeam || Be > 1))) break;
     if (Q > 1) Q = std::max(1, Q * 3 / 4);
     S = std::max(kMaxBeam, std::min(S, std::max(2 * Q, kMaxBeam)));
     if (Be > 1) Be = std::max(1, Be / 2);
-  }
-  while (false && (double)Q * cross_slot + (double)S * unit + (double)Be * enc_per > 0.80 * (double)free_b && (Q > 1 || S > kMaxBeam || Be > 1)) {
-    if (Q > 1) Q = std::max(1, Q * 3 / 4);
-    S = std::max(kMaxBeam, std::min(S, std::max(2 * Q, kMaxBeam)));
-    if (Be > 1 && (double)Be * enc_per > 0.2 * (double)free_b) Be = std::max(1, Be / 2);
-    if (Q == 1 && Be == 1) break;
   }
   Be = std::min(Be, Q);
   e->Q = Q; e->S = S; e->Be = Be;
   e->R_max = S + 512;
   e->LR_max = S + Q + BW_MAX_TOKENS;
   e->cross_cache.alloc((size_t)Q * cross_slot);
-  e->self_pool.alloc((size_t)S * unit);
+  e->n_pages = pages_for(S);
+  e->self_pool.alloc((size_t)e->n_pages * e->page_bytes);
+  e->d_page_table.alloc((size_t)S * e->n_blocks * 4);
+  BW_CUDA(cudaMemset(e->d_page_table.p, 0, e->d_page_table.bytes));
+  e->free_pages.clear();
+  for (int pg = e->n_pages - 1; pg >= 0; --pg) e->free_pages.push_back(pg);
+  e->pages_reserved = 0;
   // encoder activations
   e->A1.alloc((size_t)Be * 3000 * 3 * d.n_mels * ts);
   e->y1.alloc((size_t)Be * 3000 * dm * ts);
@@ -249,14 +258,18 @@ int bw_engine_finalize(bw_engine* e) {
   e->st_float.alloc(((size_t)Q * kMaxFinished + 2 * (size_t)Q + S) * 4);
   e->st_anc0.alloc((size_t)S * n_ctx); e->st_anc1.alloc((size_t)S * n_ctx);
   e->st_tok.alloc((size_t)Q * n_ctx * kMaxBeam * 4); e->st_parent.alloc((size_t)Q * n_ctx * kMaxBeam);
-  for (DevBuf* b : {&e->st_int, &e->st_float, &e->st_anc0, &e->st_anc1, &e->st_tok, &e->st_parent}) BW_CUDA(cudaMemset(b->p, 0, b->bytes));
+  e->step_out_bytes = (size_t)Q * 4 + (size_t)Q * kMaxBeam;
+  e->st_step.alloc(e->step_out_bytes);
+  for (DevBuf* b : {&e->st_int, &e->st_float, &e->st_anc0, &e->st_anc1, &e->st_tok, &e->st_parent, &e->st_step}) BW_CUDA(cudaMemset(b->p, 0, b->bytes));
   {
     int* p = e->st_int.as<int>();
     auto take = [&](size_t n) { int* r = p; p += n; return r; };
     ReqState& rs = e->rs;
     rs.n_beam = take(Q); rs.greedy = take(Q); rs.sample_begin = take(Q); rs.cur_len = take(Q); rs.first_seq = take(Q);
     rs.without_ts = take(Q); rs.suppress_blank = take(Q); rs.max_initial_ts = take(Q); rs.max_candidates = take(Q);
-    rs.n_finished = take(Q); rs.completed = take(Q);
+    rs.n_finished = take(Q); (void)take(Q);
+    rs.completed = e->st_step.as<int>();                                          // read back after every step ...
+    rs.last_src = e->st_step.as<unsigned char>() + (size_t)Q * 4;                // ... together with the parent slots
     rs.seed_lo = reinterpret_cast<unsigned int*>(take(Q)); rs.seed_hi = reinterpret_cast<unsigned int*>(take(Q));
     rs.fin_pos = take((size_t)Q * kMaxFinished); rs.fin_slot = take((size_t)Q * kMaxFinished);
     SeqState& ss = e->ss;
@@ -280,7 +293,7 @@ int bw_engine_finalize(bw_engine* e) {
     }
     BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_init), (size_t)Q * kInitRecInts * 4));
     e->d_init.alloc((size_t)Q * kInitRecInts * 4);
-    BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_flags), (size_t)Q * 4));
+    BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_flags), e->step_out_bytes));
     e->h_fin_bytes = fin_blob_bytes(e) * (size_t)Q;
     BW_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->h_fin), e->h_fin_bytes));
     e->d_fin.alloc(e->h_fin_bytes);
@@ -352,6 +365,8 @@ int bw_engine_stats(bw_engine* e, int64_t* out, int32_t n) {
   v[BW_STAT_DECODE_STEPS] = e->stat_steps; v[BW_STAT_ROWS] = e->stat_rows; v[BW_STAT_WINDOWS] = e->stat_windows;
   v[BW_STAT_MAX_SEGMENTS] = e->Q; v[BW_STAT_MAX_SEQUENCES] = e->S; v[BW_STAT_ENCODER_BATCHES] = e->stat_enc_batches;
   v[BW_STAT_H2D_BYTES] = e->stat_h2d; v[BW_STAT_D2H_BYTES] = e->stat_d2h;
+  v[BW_STAT_KV_PAGES_TOTAL] = e->n_pages; v[BW_STAT_KV_PAGES_IN_USE] = e->stat_pages_in_use; v[BW_STAT_KV_PAGES_PEAK] = e->stat_pages_peak;
+  v[BW_STAT_KV_PAGE_BYTES] = (int64_t)e->page_bytes;
   for (int i = 0; i < n && i < BW_STAT_COUNT; ++i) out[i] = v[i];
   BW_API_END
 }

@@ -1,8 +1,9 @@
 // Attention kernels (head dim 64 for every Whisper size).
 //  * attn_encoder_simt : non-causal encoder self-attention, SIMT online softmax (fp32 validation mode
 //    and cross-check for the tcgen05 kernel in attention_tc.cu).
-//  * dec_self_attention : one query per live hypothesis over its paged self-KV (page = 1 token; the
-//    beam ancestry table `anc` redirects each position to the beam slot that wrote it).
+//  * dec_self_attention : one query per live hypothesis over its paged self-KV (pages of 16 positions per
+//    hypothesis slot behind a page table; the beam ancestry table `anc` redirects each position to the beam
+//    slot that wrote it).
 //  * dec_cross_attention: the decoder step's HBM-bound kernel -- streams the cached encoder K/V of a
 //    segment ONCE for all beams of that segment (NQ queries share each 16-byte load), split along T.
 // Upstream: whisper/model.py MultiHeadAttention.qkv_attention (SDPA, scale 1/sqrt(64)).
@@ -156,7 +157,8 @@ template <> __device__ __forceinline__ void load_smem_vec<float>(const float* p,
 template <typename T>
 __global__ void __launch_bounds__(128)
 dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const int* __restrict__ row_bpos,
-                          const float* __restrict__ qkv, T* __restrict__ pool, long long unit_stride, int n_ctx,
+                          const int* __restrict__ row_page, const float* __restrict__ qkv, T* __restrict__ pool,
+                          long long page_stride, int n_ctx, int n_blocks, int n_units, const int* __restrict__ page_table,
                           const int* __restrict__ seq_first, const unsigned char* __restrict__ anc, int layer, int d,
                           T* __restrict__ out, unsigned long long* trace_buf) {
   constexpr int VEC = Vec16<T>::N, LPR = 64 / VEC, RPW = 32 / LPR;
@@ -164,6 +166,7 @@ dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict
   T* Ks = reinterpret_cast<T*>(self_smem);  // [kSelfChunk][64]
   T* Vs = Ks + kSelfChunk * 64;
   __shared__ float part[4][66];
+  __shared__ int s_pt[kMaxBeam * kMaxBlocks];  // page table rows of the request's beam slots
   unsigned long long* const trace = ((blockIdx.x | blockIdx.y) == 0 && threadIdx.x == 0) ? trace_buf : nullptr;
   trace_mark(trace, (3u << 24) | 1);
   pdl_trigger();
@@ -179,23 +182,33 @@ dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane % LPR, rg = lane / LPR;
   const int n = pos + 1;
+  // Page-table rows of the slots this hypothesis can descend from.  Entries that matter here (blocks holding positions
+  // < bpos) were published by EARLIER steps; this step's embed kernel rewrites at most the current block's entry with
+  // the value it already has, so reading them before the dependency wait is safe.
+  if (bpos > 0) {
+    const int nu = single ? 1 : min(kMaxBeam, n_units - first);
+    for (int i = threadIdx.x; i < nu * n_blocks; i += 128) s_pt[i] = page_table[(long long)first * n_blocks + i];
+    __syncthreads();
+  }
   auto stage_cached = [&](int c0, int cn) {
     for (int idx = threadIdx.x; idx < cn * 2 * LPR; idx += 128) {
       const int ch = idx % LPR, kv = (idx / LPR) & 1, tl = idx / (2 * LPR);
       const int t = c0 + tl;
-      if (t < bpos)
-        cp_async_16((kv ? Vs : Ks) + tl * 64 + ch * VEC, pool + (long long)(single ? first : first + my_anc[t]) * unit_stride +
-                                                               ((long long)(layer * 2 + kv) * n_ctx + t) * d + h * 64 + ch * VEC);
+      if (t < bpos) {
+        const int page = s_pt[(single ? 0 : my_anc[t]) * n_blocks + t / kPageTokens];
+        cp_async_16((kv ? Vs : Ks) + tl * 64 + ch * VEC, pool + (long long)page * page_stride +
+                                                               ((long long)(layer * 2 + kv) * kPageTokens + (t % kPageTokens)) * d + h * 64 + ch * VEC);
+      }
     }
   };
   stage_cached(0, min(kSelfChunk, n));
   pdl_wait();
   trace_mark(trace, (3u << 24) | 2);
   const float* qrow = qkv + (long long)r * 3 * d + h * 64;
-  // fused append: k/v of this row -> pool[unit s][layer][k|v][pos]
+  // fused append: k/v of this row -> its page [layer][k|v][pos % kPageTokens]
   {
     const int c = threadIdx.x & 63, kvsel = threadIdx.x >> 6;  // 0: k, 1: v
-    pool[(long long)s * unit_stride + ((long long)(layer * 2 + kvsel) * n_ctx + pos) * d + h * 64 + c] =
+    pool[(long long)row_page[r] * page_stride + ((long long)(layer * 2 + kvsel) * kPageTokens + (pos % kPageTokens)) * d + h * 64 + c] =
         from_f<T>(qrow[(1 + kvsel) * d + c]);
   }
   float qf[VEC];
@@ -475,7 +488,8 @@ template <typename T>
 void dec_self_attention(const DecRows& rows, const float* qkv, const SelfKV& kv, int layer, int d, int n_head, T* out,
                         cudaStream_t stream) {
   if (rows.n_rows <= 0) return;
-  BW_CHECK(kv.n_ctx <= 448, "n_text_ctx > 448 unsupported");
+  BW_CHECK(kv.n_ctx <= 448 && kv.n_blocks <= kMaxBlocks && kv.n_blocks * kPageTokens >= kv.n_ctx, "n_text_ctx > 448 unsupported");
+  BW_CHECK(rows.row_page && kv.page_table, "paged self-attention needs row_page and a page table");
   dim3 grid(n_head, rows.n_rows);
   constexpr int smem = 2 * kSelfChunk * 64 * (int)sizeof(T);
   static std::atomic<unsigned long long> attr_set{0};
@@ -485,8 +499,9 @@ void dec_self_attention(const DecRows& rows, const float* qkv, const SelfKV& kv,
     BW_CUDA(cudaFuncSetAttribute(dec_self_attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set.fetch_or(1ull << dev);
   }
-  launch_kernel(dec_self_attention_kernel<T>, grid, dim3(128), smem, stream, rows.row_seq, rows.row_pos, rows.row_bpos, qkv,
-                reinterpret_cast<T*>(kv.pool), kv.unit_stride, kv.n_ctx, kv.seq_first, kv.anc, layer, d, out, g_trace_dev);
+  launch_kernel(dec_self_attention_kernel<T>, grid, dim3(128), smem, stream, rows.row_seq, rows.row_pos, rows.row_bpos, rows.row_page, qkv,
+                reinterpret_cast<T*>(kv.pool), kv.page_stride, kv.n_ctx, kv.n_blocks, kv.n_units, kv.page_table, kv.seq_first, kv.anc,
+                layer, d, out, g_trace_dev);
   ++g_kernel_launches;
 }
 template void dec_self_attention<float>(const DecRows&, const float*, const SelfKV&, int, int, int, float*, cudaStream_t);

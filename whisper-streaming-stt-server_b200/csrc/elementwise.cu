@@ -110,13 +110,15 @@ __global__ void permute_conv_kernel(const float* __restrict__ src, T* __restrict
 template <typename T>
 __global__ void dec_embed_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos,
                                  const int* __restrict__ row_tok, const int* __restrict__ next_tok,
-                                 const T* __restrict__ tok_emb, const T* __restrict__ pos_emb, float* __restrict__ x, int d) {
+                                 const T* __restrict__ tok_emb, const T* __restrict__ pos_emb, float* __restrict__ x, int d,
+                                 const int* __restrict__ row_page, int* __restrict__ page_table, int n_blocks) {
   pdl_trigger();
   pdl_wait();
   const int r = blockIdx.x;
   int tok = row_tok[r];
   if (tok < 0) tok = next_tok[row_seq[r]];
   const int pos = row_pos[r];
+  if (threadIdx.x == 0 && page_table) page_table[row_seq[r] * n_blocks + pos / kPageTokens] = row_page[r];
   for (int c = threadIdx.x; c < d; c += blockDim.x)
     x[(long long)r * d + c] = to_f(tok_emb[(long long)tok * d + c]) + to_f(pos_emb[(long long)pos * d + c]);
 }
@@ -141,7 +143,8 @@ template <typename T>
 __global__ void dec_embed_ln_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos,
                                     const int* __restrict__ row_tok, const int* __restrict__ next_tok,
                                     const T* __restrict__ tok_emb, const T* __restrict__ pos_emb, float* __restrict__ x, int d,
-                                    bf16* __restrict__ xb, float2* __restrict__ stats) {
+                                    bf16* __restrict__ xb, float2* __restrict__ stats, const int* __restrict__ row_page,
+                                    int* __restrict__ page_table, int n_blocks) {
   extern __shared__ float embed_row[];
   pdl_trigger();
   pdl_wait();
@@ -149,6 +152,7 @@ __global__ void dec_embed_ln_kernel(const int* __restrict__ row_seq, const int* 
   int tok = row_tok[r];
   if (tok < 0) tok = next_tok[row_seq[r]];
   const int pos = row_pos[r];
+  if (threadIdx.x == 0 && page_table) page_table[row_seq[r] * n_blocks + pos / kPageTokens] = row_page[r];
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     const float v = to_f(tok_emb[(long long)tok * d + c]) + to_f(pos_emb[(long long)pos * d + c]);
     x[(long long)r * d + c] = v;
@@ -196,21 +200,6 @@ fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma, con
   }
 }
 
-template <typename T>
-__global__ void dec_kv_append_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const float* __restrict__ qkv,
-                                     T* __restrict__ pool, long long unit_stride, int n_ctx, int layer, int d) {
-  pdl_trigger();
-  pdl_wait();
-  const int r = blockIdx.x;
-  const int s = row_seq[r], pos = row_pos[r];
-  T* kdst = pool + (long long)s * unit_stride + ((long long)(layer * 2 + 0) * n_ctx + pos) * d;
-  T* vdst = pool + (long long)s * unit_stride + ((long long)(layer * 2 + 1) * n_ctx + pos) * d;
-  const float* src = qkv + (long long)r * 3 * d;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    kdst[c] = from_f<T>(src[d + c]);
-    vdst[c] = from_f<T>(src[2 * d + c]);
-  }
-}
 
 inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
@@ -277,25 +266,26 @@ template void permute_conv_weight<float>(const float*, float*, int, int, cudaStr
 template void permute_conv_weight<bf16>(const float*, bf16*, int, int, cudaStream_t);
 
 template <typename T>
-void dec_embed(const DecRows& rows, const int* next_tok, const T* tok_emb, const T* pos_emb, float* x, int d,
-               cudaStream_t stream) {
+void dec_embed(const DecRows& rows, const int* next_tok, const T* tok_emb, const T* pos_emb, float* x, int d, int* page_table,
+               int n_blocks, cudaStream_t stream) {
   if (rows.n_rows <= 0) return;
-  launch_kernel(dec_embed_kernel<T>, dim3(rows.n_rows), dim3(128), 0, stream, rows.row_seq, rows.row_pos, rows.row_tok, next_tok, tok_emb, pos_emb, x, d);
+  launch_kernel(dec_embed_kernel<T>, dim3(rows.n_rows), dim3(128), 0, stream, rows.row_seq, rows.row_pos, rows.row_tok, next_tok, tok_emb, pos_emb, x, d,
+                rows.row_page, rows.row_page ? page_table : nullptr, n_blocks);
   ++g_kernel_launches;
 }
-template void dec_embed<float>(const DecRows&, const int*, const float*, const float*, float*, int, cudaStream_t);
-template void dec_embed<bf16>(const DecRows&, const int*, const bf16*, const bf16*, float*, int, cudaStream_t);
+template void dec_embed<float>(const DecRows&, const int*, const float*, const float*, float*, int, int*, int, cudaStream_t);
+template void dec_embed<bf16>(const DecRows&, const int*, const bf16*, const bf16*, float*, int, int*, int, cudaStream_t);
 
 template <typename T>
 void dec_embed_ln(const DecRows& rows, const int* next_tok, const T* tok_emb, const T* pos_emb, float* x, int d, bf16* xb,
-                  float2* stats, cudaStream_t stream) {
+                  float2* stats, int* page_table, int n_blocks, cudaStream_t stream) {
   if (rows.n_rows <= 0) return;
   BW_CHECK(d % 64 == 0, "LayerNorm-fused decoder needs d % 64 == 0");
   launch_kernel(dec_embed_ln_kernel<T>, dim3(rows.n_rows), dim3(128), (size_t)d * 4, stream, rows.row_seq, rows.row_pos, rows.row_tok,
-                next_tok, tok_emb, pos_emb, x, d, xb, stats);
+                next_tok, tok_emb, pos_emb, x, d, xb, stats, rows.row_page, rows.row_page ? page_table : nullptr, n_blocks);
   ++g_kernel_launches;
 }
-template void dec_embed_ln<bf16>(const DecRows&, const int*, const bf16*, const bf16*, float*, int, bf16*, float2*, cudaStream_t);
+template void dec_embed_ln<bf16>(const DecRows&, const int*, const bf16*, const bf16*, float*, int, bf16*, float2*, int*, int, cudaStream_t);
 
 void rows_ln_partials(const float* x, int rows, int d, bf16* xb, float2* stats, cudaStream_t stream) {
   if (rows <= 0) return;
@@ -310,15 +300,5 @@ void fold_layernorm(const float* W, const float* gamma, const float* beta, const
   fold_ln_kernel<<<N, 256, 0, stream>>>(W, gamma, beta, bias, K, Wf, c1, c2);
   BW_CUDA(cudaGetLastError());
 }
-
-template <typename T>
-void dec_kv_append(const DecRows& rows, const float* qkv, const SelfKV& kv, int layer, int d, cudaStream_t stream) {
-  if (rows.n_rows <= 0) return;
-  launch_kernel(dec_kv_append_kernel<T>, dim3(rows.n_rows), dim3(128), 0, stream, rows.row_seq, rows.row_pos, qkv,
-                reinterpret_cast<T*>(kv.pool), kv.unit_stride, kv.n_ctx, layer, d);
-  ++g_kernel_launches;
-}
-template void dec_kv_append<float>(const DecRows&, const float*, const SelfKV&, int, int, cudaStream_t);
-template void dec_kv_append<bf16>(const DecRows&, const float*, const SelfKV&, int, int, cudaStream_t);
 
 }  // namespace bw

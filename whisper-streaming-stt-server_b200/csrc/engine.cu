@@ -24,6 +24,7 @@ __global__ void init_requests_kernel(const int* __restrict__ init, int n, ReqSta
     rs.n_beam[q] = G; rs.greedy[q] = r[2]; rs.sample_begin[q] = r[3]; rs.cur_len[q] = r[4]; rs.first_seq[q] = first_seq;
     rs.without_ts[q] = r[6]; rs.suppress_blank[q] = r[7]; rs.max_initial_ts[q] = r[8]; rs.max_candidates[q] = r[9];
     rs.n_finished[q] = 0; rs.completed[q] = 0; rs.no_speech_prob[q] = nanf("");
+    for (int j = 0; j < kMaxBeam; ++j) rs.last_src[q * kMaxBeam + j] = (unsigned char)j;
     rs.temperature[q] = __int_as_float(r[11]); rs.seed_lo[q] = (unsigned int)r[12]; rs.seed_hi[q] = (unsigned int)r[13];
     for (int j = 0; j < G; ++j) {
       const int s = first_seq + j;
@@ -209,8 +210,18 @@ struct Impl {
   // ---- one decoder step over `R` rows; control arrays already on the device ----
   struct StepCtl {
     int R = 0, n_groups = 0, max_group_rows = 1, n_lrows = 0;
-    const int *row_seq, *row_pos, *row_tok, *row_bpos, *grp_first, *grp_n, *grp_x, *lrow_src;
+    const int *row_seq, *row_pos, *row_tok, *row_bpos, *row_page, *grp_first, *grp_n, *grp_x, *lrow_src;
   };
+  SelfKV self_kv() const {
+    const auto& d = D();
+    SelfKV skv;
+    skv.pool = e->self_pool.p;
+    skv.page_stride = (long long)d.n_text_layer * 2 * kPageTokens * d.n_text_state;
+    skv.n_ctx = d.n_text_ctx; skv.n_blocks = e->n_blocks; skv.n_units = e->S;
+    skv.page_table = e->d_page_table.as<int>();
+    skv.seq_first = e->ss.seq_first; skv.anc = e->ss.anc[e->anc_cur];
+    return skv;
+  }
   void decoder_layers(const StepCtl& c, DecGroup& G) const {
     static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;
     PdlScope pdl(use_pdl && !std::is_same<T, float>::value);
@@ -219,14 +230,14 @@ struct Impl {
     cudaStream_t st = stream;
     DecRows rows;
     rows.n_rows = c.R; rows.row_seq = c.row_seq; rows.row_pos = c.row_pos; rows.row_tok = c.row_tok; rows.row_bpos = c.row_bpos;
+    rows.row_page = c.row_page;
     float* x = G.d_x.as<float>();
     if constexpr (std::is_same<T, bf16>::value) {
       if (e->fuse_ln) return decoder_layers_fused(c, G, rows);
     }
-    dec_embed<T>(rows, e->ss.next_tok, reinterpret_cast<const T*>(e->w.tok_emb), reinterpret_cast<const T*>(e->w.dec_pos), x, dm, st);
-    SelfKV skv;
-    skv.pool = e->self_pool.p; skv.unit_stride = (long long)L * 2 * d.n_text_ctx * dm; skv.n_ctx = d.n_text_ctx;
-    skv.seq_first = e->ss.seq_first; skv.anc = e->ss.anc[e->anc_cur];
+    dec_embed<T>(rows, e->ss.next_tok, reinterpret_cast<const T*>(e->w.tok_emb), reinterpret_cast<const T*>(e->w.dec_pos), x, dm,
+                 e->d_page_table.as<int>(), e->n_blocks, st);
+    const SelfKV skv = self_kv();
     CrossKV xkv;
     xkv.cache = e->cross_cache.p; xkv.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; xkv.T_enc = d.n_audio_ctx;
     xkv.n_slots = e->Q; xkv.n_layer = L;
@@ -272,10 +283,8 @@ struct Impl {
     bf16* xb = G.d_xb.as<bf16>();
     float2* lst = G.d_lnst.as<float2>();
     dec_embed_ln<bf16>(rows, e->ss.next_tok, reinterpret_cast<const bf16*>(e->w.tok_emb), reinterpret_cast<const bf16*>(e->w.dec_pos), x, dm,
-                       xb, lst, st);
-    SelfKV skv;
-    skv.pool = e->self_pool.p; skv.unit_stride = (long long)L * 2 * d.n_text_ctx * dm; skv.n_ctx = d.n_text_ctx;
-    skv.seq_first = e->ss.seq_first; skv.anc = e->ss.anc[e->anc_cur];
+                       xb, lst, e->d_page_table.as<int>(), e->n_blocks, st);
+    const SelfKV skv = self_kv();
     CrossKV xkv;
     xkv.cache = e->cross_cache.p; xkv.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; xkv.T_enc = d.n_audio_ctx;
     xkv.n_slots = e->Q; xkv.n_layer = L;
@@ -496,15 +505,15 @@ void engine_window_to_A1(bw_engine* e, const float* logmel, int ld, int n_real, 
   else Impl<bf16>(e).window_to_A1(logmel, ld, n_real, gmax, seek, seg, bi);
 }
 void engine_decoder_layers(bw_engine* e, DecGroup& G, int R, int n_groups, int max_group_rows, int n_lrows, const int* row_seq,
-                           const int* row_pos, const int* row_tok, const int* row_bpos, const int* grp_first, const int* grp_n,
-                           const int* grp_x, const int* lrow_src) {
+                           const int* row_pos, const int* row_tok, const int* row_bpos, const int* row_page, const int* grp_first,
+                           const int* grp_n, const int* grp_x, const int* lrow_src) {
   if (e->fp32) {
     Impl<float>::StepCtl c; c.R = R; c.n_groups = n_groups; c.max_group_rows = max_group_rows; c.n_lrows = n_lrows;
-    c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.row_bpos = row_bpos; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
+    c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.row_bpos = row_bpos; c.row_page = row_page; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
     Impl<float>(e, G.stream).decoder_layers(c, G);
   } else {
     Impl<bf16>::StepCtl c; c.R = R; c.n_groups = n_groups; c.max_group_rows = max_group_rows; c.n_lrows = n_lrows;
-    c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.row_bpos = row_bpos; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
+    c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.row_bpos = row_bpos; c.row_page = row_page; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
     Impl<bf16>(e, G.stream).decoder_layers(c, G);
   }
 }

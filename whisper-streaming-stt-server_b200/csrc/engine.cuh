@@ -157,6 +157,11 @@ struct Request {
   std::mutex mu;
   std::condition_variable cv;
   bool done = false;
+  // self-KV pages (scheduler thread only): page of (beam slot, block) or -1; per hypothesis and block, the set of beam
+  // slots whose pages its ancestry references (bit j = slot j) -- what the page collector works from
+  std::vector<int> pages;
+  std::vector<unsigned char> ref_mask;
+  int pages_reserved = 0, n_blocks_max = 0;
   // runtime
   int q = -1, first_seq = -1, G = 1, cur_len = 0, steps = 0;
   bool prefilled = false;
@@ -203,13 +208,21 @@ struct bw_engine {
   // pools
   int Q = 0, S = 0, Be = 0, R_max = 0, LR_max = 0;
   bw::DevBuf cross_cache, self_pool;
+  // paged self-KV: n_pages pages of kPageTokens positions ([L][2][kPageTokens][d] each), page table on the device,
+  // free list + reservations on the host (scheduler thread)
+  int n_pages = 0, n_blocks = 0;
+  size_t page_bytes = 0;
+  bw::DevBuf d_page_table;
+  std::vector<int> free_pages;
+  int pages_reserved = 0;
+  std::atomic<long long> stat_pages_in_use{0}, stat_pages_peak{0};
   // encoder activations
   bw::DevBuf A1, y1, A2, enc_x, enc_xn, enc_qkv, enc_att, enc_h, enc_out;
   // decoder activations: one working set per request group
   bw::DecGroup grp[bw::kMaxGroups];
   bw::DevBuf d_lang_probs, d_lang_arg;
   // decoder state
-  bw::DevBuf st_int, st_float, st_anc0, st_anc1, st_tok, st_parent;
+  bw::DevBuf st_int, st_float, st_anc0, st_anc1, st_tok, st_parent, st_step;  // st_step: [Q] completed | [Q][kMaxBeam] last_src
   bw::ReqState rs{};
   bw::SeqState ss{};
   int anc_cur = 0;
@@ -217,7 +230,8 @@ struct bw_engine {
   bw::DevBuf d_init;
   int* h_init = nullptr;      // pinned
   size_t ctrl_ints = 0;
-  int* h_flags = nullptr;     // pinned [Q] completed flags
+  int* h_flags = nullptr;     // pinned copy of st_step: [Q] completed flags, then [Q][kMaxBeam] parent slots (bytes)
+  size_t step_out_bytes = 0;
   unsigned char* h_fin = nullptr;  // pinned scratch for finalisation
   bw::DevBuf d_fin;                // device side of it (gather_final_kernel packs finished requests here)
   size_t h_fin_bytes = 0;

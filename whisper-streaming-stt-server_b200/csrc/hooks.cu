@@ -146,6 +146,16 @@ int bw_bench_encoder(bw_engine* e, int32_t batch, int32_t iters, float* ms_out, 
 namespace {
 // Synthetic resident decode: `n_segments` windows x `n_group` hypotheses, positions [start_len, start_len + n_steps).
 // Same launches, control upload and per-step completion read-back as the scheduler's decode_step().
+// pages of the synthetic decode: hypothesis slot u, block b -> page u * nb + b (the engine is idle: every page is free)
+int synthetic_pages(bw_engine* e, int n_segments, int n_group, int max_len) {
+  const int nb = kv_blocks_for(max_len);
+  BW_CHECK((long long)n_segments * n_group * nb <= e->n_pages, "synthetic decode exceeds the self-KV page pool");
+  std::vector<int> pt((size_t)e->S * e->n_blocks, 0);
+  for (int u = 0; u < n_segments * n_group; ++u)
+    for (int b = 0; b < nb; ++b) pt[(size_t)u * e->n_blocks + b] = u * nb + b;
+  BW_CUDA(cudaMemcpy(e->d_page_table.p, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice));
+  return nb;
+}
 void synthetic_init(bw_engine* e, int n_segments, int n_group, int start_len) {
   for (int i = 0; i < n_segments; ++i) {
     int* rec = e->h_init + i * kInitRecInts;
@@ -158,7 +168,7 @@ void synthetic_init(bw_engine* e, int n_segments, int n_group, int start_len) {
   BW_CUDA(cudaStreamSynchronize(e->stream));
 }
 // same grouping, launches, control upload and per-step completion read-back as the scheduler's decode_step()
-void synthetic_step(bw_engine* e, Ctl* ctls, int n_segments, int n_group, int cur) {
+void synthetic_step(bw_engine* e, Ctl* ctls, int n_segments, int n_group, int cur, int nb) {
   const int ng = choose_groups(n_segments);
   for (int g = 0; g < ng; ++g) ctls[g].reset();
   for (int i = 0; i < n_segments; ++i) {
@@ -168,17 +178,18 @@ void synthetic_step(bw_engine* e, Ctl* ctls, int n_segments, int n_group, int cu
     c.act_req[c.NA] = i; c.act_first[c.NA] = c.SR; c.act_force[c.NA] = -1; ++c.NA;
     for (int j = 0; j < n_group; ++j) {
       c.row_seq[c.R] = i * n_group + j; c.row_pos[c.R] = cur - 1; c.row_tok[c.R] = -1; c.row_bpos[c.R] = cur - 1;
+      c.row_page[c.R] = (i * n_group + j) * nb + (cur - 1) / kPageTokens;
       c.lrow_src[c.LR] = c.R; c.srow_lrow[c.SR] = c.LR; c.srow_req[c.SR] = i; c.srow_seq[c.SR] = i * n_group + j;
       ++c.R; ++c.LR; ++c.SR;
     }
   }
   for (int g = 0; g < ng; ++g) enqueue_group_step(e, e->grp[g], ctls[g]);
   if (ng == 1) {
-    BW_CUDA(cudaMemcpyAsync(e->h_flags, e->rs.completed, (size_t)e->Q * 4, cudaMemcpyDeviceToHost, e->grp[0].stream));
+    BW_CUDA(cudaMemcpyAsync(e->h_flags, e->st_step.p, e->step_out_bytes, cudaMemcpyDeviceToHost, e->grp[0].stream));
     BW_CUDA(cudaStreamSynchronize(e->grp[0].stream));
   } else {
     for (int g = 0; g < ng; ++g) BW_CUDA(cudaStreamSynchronize(e->grp[g].stream));
-    BW_CUDA(cudaMemcpyAsync(e->h_flags, e->rs.completed, (size_t)e->Q * 4, cudaMemcpyDeviceToHost, e->stream));
+    BW_CUDA(cudaMemcpyAsync(e->h_flags, e->st_step.p, e->step_out_bytes, cudaMemcpyDeviceToHost, e->stream));
     BW_CUDA(cudaStreamSynchronize(e->stream));
   }
   e->anc_cur ^= 1;
@@ -203,17 +214,19 @@ int bw_bench_decoder_step(bw_engine* e, int32_t n_segments, int32_t n_group, int
   BW_CHECK(e->live.empty(), "engine busy");
   SynCtls sc(e);
   fill_cross_cache(e, n_segments);
+  BW_CHECK(e->stat_pages_in_use == 0, "engine busy");
+  const int nb = synthetic_pages(e, n_segments, n_group, context_len + iters + 2);
   {
-    const long long n = (long long)n_segments * n_group * (long long)(e->self_pool.bytes / e->S) / (e->fp32 ? 4 : 2);
+    const long long n = (long long)n_segments * n_group * nb * (long long)(e->page_bytes / (e->fp32 ? 4 : 2));
     if (e->fp32) fill_random<float>(e->self_pool.as<float>(), n, 0x5e1full, 1.f, e->stream);
     else fill_random<bf16>(e->self_pool.as<bf16>(), n, 0x5e1full, 1.f, e->stream);
   }
   synthetic_init(e, n_segments, n_group, context_len);
   int cur = context_len;
-  synthetic_step(e, sc.c, n_segments, n_group, cur++);
+  synthetic_step(e, sc.c, n_segments, n_group, cur++, nb);
   EvTimer t(e->stream);  // e->stream is idle here and receives the completion read-back of every step
   t.start();
-  for (int i = 0; i < iters; ++i) synthetic_step(e, sc.c, n_segments, n_group, cur++);
+  for (int i = 0; i < iters; ++i) synthetic_step(e, sc.c, n_segments, n_group, cur++, nb);
   *ms_out = t.stop_ms() / iters;
   const double ts = e->fp32 ? 4 : 2, d = e->dims.n_text_state, L = e->dims.n_text_layer, V = e->dims.n_vocab;
   const double S = (double)n_segments * n_group;
@@ -244,6 +257,8 @@ int bw_bench_pipeline(bw_engine* e, const float* pcm_host, const int64_t* offset
   for (int i = 0; i < n_segments; ++i)
     BW_CUDA(cudaMemcpyAsync(bufs[i].pcm, pcm_host + offsets[i], (size_t)lengths[i] * 4, cudaMemcpyHostToDevice, e->stream));
   BW_CUDA(cudaStreamSynchronize(e->stream));
+  BW_CHECK(e->stat_pages_in_use == 0, "engine busy");
+  const int nb = synthetic_pages(e, n_segments, n_group, 3 + n_steps + 1);
   SynCtls sc(e);
   auto frames = [&](int i, int& total, int& n_real, int& seg) {
     total = (int)((lengths[i] + 480000) / 160);
@@ -269,7 +284,7 @@ int bw_bench_pipeline(bw_engine* e, const float* pcm_host, const int64_t* offset
     for (int i = 0; i < nb; ++i) engine_cross_kv(e, i, s0 + i);
   }
   synthetic_init(e, n_segments, n_group, 3);
-  for (int i = 0; i < n_steps; ++i) synthetic_step(e, sc.c, n_segments, n_group, 3 + i);
+  for (int i = 0; i < n_steps; ++i) synthetic_step(e, sc.c, n_segments, n_group, 3 + i, nb);
   *ms_out = t.stop_ms();
   {
     std::lock_guard<std::mutex> cg(e->call_mu);
@@ -392,16 +407,20 @@ int bw_test_dec_cross_attention(const void* cache, int32_t n_slots, int32_t n_la
 }
 
 int bw_test_dec_self_attention(int32_t n_rows, const int32_t* row_seq, const int32_t* row_pos, const int32_t* row_bpos,
-                               const float* qkv, void* pool, int64_t unit_stride, int32_t n_ctx, const int32_t* seq_first,
-                               const uint8_t* anc, int32_t layer, int32_t d, int32_t n_head, void* out, void* stream) {
+                               const int32_t* row_page, const float* qkv, void* pool, int32_t n_layer, int32_t n_ctx, int32_t n_units,
+                               const int32_t* page_table, const int32_t* seq_first, const uint8_t* anc, int32_t layer, int32_t d,
+                               int32_t n_head, void* out, void* stream) {
   BW_API_BEGIN
-  BW_CHECK(row_seq && row_pos && row_bpos && qkv && pool && seq_first && anc && out, "null argument");
-  BW_CHECK(n_rows >= 1 && d == 64 * n_head && n_ctx >= 1 && layer >= 0, "bad geometry");
+  BW_CHECK(row_seq && row_pos && row_bpos && row_page && qkv && pool && page_table && seq_first && anc && out, "null argument");
+  BW_CHECK(n_rows >= 1 && d == 64 * n_head && n_ctx >= 1 && layer >= 0 && layer < n_layer && n_units >= 1, "bad geometry");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   DecRows rows;
   rows.n_rows = n_rows; rows.row_seq = row_seq; rows.row_pos = row_pos; rows.row_bpos = row_bpos; rows.row_tok = nullptr;
+  rows.row_page = row_page;
   SelfKV kv;
-  kv.pool = pool; kv.unit_stride = unit_stride; kv.n_ctx = n_ctx; kv.seq_first = seq_first; kv.anc = anc;
+  kv.pool = pool; kv.page_stride = (long long)n_layer * 2 * kPageTokens * d; kv.n_ctx = n_ctx;
+  kv.n_blocks = (n_ctx + kPageTokens - 1) / kPageTokens; kv.n_units = n_units; kv.page_table = page_table;
+  kv.seq_first = seq_first; kv.anc = anc;
   dec_self_attention<bf16>(rows, qkv, kv, layer, d, n_head, reinterpret_cast<bf16*>(out), st);
   BW_CUDA(cudaStreamSynchronize(st));
   BW_API_END

@@ -54,6 +54,10 @@ template <typename T>
 void attn_encoder_simt(const T* qkv, T* out, int batch, int T_len, int n_head, cudaStream_t stream);
 void attn_encoder_tc(const bf16* qkv, bf16* out, int batch, int T_len, int n_head, cudaStream_t stream);
 
+constexpr int kMaxBeam = 8;           // beams per request (n_group)
+constexpr int kPageTokens = 16;       // positions per page of the self-attention KV pool
+constexpr int kMaxBlocks = 28;        // pages per hypothesis at n_text_ctx = 448
+
 // Decoder row descriptors (one row = one (sequence, position) token fed through the decoder step)
 struct DecRows {
   int n_rows = 0;
@@ -61,38 +65,43 @@ struct DecRows {
   const int* row_pos = nullptr;   // [R] position of the row's token in its sequence
   const int* row_tok = nullptr;   // [R] token id, or -1: take next_tok[row_seq]
   const int* row_bpos = nullptr;  // [R] position of the first row of this sequence fed in THIS step (<= row_pos)
+  const int* row_page = nullptr;  // [R] page of the self-KV pool that receives this row's k / v (every layer)
 };
 
-// x[r] = E[tok] + pos_emb[pos]  (fp32 residual stream)
+// x[r] = E[tok] + pos_emb[pos]  (fp32 residual stream).  First kernel of a decoder step: it also publishes the step's
+// page assignments, page_table[row_seq * n_blocks + row_pos / kPageTokens] = row_page (page_table may be null).
 template <typename T>
-void dec_embed(const DecRows& rows, const int* next_tok, const T* tok_emb, const T* pos_emb, float* x, int d,
-               cudaStream_t stream);
+void dec_embed(const DecRows& rows, const int* next_tok, const T* tok_emb, const T* pos_emb, float* x, int d, int* page_table,
+               int n_blocks, cudaStream_t stream);
 
 // ---- decoder LayerNorm fusion (bf16 tensor-core mode): see gemm.cuh / gemm_tc_rows ----
 // embedding rows + their bf16 copy + per-64-column LayerNorm partials (the first layer's consumer GEMM reads them)
 template <typename T>
 void dec_embed_ln(const DecRows& rows, const int* next_tok, const T* tok_emb, const T* pos_emb, float* x, int d, bf16* xb,
-                  float2* stats, cudaStream_t stream);
+                  float2* stats, int* page_table, int n_blocks, cudaStream_t stream);
 void rows_ln_partials(const float* x, int rows, int d, bf16* xb, float2* stats, cudaStream_t stream);
 // Wf = bf16(W * gamma), c1 = rowsum(Wf), c2 = W.beta + bias   (W fp32 [N, K])
 void fold_layernorm(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K, bf16* Wf, float* c1,
                     float* c2, cudaStream_t stream);
 
-// Self-attention KV pool: unit u (= sequence slot) holds [L][2][n_ctx][d] of one hypothesis slot.
-// Beams of one request occupy adjacent units starting at seq_first[s]; the key/value of sequence s at
-// position t lives in unit seq_first[s] + anc[s][t] (beam reordering never copies K/V, it rewrites anc).
+// Paged self-attention KV pool.  A page holds kPageTokens consecutive positions of ONE hypothesis slot for every layer:
+// [L][2 (k | v)][kPageTokens][d].  page_table[u * n_blocks + t / kPageTokens] = page of slot u's block; pages are handed
+// out by the scheduler (host free list; memory follows the tokens in use) and published by the step's embed kernel.
+// Beams of one request occupy adjacent slots starting at seq_first[s]; the key / value of hypothesis s at position t
+// lives in slot seq_first[s] + anc[s][t] (beam reordering never copies K/V, it rewrites the ancestry row; pages no
+// surviving hypothesis references any more go back to the free list).
 struct SelfKV {
   void* pool = nullptr;                // T*
-  long long unit_stride = 0;           // elements per unit = L*2*n_ctx*d
+  long long page_stride = 0;           // elements per page = L * 2 * kPageTokens * d
   int n_ctx = 448;
+  int n_blocks = kMaxBlocks;           // ceil(n_ctx / kPageTokens)
+  int n_units = 0;                     // hypothesis slots behind page_table
+  const int* page_table = nullptr;     // [n_units][n_blocks]
   const int* seq_first = nullptr;      // [S] first sequence slot of the owning request
   const unsigned char* anc = nullptr;  // [S][n_ctx] beam slot holding position t (current ping-pong buffer)
 };
-// scatter this step's k/v (from the fp32 qkv rows [R, 3d]) into the pool for `layer`
-template <typename T>
-void dec_kv_append(const DecRows& rows, const float* qkv, const SelfKV& kv, int layer, int d, cudaStream_t stream);
 // out[r] = softmax(q_r . K[0..pos_r]) V   (head dim 64); q = first d columns of the fp32 qkv rows.
-// Also appends this step's k/v to the pool (the separate dec_kv_append launch is no longer needed).
+// Also appends this step's k/v (columns d..3d of the row) to the row's page.
 template <typename T>
 void dec_self_attention(const DecRows& rows, const float* qkv, const SelfKV& kv, int layer, int d, int n_head, T* out,
                         cudaStream_t stream);
@@ -121,7 +130,6 @@ struct TokenTables {
   const unsigned int* suppress_bits = nullptr;  // [ceil(V/32)] bit set = SuppressTokens id
 };
 
-constexpr int kMaxBeam = 8;           // beams per request (n_group)
 constexpr int kMaxCand = kMaxBeam + 1;
 constexpr int kMaxFinished = 16;
 constexpr int kInitRecInts = 16;      // admission record (init_requests_kernel input), ints per request
@@ -145,6 +153,7 @@ struct ReqState {
   int* fin_pos;         // [Q][kMaxFinished] position of last token before EOT
   int* fin_slot;        // [Q][kMaxFinished] beam slot holding that token
   int* completed;       // out: all candidates collected
+  unsigned char* last_src;  // out [Q][kMaxBeam]: beam slot each surviving hypothesis descended from in the last update
   float* no_speech_prob;
   int* tok;             // [Q][n_ctx][kMaxBeam] token written at (position, slot)
   unsigned char* parent;  // [Q][n_ctx][kMaxBeam] slot of the predecessor token

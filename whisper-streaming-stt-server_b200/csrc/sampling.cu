@@ -352,6 +352,7 @@ beam_update_kernel(const int* __restrict__ active_req, const int* __restrict__ r
         rs.parent[((long long)q * n_ctx + npos) * kMaxBeam + j] = anc_c[(long long)(first_seq + src) * n_ctx + pos];
       }
       new_src[j] = src;
+      rs.last_src[q * kMaxBeam + j] = (unsigned char)src;
     }
     n_new = saved;
     rs.cur_len[q] = cur_len + 1;

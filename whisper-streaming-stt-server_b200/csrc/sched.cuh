@@ -19,8 +19,8 @@ void engine_encoder_forward(bw_engine* e, int nb);
 void engine_cross_kv(bw_engine* e, int bi, int q);
 void engine_window_to_A1(bw_engine* e, const float* logmel, int ld, int n_real, const int* gmax, int seek, int seg, int bi);
 void engine_decoder_layers(bw_engine* e, DecGroup& G, int R, int n_groups, int max_group_rows, int n_lrows, const int* row_seq,
-                           const int* row_pos, const int* row_tok, const int* row_bpos, const int* grp_first, const int* grp_n,
-                           const int* grp_x, const int* lrow_src);
+                           const int* row_pos, const int* row_tok, const int* row_bpos, const int* row_page, const int* grp_first,
+                           const int* grp_n, const int* grp_x, const int* lrow_src);
 void engine_init_requests(bw_engine* e, const int* init_dev, int n);
 void engine_fold_layernorms(bw_engine* e);
 void engine_gather_final(bw_engine* e, const int* list_dev, int n, int blob_bytes, unsigned char* out_dev);
@@ -38,7 +38,7 @@ struct DeviceGuard {
 
 // ---- per-group control block (ints), mirrored host (pinned) / device ----
 struct Ctl {
-  int *row_seq, *row_pos, *row_tok, *row_bpos, *grp_first, *grp_n, *grp_x, *lrow_src, *srow_lrow, *srow_req, *srow_seq, *act_req,
+  int *row_seq, *row_pos, *row_tok, *row_bpos, *row_page, *grp_first, *grp_n, *grp_x, *lrow_src, *srow_lrow, *srow_req, *srow_seq, *act_req,
       *act_first, *act_force, *ns_lrow, *ns_req;
   int* base = nullptr;
   size_t total = 0;
@@ -48,7 +48,7 @@ struct Ctl {
     base = b;
     int* p = b;
     auto take = [&](size_t n) { int* r = p; p += n; return r; };
-    row_seq = take(Rm); row_pos = take(Rm); row_tok = take(Rm); row_bpos = take(Rm);
+    row_seq = take(Rm); row_pos = take(Rm); row_tok = take(Rm); row_bpos = take(Rm); row_page = take(Rm);
     grp_first = take(Rm); grp_n = take(Rm); grp_x = take(Rm);
     lrow_src = take(LRm); srow_lrow = take(LRm); srow_req = take(LRm); srow_seq = take(LRm);
     act_req = take(Q); act_first = take(Q); act_force = take(Q); ns_lrow = take(Q); ns_req = take(Q);
@@ -61,6 +61,10 @@ struct Ctl {
 void enqueue_group_step(bw_engine* e, DecGroup& G, Ctl& c);
 int choose_groups(int n_segments);
 void scheduler_main(bw_engine* e);
+// self-KV page pool (host free list; scheduler thread / synthetic benches only)
+int kv_blocks_for(int n_tokens);                       // pages one hypothesis needs for n_tokens positions
+int kv_page_of(bw_engine* e, Request* r, int slot, int block);  // the request's page for (beam slot, block), allocated on demand
+void kv_release(bw_engine* e, Request* r);             // every page + the reservation of a finished request
 int submit_and_wait(bw_engine* e, Request& r);
 // one host thread hands a whole batch to the scheduler and waits for every request of it
 int submit_many_and_wait(bw_engine* e, const std::vector<Request*>& rs);

@@ -25,7 +25,7 @@ void enqueue_group_step_eager(bw_engine* e, DecGroup& G, Ctl& c) {
   auto dev = [&](int* h) { return dbase + (h - c.base); };
   BW_CUDA(cudaMemcpyAsync(dbase, c.base, c.total * 4, cudaMemcpyHostToDevice, G.stream));
   engine_decoder_layers(e, G, c.R, c.NG, c.max_grp, c.LR, dev(c.row_seq), dev(c.row_pos), dev(c.row_tok), dev(c.row_bpos),
-                        dev(c.grp_first), dev(c.grp_n), dev(c.grp_x), dev(c.lrow_src));
+                        dev(c.row_page), dev(c.grp_first), dev(c.grp_n), dev(c.grp_x), dev(c.lrow_src));
   const float* logits = G.d_logits.as<float>();
   const int V = e->dims.n_vocab;
   static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;
@@ -94,9 +94,71 @@ int choose_groups(int n_segments) {
   return 1;  // measured: extra groups re-stream the weights and lengthen the step (profiles/r1_notes.md)
 }
 
+// ---- self-KV page pool -------------------------------------------------------------------------------------------
+// Host free list, scheduler thread only.  A request reserves its worst case at admission (every hypothesis holding every
+// block up to n_initial + sample_len positions), so an allocation during decoding can never fail and nothing is ever
+// preempted; pages are TAKEN only when a hypothesis slot first writes into a block and RETURNED as soon as no surviving
+// hypothesis' ancestry references them (collect_pages), so the pool in use follows the tokens in use.
+int kv_blocks_for(int n_tokens) { return (std::max(n_tokens, 1) + kPageTokens - 1) / kPageTokens; }
+
+int kv_page_of(bw_engine* e, Request* r, int slot, int block) {
+  int& pg = r->pages[(size_t)slot * e->n_blocks + block];
+  if (pg < 0) {
+    if (e->free_pages.empty()) throw std::runtime_error("self-KV page pool exhausted despite reservations (scheduler bug)");
+    pg = e->free_pages.back();
+    e->free_pages.pop_back();
+    const long long used = ++e->stat_pages_in_use;
+    if (used > e->stat_pages_peak) e->stat_pages_peak = used;
+  }
+  return pg;
+}
+
+void kv_release(bw_engine* e, Request* r) {
+  for (int& pg : r->pages)
+    if (pg >= 0) { e->free_pages.push_back(pg); pg = -1; --e->stat_pages_in_use; }
+  e->pages_reserved -= r->pages_reserved;
+  r->pages_reserved = 0;
+}
+
 namespace {
 
+// admission: pages the request may need at worst; sets up its (empty) page table and ancestry masks
+int kv_reserve(bw_engine* e, Request* r) {
+  const int n_init = (int)r->initial.size();
+  const int max_tokens = (r->kind == REQ_DECODE) ? std::min(e->dims.n_text_ctx, n_init + r->sample_len) : n_init;
+  r->n_blocks_max = kv_blocks_for(max_tokens);
+  return r->n_blocks_max * r->G;
+}
+void kv_begin(bw_engine* e, Request* r, int need) {
+  r->pages.assign((size_t)r->G * e->n_blocks, -1);
+  r->ref_mask.assign((size_t)r->G * e->n_blocks, 0);
+  r->pages_reserved = need;
+  e->pages_reserved += need;
+}
+
+// After a step: hypothesis j of request r descends from old hypothesis src[j] (beam_update's reorder).  Its ancestry
+// references, per block, the beam slots of its parent; slot j itself holds the position it is about to write.  Pages of
+// COMPLETE blocks that no surviving hypothesis references go back to the free list.
+void collect_pages(bw_engine* e, Request* r, const unsigned char* src, int next_pos) {
+  const int G = r->G, NB = e->n_blocks;
+  if (G > 1) {
+    unsigned char old[kMaxBeam * kMaxBlocks];
+    memcpy(old, r->ref_mask.data(), (size_t)G * NB);
+    for (int j = 0; j < G; ++j) memcpy(&r->ref_mask[(size_t)j * NB], &old[(size_t)std::min<int>(src[j], G - 1) * NB], NB);
+    const int cur_block = std::min(next_pos / kPageTokens, NB);
+    for (int b = 0; b < cur_block; ++b) {
+      unsigned live = 0;
+      for (int j = 0; j < G; ++j) live |= r->ref_mask[(size_t)j * NB + b];
+      for (int j = 0; j < G; ++j) {
+        int& pg = r->pages[(size_t)j * NB + b];
+        if (pg >= 0 && !(live >> j & 1u)) { e->free_pages.push_back(pg); pg = -1; --e->stat_pages_in_use; }
+      }
+    }
+  }
+}
+
 void release_slots(bw_engine* e, Request* r) {
+  kv_release(e, r);
   if (r->q >= 0) e->free_q.push_back(r->q);
   if (r->first_seq >= 0)
     for (int j = 0; j < r->G; ++j) e->seq_used[r->first_seq + j] = 0;
@@ -274,8 +336,12 @@ void decode_step(bw_engine* e, Ctl* ctls) {
       const int row0 = R;
       for (int t = 0; t < n_init; ++t) {
         ctl.row_seq[R] = r->first_seq; ctl.row_pos[R] = t; ctl.row_tok[R] = r->initial[t]; ctl.row_bpos[R] = 0;
+        ctl.row_page[R] = kv_page_of(e, r, 0, t / kPageTokens);
         ++R;
       }
+      // every hypothesis starts as a copy of slot 0's prefix
+      for (int j = 0; j < r->G; ++j)
+        for (int b = 0; b <= (n_init - 1) / kPageTokens; ++b) r->ref_mask[(size_t)j * e->n_blocks + b] |= 1u;
       for (int t = 0; t < n_init; t += 8) {
         ctl.grp_first[NG] = row0 + t; ctl.grp_n[NG] = std::min(8, n_init - t); ctl.grp_x[NG] = r->q;
         max_grp = std::max(max_grp, ctl.grp_n[NG]);
@@ -310,6 +376,8 @@ void decode_step(bw_engine* e, Ctl* ctls) {
       if (r->step_logits_out) forced_reqs.push_back({r, gi, LR, 1});
       for (int j = 0; j < r->G; ++j) {
         ctl.row_seq[R] = r->first_seq + j; ctl.row_pos[R] = r->cur_len - 1; ctl.row_tok[R] = -1; ctl.row_bpos[R] = r->cur_len - 1;
+        ctl.row_page[R] = kv_page_of(e, r, j, (r->cur_len - 1) / kPageTokens);  // slot j writes position cur_len - 1
+        r->ref_mask[(size_t)j * e->n_blocks + (r->cur_len - 1) / kPageTokens] |= (unsigned char)(1u << j);
         ctl.lrow_src[LR] = R;
         ctl.srow_lrow[SR] = LR; ctl.srow_req[SR] = r->q; ctl.srow_seq[SR] = r->first_seq + j;
         ++R; ++LR; ++SR;
@@ -335,15 +403,17 @@ void decode_step(bw_engine* e, Ctl* ctls) {
     BW_CUDA(cudaMemcpyAsync(s.r->step_logits_out + (size_t)s.r->steps * V, e->grp[s.grp].d_logits.as<float>() + (size_t)s.lrow0 * V,
                             (size_t)V * 4, cudaMemcpyDeviceToHost, e->grp[s.grp].stream));
   // completion flags: one D2H behind the step on the step's own stream, one host synchronisation per step
+  // completion flags + the beam reorder (parent slot of every surviving hypothesis, what the page collector needs)
   if (ng == 1) {
-    BW_CUDA(cudaMemcpyAsync(e->h_flags, e->rs.completed, (size_t)e->Q * 4, cudaMemcpyDeviceToHost, e->grp[0].stream));
+    BW_CUDA(cudaMemcpyAsync(e->h_flags, e->st_step.p, e->step_out_bytes, cudaMemcpyDeviceToHost, e->grp[0].stream));
     BW_CUDA(cudaStreamSynchronize(e->grp[0].stream));
   } else {
     for (int g = 0; g < ng; ++g) BW_CUDA(cudaStreamSynchronize(e->grp[g].stream));
-    BW_CUDA(cudaMemcpyAsync(e->h_flags, e->rs.completed, (size_t)e->Q * 4, cudaMemcpyDeviceToHost, e->stream));
+    BW_CUDA(cudaMemcpyAsync(e->h_flags, e->st_step.p, e->step_out_bytes, cudaMemcpyDeviceToHost, e->stream));
     BW_CUDA(cudaStreamSynchronize(e->stream));
   }
-  e->stat_d2h += (long long)e->Q * 4;
+  e->stat_d2h += (long long)e->step_out_bytes;
+  const unsigned char* h_src = reinterpret_cast<const unsigned char*>(e->h_flags) + (size_t)e->Q * 4;
   e->anc_cur ^= 1;
   e->stat_steps += 1;
   e->stat_rows += total_rows;
@@ -355,6 +425,7 @@ void decode_step(bw_engine* e, Ctl* ctls) {
     r->prefilled = true;
     r->cur_len += 1;
     r->steps += 1;
+    collect_pages(e, r, h_src + (size_t)r->q * kMaxBeam, r->cur_len - 1);
     if (e->h_flags[r->q] || r->steps >= r->sample_len || r->cur_len > d.n_text_ctx) done.push_back(r);
     else still.push_back(r);
   }
@@ -438,8 +509,16 @@ void scheduler_main(bw_engine* e) {
         const int n_init = (int)r->initial.size();
         const int need_l = (r->kind == REQ_LOGITS) ? n_init : 2;
         if (e->free_q.empty() || rows + n_init > e->R_max || lrows + need_l > e->LR_max) break;
+        const int need_pages = kv_reserve(e, r);
+        if (need_pages > e->n_pages) {  // can never be admitted: fail it instead of blocking the queue behind it
+          e->pending.pop_front();
+          finish_request(r, BW_ERR_NOMEM, "window needs more self-KV pages than the pool holds (raise max_kv_pages)");
+          continue;
+        }
+        if (e->pages_reserved + need_pages > e->n_pages) break;
         const int fs = find_seq_block(e, r->G);
         if (fs < 0) break;
+        kv_begin(e, r, need_pages);
         r->q = e->free_q.back();
         e->free_q.pop_back();
         r->first_seq = fs;

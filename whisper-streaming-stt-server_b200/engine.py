@@ -127,7 +127,7 @@ class Engine:
     """One weight copy + KV pools + scheduler thread on one GPU."""
 
     def __init__(self, dims: ModelDims, state: Dict[str, object], device_index: int = 0, compute: str = "bf16",
-                 max_segments: int = 0, max_sequences: int = 0, max_encoder_batch: int = 0, flags: int = 0):
+                 max_segments: int = 0, max_sequences: int = 0, max_encoder_batch: int = 0, flags: int = 0, max_kv_pages: int = 0):
         self.lib = L.load()
         if self.lib.bw_device_count() <= 0:
             raise L.B200WhisperError("no CUDA device visible: the b200_whisper backend has no CPU fallback")
@@ -141,7 +141,7 @@ class Engine:
         self._resamplers = set()
         cd = L.ModelDimsC(*[getattr(dims, f) for f, _ in L.ModelDimsC._fields_])
         cfg = L.EngineConfigC(device_index, L.BW_COMPUTE_FP32 if compute == "fp32" else L.BW_COMPUTE_BF16, max_segments,
-                              max_sequences, max_encoder_batch, flags)
+                              max_sequences, max_encoder_batch, flags, max_kv_pages)
         L.check(self.lib.bw_engine_create(C.byref(cd), C.byref(cfg), C.byref(self.handle)), "bw_engine_create")
         try:
             self._load(state)
