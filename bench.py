@@ -77,7 +77,11 @@ def parse_args():
                     help="length of the real-time streaming-session run reported under `streaming` (0 = skip)")
     ap.add_argument("--streaming-sessions", type=int, default=0, help="sessions per GPU in that run (0 = 3 x --sessions)")
     ap.add_argument("--cpu-threads", type=int, default=0)
-    args = ap.parse_args()
+    return resolve_config(ap.parse_args())
+
+
+def resolve_config(args):
+    """fill model / sessions / decode profile / window kind from BASELINE.json configs[args.config]"""
     cfg = CONFIGS[args.config]
     args.model = args.model or cfg["model"]
     args.sessions = args.sessions or cfg["sessions"]

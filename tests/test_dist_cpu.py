@@ -57,7 +57,8 @@ def test_reference_arm_is_rank0_only(monkeypatch):
     called = []
     monkeypatch.setattr(bench, "cpu_oracle_window", lambda *a, **k: called.append(1) or (1.0, 1))
     monkeypatch.setattr(bench, "emit", lambda line: called.append(line))
-    args = type("A", (), {"gpus": 2, "steps": 1, "warmup": 0, "model": "test-tiny", "cpu_threads": 1, "sessions": 128})()
+    args = bench.resolve_config(type("A", (), {"gpus": 2, "steps": 1, "warmup": 0, "model": "test-tiny", "cpu_threads": 1, "sessions": 128,
+                                               "config": 4})())
     monkeypatch.setenv("RANK", "1")
     monkeypatch.setenv("WORLD_SIZE", "2")
     bench.run_reference(args)
@@ -68,5 +69,6 @@ def test_reference_arm_is_rank0_only(monkeypatch):
     import json
 
     line = json.loads(called[1])
-    assert line["impl"] == "reference" and line["config"]["workload"] == bench.workload_name("test-tiny", 128) and line["n_gpus"] == 2
+    assert line["impl"] == "reference" and line["config"]["workload"] == bench.workload_name(args) and line["n_gpus"] == 2
+    assert "configs[4]" in line["config"]["workload"] and "faster_whisper_int8" in line
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
