@@ -545,26 +545,20 @@ void dec_cross_attention(const int* group_first_row, const int* group_n_rows, co
   while (n_split < kMaxSplit && base * n_split < 4 * 148) n_split *= 2;
   if (force_split > 0) n_split = std::min(force_split, (int)kMaxSplit);  // tests: any split count, not just powers of two
   if constexpr (std::is_same<T, bf16>::value) {
-    static const bool simt = getenv("B200W_XATTN_SIMT") != nullptr;
-    if (!simt && kv.n_slots > 0) {
-      dec_cross_attention_mma(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, kv.n_layer, layer, d, n_head, n_split,
-                              out, workspace, stream);
-      if (n_split > 1) {
-        dim3 grid(n_head, n_rows);
-        launch_kernel(dec_cross_combine_kernel<T>, grid, dim3(64), 0, stream, (const float*)workspace, n_split, d, out);
-        ++g_kernel_launches;
-      }
-      return;
-    }
+    // product mode: TMA + ldmatrix + mma.sync streaming kernel (attention_xdec.cu)
+    BW_CHECK(kv.n_slots > 0 && kv.n_layer > 0, "cross-attention needs the cache geometry (TMA map)");
+    dec_cross_attention_mma(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, kv.n_layer, layer, d, n_head, n_split,
+                            out, workspace, stream);
+  } else {
+    // fp32 validation mode: SIMT kernel with deterministic reduction order
+    if (max_group_rows <= 1) launch_cross<T, 1>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
+    else if (max_group_rows <= 2) launch_cross<T, 2>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
+    else if (max_group_rows <= 4) launch_cross<T, 4>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
+    else launch_cross<T, 8>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
   }
-  if (max_group_rows <= 1) launch_cross<T, 1>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
-  else if (max_group_rows <= 2) launch_cross<T, 2>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
-  else if (max_group_rows <= 4) launch_cross<T, 4>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
-  else launch_cross<T, 8>(group_first_row, group_n_rows, group_xslot, n_groups, q, kv, layer, d, n_head, n_split, out, workspace, stream);
   if (n_split > 1) {
     dim3 grid(n_head, n_rows);
-    dec_cross_combine_kernel<T><<<grid, 64, 0, stream>>>(workspace, n_split, d, out);
-    BW_CUDA(cudaGetLastError());
+    launch_kernel(dec_cross_combine_kernel<T>, grid, dim3(64), 0, stream, (const float*)workspace, n_split, d, out);
     ++g_kernel_launches;
   }
 }

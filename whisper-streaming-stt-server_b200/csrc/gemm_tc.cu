@@ -1218,10 +1218,8 @@ void gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   if (g.N <= 32) return launch<32, 5, 2>(g, stream);
   if (g.N <= 64) return launch<64, 4, 2>(g, stream);
   (void)mt;
-  // 128x128 with two CTAs per SM: one CTA's epilogue overlaps the other's main loop.  (The 128x256 / 1 CTA
-  // variant measured slower here -- profiles/r1a_summary.txt -- until the kernel is persistent.)
-  static const bool wide = getenv("B200W_GEMM_WIDE") != nullptr;
-  if (wide && g.N > 128 && mt * ((g.N + 255) / 256) * g.Z >= 2 * 148) return launch<256, 4, 1>(g, stream);
+  // 128x128 with two CTAs per SM: one CTA's epilogue overlaps the other's main loop.  (A 128x256 / 1 CTA
+  // variant measured slower here -- profiles/r1a_summary.txt; large GEMMs take the persistent pair kernel above.)
   return launch<128, 3, 2>(g, stream);
 }
 
