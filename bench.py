@@ -77,6 +77,8 @@ def parse_args():
                     help="length of the real-time streaming-session run reported under `streaming` (0 = skip)")
     ap.add_argument("--streaming-sessions", type=int, default=0, help="sessions per GPU in that run (0 = 3 x --sessions)")
     ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--wire-channels", type=int, default=-1,
+                    help="streams of the wire-level leg (unmodified server + its own grpc_load_test.py); 0 = skip, -1 = 64 at N = 1")
     return resolve_config(ap.parse_args())
 
 
@@ -246,6 +248,33 @@ def workload_name(args) -> str:
     if args.model != args.cfg["model"] or args.sessions != args.cfg["sessions"]:
         name += f" [overridden: model {args.model}, {args.sessions} sessions per GPU]"
     return name
+
+
+def wire_leg(args, channels: int):
+    """Secondary e2e: the UNMODIFIED reference server, started by b200_whisper.launcher with this backend and
+    the real engine, under the reference's own load generator tools/bench/grpc_load_test.py run unchanged (100 ms chunks in
+    real time; the server's VAD gate on over an energy stand-in for the absent Silero model so that its partial-decode
+    schedule runs).  The reference tree is not on the GPU box: tools/install_reference.sh puts it under baseline/_ref."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "wire_bench.py"), "--json", "--channels", str(channels), "--seconds", "10",
+           "--pool-size", str(channels), "--model", f"random:{args.model}:0:0.1", "--energy-vad", "--ready-timeout", "240",
+           "--decode-profile", args.cfg["profile"]]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=ROOT)
+        rep = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:  # noqa: BLE001 - the wire leg must never take the bench line down with it
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+    if "unavailable" in rep:
+        return rep
+    sm = rep.get("summary", {})
+    pick = lambda sec: {k: sm.get(sec, {}).get(k) for k in ("p50", "p95", "p99")}  # noqa: E731
+    return {"channels": channels, "audio_s_per_channel": rep["audio_s_per_channel"], "wall_s": rep["wall_s"],
+            "audio_s_per_s": sm.get("Info", {}).get("Audio-sec/sec"), "sessions": sm.get("Info", {}).get("Sessions"),
+            "failures": sm.get("Info", {}).get("Failures"), "responses": sm.get("Info", {}).get("Responses"),
+            "decode_inference_s": pick("Decode Inference"), "decode_queue_wait_s": pick("Decode Queue Wait"),
+            "decode_total_s": pick("Decode Total"), "decodes_per_session": pick("Decode Count"), "tail_latency_s": pick("Tail"),
+            "note": "unmodified server + grpc_load_test.py (reference tools/bench/grpc_load_test.py:742,1028-1052), real-time pacing: "
+                    "audio_s_per_s is bounded by channels x 1.0; latencies are the server's own stt-decode-* metadata; VAD gate on over "
+                    "an energy stand-in (silero_vad absent); the server process builds its own engine next to the bench's"}
 
 
 def cpu_sample_seconds(args) -> float:
@@ -422,6 +451,9 @@ def run_b200(args):
                                "sample": f"1 session x 1 window ({cs:.0f} s audio, full 30 s encoder pass + 224 decoder steps, beam "
                                          f"{args.profile['beam_size']}), fp32 torch on {cores} threads, {dt:.1f} s"}
     out["faster_whisper_int8"] = faster_whisper_row()
+    wire_channels = args.wire_channels if args.wire_channels >= 0 else (64 if world == 1 and args.windows != "chunk30" else 0)
+    if wire_channels > 0:
+        out["wire"] = wire_leg(args, wire_channels)
     emit(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

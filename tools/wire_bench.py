@@ -78,6 +78,7 @@ def main() -> None:
     ap.add_argument("--compute-type", default="bfloat16")
     ap.add_argument("--json", action="store_true", help="last stdout line = one JSON object with the parsed load-test summary")
     ap.add_argument("--server-log", default=None, help="file for the server's stdout/stderr (default: discarded)")
+    ap.add_argument("--ready-timeout", type=float, default=600.0, help="seconds to wait for the server's gRPC port")
     args, extra = ap.parse_known_args()
     extra = [a for a in extra if a != "--"]
     layout = reference_layout(args.server_root)
@@ -123,7 +124,7 @@ def main() -> None:
         import grpc
 
         protostubs.install(os.path.join(tree, "proto", "stt.proto"))
-        grpc.channel_ready_future(grpc.insecure_channel(f"127.0.0.1:{port}")).result(timeout=600)
+        grpc.channel_ready_future(grpc.insecure_channel(f"127.0.0.1:{port}")).result(timeout=args.ready_timeout)
         sys.argv = ["grpc_load_test.py", "--target", f"127.0.0.1:{port}", "--channels", str(args.channels), "--iterations", "1",
                     "--audio", wav, "--chunk-ms", "100", "--realtime", "--decode-profile", args.decode_profile, "--language", "en",
                     "--vad-mode", "continue", *extra]
