@@ -145,7 +145,7 @@ def _self_ref(qkv, pool_before, pt, rows, seq_first, anc, layer, d, n_head):
     return out
 
 
-def _run_self(rows, qkv, pool, pt, seq_first_dev_vals, anc, layer, d, n_head, n_ctx, n_layer):
+def _run_self(rows, qkv, pool, pt, seq_first_dev_vals, anc, layer, d, n_head, n_ctx, n_layer, max_ctx=None):
     lib = L.load()
     R = qkv.shape[0]
     out = torch.full((R, d), float("nan"), device=DEV, dtype=torch.bfloat16)
@@ -157,12 +157,13 @@ def _run_self(rows, qkv, pool, pt, seq_first_dev_vals, anc, layer, d, n_head, n_
     torch.cuda.synchronize()
     L.check(lib.bw_test_dec_self_attention(R, rs.data_ptr(), rp.data_ptr(), rb.data_ptr(), rpage.data_ptr(), qkv.data_ptr(), pool.data_ptr(),
                                            n_layer, n_ctx, pt.shape[0], pt_d.data_ptr(), sf.data_ptr(), anc_d.data_ptr(), layer, d, n_head,
-                                           out.data_ptr(), None), "bw_test_dec_self_attention")
+                                           max(rows["pos"]) + 1 if max_ctx is None else max_ctx, out.data_ptr(), None),
+            "bw_test_dec_self_attention")
     torch.cuda.synchronize()
     return out
 
 
-@pytest.mark.parametrize("ctx", [1, 100, 447])
+@pytest.mark.parametrize("ctx", [1, 31, 32, 63, 100, 447])  # staging of 32 / 64 / 128 positions per pass, 1 .. 4 passes
 @pytest.mark.parametrize("G", [1, 5, 8])
 def test_self_attention_bf16_cached_decode_through_ancestry(ctx, G):
     """one new token per hypothesis at position `ctx` (the step's row), `ctx` cached positions behind it.  G > 1: every
@@ -219,10 +220,12 @@ def test_self_attention_bf16_prefill_rows():
     anc = torch.zeros((S, n_ctx), dtype=torch.int64)
     flag = 0x40000000
     qkv = torch.randn((n_init + 3, 3 * d), device=DEV, generator=g)
-    out = _run_self(rows, qkv, pool, pt, [s | flag for s in range(S)], anc, layer, d, n_head, n_ctx, n_layer)
     ref = _self_ref(qkv, pool_before, pt, rows, list(range(S)), anc, layer, d, n_head)
-    r = _rel(out, ref)
-    assert r < 5e-3, f"prefill rel-L2 {r}"
+    for max_ctx in (None, 0):  # the exact longest context, and "unknown" (largest staging)
+        pool.copy_(pool_before)
+        out = _run_self(rows, qkv, pool, pt, [s | flag for s in range(S)], anc, layer, d, n_head, n_ctx, n_layer, max_ctx)
+        r = _rel(out, ref)
+        assert r < 5e-3, f"prefill rel-L2 {r}"
 
 
 # ---------------------------------------------------------------------------------------------------- sample_topk

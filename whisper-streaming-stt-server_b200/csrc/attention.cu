@@ -137,7 +137,8 @@ constexpr int kSingleBeamFlag = 0x40000000;  // set in seq_first[s] when the req
 // chunk in flight at once: the kernel is a pure HBM stream, 2*t*128 B per CTA), then consumed by 8-lane groups
 // with an online softmax; one shared-memory merge at the end.  (The first version walked the keys with dependent
 // global loads: 9 us per CTA and 2 waves at context 100 -- tools/trace_step.py.)
-constexpr int kSelfChunk = 128;  // positions staged per pass
+// positions staged per pass: 32 / 64 / 128, the smallest that covers the step's longest context (fewer bytes of shared
+// memory per CTA = more CTAs per SM: 6 at 128, 9 (register-limited) at 64 and below)
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -154,7 +155,7 @@ template <> __device__ __forceinline__ void load_smem_vec<float>(const float* p,
   f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
 }
 
-template <typename T>
+template <typename T, int kSelfChunk>
 __global__ void __launch_bounds__(128)
 dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const int* __restrict__ row_bpos,
                           const int* __restrict__ row_page, const float* __restrict__ qkv, T* __restrict__ pool,
@@ -474,6 +475,8 @@ __global__ void dec_cross_combine_kernel(const float* __restrict__ ws, int n_spl
 
 }  // namespace
 
+int dec_self_chunk(int max_ctx) { return (max_ctx > 0 && max_ctx <= 32) ? 32 : (max_ctx > 0 && max_ctx <= 64) ? 64 : 128; }
+
 template <typename T>
 void attn_encoder_simt(const T* qkv, T* out, int batch, int T_len, int n_head, cudaStream_t stream) {
   dim3 grid((T_len + 31) / 32, n_head, batch);
@@ -491,17 +494,22 @@ void dec_self_attention(const DecRows& rows, const float* qkv, const SelfKV& kv,
   BW_CHECK(kv.n_ctx <= 448 && kv.n_blocks <= kMaxBlocks && kv.n_blocks * kPageTokens >= kv.n_ctx, "n_text_ctx > 448 unsupported");
   BW_CHECK(rows.row_page && kv.page_table, "paged self-attention needs row_page and a page table");
   dim3 grid(n_head, rows.n_rows);
-  constexpr int smem = 2 * kSelfChunk * 64 * (int)sizeof(T);
+  const int chunk = dec_self_chunk(rows.max_ctx);
+  auto launch = [&](auto kern, int smem) {
+    launch_kernel(kern, grid, dim3(128), (size_t)smem, stream, rows.row_seq, rows.row_pos, rows.row_bpos, rows.row_page, qkv,
+                  reinterpret_cast<T*>(kv.pool), kv.page_stride, kv.n_ctx, kv.n_blocks, kv.n_units, kv.page_table, kv.seq_first, kv.anc,
+                  layer, d, out, g_trace_dev);
+  };
   static std::atomic<unsigned long long> attr_set{0};
   int dev = 0;
   BW_CUDA(cudaGetDevice(&dev));
   if (!(attr_set.load() >> dev & 1ull)) {
-    BW_CUDA(cudaFuncSetAttribute(dec_self_attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BW_CUDA(cudaFuncSetAttribute(dec_self_attention_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 64 * (int)sizeof(T)));
     attr_set.fetch_or(1ull << dev);
   }
-  launch_kernel(dec_self_attention_kernel<T>, grid, dim3(128), smem, stream, rows.row_seq, rows.row_pos, rows.row_bpos, rows.row_page, qkv,
-                reinterpret_cast<T*>(kv.pool), kv.page_stride, kv.n_ctx, kv.n_blocks, kv.n_units, kv.page_table, kv.seq_first, kv.anc,
-                layer, d, out, g_trace_dev);
+  if (chunk == 32) launch(dec_self_attention_kernel<T, 32>, 2 * 32 * 64 * (int)sizeof(T));
+  else if (chunk == 64) launch(dec_self_attention_kernel<T, 64>, 2 * 64 * 64 * (int)sizeof(T));
+  else launch(dec_self_attention_kernel<T, 128>, 2 * 128 * 64 * (int)sizeof(T));
   ++g_kernel_launches;
 }
 template void dec_self_attention<float>(const DecRows&, const float*, const SelfKV&, int, int, int, float*, cudaStream_t);

@@ -209,7 +209,7 @@ struct Impl {
 
   // ---- one decoder step over `R` rows; control arrays already on the device ----
   struct StepCtl {
-    int R = 0, n_groups = 0, max_group_rows = 1, n_lrows = 0;
+    int R = 0, n_groups = 0, max_group_rows = 1, n_lrows = 0, max_ctx = 0;
     const int *row_seq, *row_pos, *row_tok, *row_bpos, *row_page, *grp_first, *grp_n, *grp_x, *lrow_src;
   };
   SelfKV self_kv() const {
@@ -230,7 +230,7 @@ struct Impl {
     cudaStream_t st = stream;
     DecRows rows;
     rows.n_rows = c.R; rows.row_seq = c.row_seq; rows.row_pos = c.row_pos; rows.row_tok = c.row_tok; rows.row_bpos = c.row_bpos;
-    rows.row_page = c.row_page;
+    rows.row_page = c.row_page; rows.max_ctx = c.max_ctx;
     float* x = G.d_x.as<float>();
     if constexpr (std::is_same<T, bf16>::value) {
       if (e->fuse_ln) return decoder_layers_fused(c, G, rows);
@@ -504,15 +504,15 @@ void engine_window_to_A1(bw_engine* e, const float* logmel, int ld, int n_real, 
   if (e->fp32) Impl<float>(e).window_to_A1(logmel, ld, n_real, gmax, seek, seg, bi);
   else Impl<bf16>(e).window_to_A1(logmel, ld, n_real, gmax, seek, seg, bi);
 }
-void engine_decoder_layers(bw_engine* e, DecGroup& G, int R, int n_groups, int max_group_rows, int n_lrows, const int* row_seq,
+void engine_decoder_layers(bw_engine* e, DecGroup& G, int R, int n_groups, int max_group_rows, int n_lrows, int max_ctx, const int* row_seq,
                            const int* row_pos, const int* row_tok, const int* row_bpos, const int* row_page, const int* grp_first,
                            const int* grp_n, const int* grp_x, const int* lrow_src) {
   if (e->fp32) {
-    Impl<float>::StepCtl c; c.R = R; c.n_groups = n_groups; c.max_group_rows = max_group_rows; c.n_lrows = n_lrows;
+    Impl<float>::StepCtl c; c.R = R; c.n_groups = n_groups; c.max_group_rows = max_group_rows; c.n_lrows = n_lrows; c.max_ctx = max_ctx;
     c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.row_bpos = row_bpos; c.row_page = row_page; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
     Impl<float>(e, G.stream).decoder_layers(c, G);
   } else {
-    Impl<bf16>::StepCtl c; c.R = R; c.n_groups = n_groups; c.max_group_rows = max_group_rows; c.n_lrows = n_lrows;
+    Impl<bf16>::StepCtl c; c.R = R; c.n_groups = n_groups; c.max_group_rows = max_group_rows; c.n_lrows = n_lrows; c.max_ctx = max_ctx;
     c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.row_bpos = row_bpos; c.row_page = row_page; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
     Impl<bf16>(e, G.stream).decoder_layers(c, G);
   }

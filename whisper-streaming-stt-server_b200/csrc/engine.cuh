@@ -75,15 +75,16 @@ enum ReqKind { REQ_DECODE = 0, REQ_LANG = 1, REQ_LOGITS = 2 };
 // groups that run on their own streams: one group's latency-bound LayerNorm / skinny-GEMM chain executes
 // underneath another group's HBM-bound cross-attention.
 struct StepGraphKey {
-  int R, NG, LR, SR, NA, NNS, max_grp, anc;
+  int R, NG, LR, SR, NA, NNS, max_grp, anc, self_chunk;  // self_chunk: the self-attention launch geometry (dec_self_chunk)
   bool operator==(const StepGraphKey& o) const {
-    return R == o.R && NG == o.NG && LR == o.LR && SR == o.SR && NA == o.NA && NNS == o.NNS && max_grp == o.max_grp && anc == o.anc;
+    return R == o.R && NG == o.NG && LR == o.LR && SR == o.SR && NA == o.NA && NNS == o.NNS && max_grp == o.max_grp && anc == o.anc &&
+           self_chunk == o.self_chunk;
   }
 };
 struct StepGraphKeyHash {
   size_t operator()(const StepGraphKey& k) const {
     size_t h = 1469598103934665603ull;
-    for (int v : {k.R, k.NG, k.LR, k.SR, k.NA, k.NNS, k.max_grp, k.anc}) h = (h ^ (size_t)v) * 1099511628211ull;
+    for (int v : {k.R, k.NG, k.LR, k.SR, k.NA, k.NNS, k.max_grp, k.anc, k.self_chunk}) h = (h ^ (size_t)v) * 1099511628211ull;
     return h;
   }
 };

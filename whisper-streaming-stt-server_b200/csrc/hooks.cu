@@ -175,6 +175,7 @@ void synthetic_step(bw_engine* e, Ctl* ctls, int n_segments, int n_group, int cu
     Ctl& c = ctls[i % ng];
     c.grp_first[c.NG] = c.R; c.grp_n[c.NG] = n_group; c.grp_x[c.NG] = i; ++c.NG;
     c.max_grp = std::max(c.max_grp, n_group);
+    c.max_ctx = std::max(c.max_ctx, cur);
     c.act_req[c.NA] = i; c.act_first[c.NA] = c.SR; c.act_force[c.NA] = -1; ++c.NA;
     for (int j = 0; j < n_group; ++j) {
       c.row_seq[c.R] = i * n_group + j; c.row_pos[c.R] = cur - 1; c.row_tok[c.R] = -1; c.row_bpos[c.R] = cur - 1;
@@ -409,14 +410,14 @@ int bw_test_dec_cross_attention(const void* cache, int32_t n_slots, int32_t n_la
 int bw_test_dec_self_attention(int32_t n_rows, const int32_t* row_seq, const int32_t* row_pos, const int32_t* row_bpos,
                                const int32_t* row_page, const float* qkv, void* pool, int32_t n_layer, int32_t n_ctx, int32_t n_units,
                                const int32_t* page_table, const int32_t* seq_first, const uint8_t* anc, int32_t layer, int32_t d,
-                               int32_t n_head, void* out, void* stream) {
+                               int32_t n_head, int32_t max_ctx, void* out, void* stream) {
   BW_API_BEGIN
   BW_CHECK(row_seq && row_pos && row_bpos && row_page && qkv && pool && page_table && seq_first && anc && out, "null argument");
   BW_CHECK(n_rows >= 1 && d == 64 * n_head && n_ctx >= 1 && layer >= 0 && layer < n_layer && n_units >= 1, "bad geometry");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   DecRows rows;
   rows.n_rows = n_rows; rows.row_seq = row_seq; rows.row_pos = row_pos; rows.row_bpos = row_bpos; rows.row_tok = nullptr;
-  rows.row_page = row_page;
+  rows.row_page = row_page; rows.max_ctx = max_ctx;
   SelfKV kv;
   kv.pool = pool; kv.page_stride = (long long)n_layer * 2 * kPageTokens * d; kv.n_ctx = n_ctx;
   kv.n_blocks = (n_ctx + kPageTokens - 1) / kPageTokens; kv.n_units = n_units; kv.page_table = page_table;

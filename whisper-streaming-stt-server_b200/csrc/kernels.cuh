@@ -66,7 +66,9 @@ struct DecRows {
   const int* row_tok = nullptr;   // [R] token id, or -1: take next_tok[row_seq]
   const int* row_bpos = nullptr;  // [R] position of the first row of this sequence fed in THIS step (<= row_pos)
   const int* row_page = nullptr;  // [R] page of the self-KV pool that receives this row's k / v (every layer)
+  int max_ctx = 0;                // longest context (row_pos + 1) among the rows, 0 = unknown: sizes the self-attention staging
 };
+int dec_self_chunk(int max_ctx);  // positions the self-attention kernel stages per pass for that context (32 / 64 / 128)
 
 // x[r] = E[tok] + pos_emb[pos]  (fp32 residual stream).  First kernel of a decoder step: it also publishes the step's
 // page assignments, page_table[row_seq * n_blocks + row_pos / kPageTokens] = row_page (page_table may be null).

@@ -18,7 +18,7 @@ void engine_load_tensor(bw_engine* e, const bw_tensor_desc& t);
 void engine_encoder_forward(bw_engine* e, int nb);
 void engine_cross_kv(bw_engine* e, int bi, int q);
 void engine_window_to_A1(bw_engine* e, const float* logmel, int ld, int n_real, const int* gmax, int seek, int seg, int bi);
-void engine_decoder_layers(bw_engine* e, DecGroup& G, int R, int n_groups, int max_group_rows, int n_lrows, const int* row_seq,
+void engine_decoder_layers(bw_engine* e, DecGroup& G, int R, int n_groups, int max_group_rows, int n_lrows, int max_ctx, const int* row_seq,
                            const int* row_pos, const int* row_tok, const int* row_bpos, const int* row_page, const int* grp_first,
                            const int* grp_n, const int* grp_x, const int* lrow_src);
 void engine_init_requests(bw_engine* e, const int* init_dev, int n);
@@ -43,7 +43,7 @@ struct Ctl {
   int* base = nullptr;
   size_t total = 0;
   // fill counters of the step being built
-  int R = 0, NG = 0, LR = 0, SR = 0, NA = 0, NNS = 0, max_grp = 1;
+  int R = 0, NG = 0, LR = 0, SR = 0, NA = 0, NNS = 0, max_grp = 1, max_ctx = 0;
   void layout(int* b, int Rm, int LRm, int Q) {
     base = b;
     int* p = b;
@@ -54,7 +54,7 @@ struct Ctl {
     act_req = take(Q); act_first = take(Q); act_force = take(Q); ns_lrow = take(Q); ns_req = take(Q);
     total = (size_t)(p - b);
   }
-  void reset() { R = NG = LR = SR = NA = NNS = 0; max_grp = 1; }
+  void reset() { R = NG = LR = SR = NA = NNS = 0; max_grp = 1; max_ctx = 0; }
 };
 
 // scheduler.cu

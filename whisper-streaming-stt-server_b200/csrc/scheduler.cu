@@ -24,7 +24,7 @@ void enqueue_group_step_eager(bw_engine* e, DecGroup& G, Ctl& c) {
   int* dbase = G.d_ctrl.as<int>();
   auto dev = [&](int* h) { return dbase + (h - c.base); };
   BW_CUDA(cudaMemcpyAsync(dbase, c.base, c.total * 4, cudaMemcpyHostToDevice, G.stream));
-  engine_decoder_layers(e, G, c.R, c.NG, c.max_grp, c.LR, dev(c.row_seq), dev(c.row_pos), dev(c.row_tok), dev(c.row_bpos),
+  engine_decoder_layers(e, G, c.R, c.NG, c.max_grp, c.LR, c.max_ctx, dev(c.row_seq), dev(c.row_pos), dev(c.row_tok), dev(c.row_bpos),
                         dev(c.row_page), dev(c.grp_first), dev(c.grp_n), dev(c.grp_x), dev(c.lrow_src));
   const float* logits = G.d_logits.as<float>();
   const int V = e->dims.n_vocab;
@@ -45,7 +45,7 @@ void enqueue_group_step(bw_engine* e, DecGroup& G, Ctl& c) {
   e->stat_h2d += (long long)c.total * 4;
   static const bool use_graphs = getenv("B200W_NO_GRAPH") == nullptr;
   if (!use_graphs) return enqueue_group_step_eager(e, G, c);
-  const StepGraphKey key{c.R, c.NG, c.LR, c.SR, c.NA, c.NNS, c.max_grp, e->anc_cur};
+  const StepGraphKey key{c.R, c.NG, c.LR, c.SR, c.NA, c.NNS, c.max_grp, e->anc_cur, dec_self_chunk(c.max_ctx)};
   StepGraph& sg = G.graphs[key];
   sg.last_use = ++G.graph_clock;
   if (sg.exec) {
@@ -334,6 +334,7 @@ void decode_step(bw_engine* e, Ctl* ctls) {
     if (!r->prefilled) {
       const int n_init = (int)r->initial.size();
       const int row0 = R;
+      ctl.max_ctx = std::max(ctl.max_ctx, n_init);
       for (int t = 0; t < n_init; ++t) {
         ctl.row_seq[R] = r->first_seq; ctl.row_pos[R] = t; ctl.row_tok[R] = r->initial[t]; ctl.row_bpos[R] = 0;
         ctl.row_page[R] = kv_page_of(e, r, 0, t / kPageTokens);
@@ -371,6 +372,7 @@ void decode_step(bw_engine* e, Ctl* ctls) {
     } else {
       ctl.grp_first[NG] = R; ctl.grp_n[NG] = r->G; ctl.grp_x[NG] = r->q;
       max_grp = std::max(max_grp, r->G);
+      ctl.max_ctx = std::max(ctl.max_ctx, r->cur_len);
       ++NG;
       ctl.act_req[NA] = r->q; ctl.act_first[NA] = SR; ctl.act_force[NA] = forced_token(r); ++NA;
       if (r->step_logits_out) forced_reqs.push_back({r, gi, LR, 1});
