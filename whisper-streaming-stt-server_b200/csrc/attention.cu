@@ -295,6 +295,158 @@ dec_self_attention_kernel(const int* __restrict__ row_seq, const int* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// v2: one WARP per (row, head), no shared-memory staging and no block-level synchronisation.  The staged kernel above
+// keeps 6 (row, head) units resident per SM (32 KB of shared memory each) and pays ~5 dependent latencies per unit
+// (profiles/r2_launches_dec64x5.csv: 67 us per layer at 320 rows, 2.7x its HBM bound); here every warp streams its own
+// unit with 16 independent 16-byte loads in flight per lane, so ~20 units per SM overlap their latencies.
+//   lanes: LPR = 64 / VEC lanes share one position (VEC dims each), PPI = 32 / LPR positions per pass, U passes unrolled.
+template <typename T> struct Raw16 { uint4 v; };
+template <typename T> __device__ __forceinline__ uint4 ld_raw16(const T* p) {
+  uint4 u;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+  return u;
+}
+template <typename T> __device__ __forceinline__ void unpack16(const uint4& u, float* f);
+template <> __device__ __forceinline__ void unpack16<bf16>(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+template <> __device__ __forceinline__ void unpack16<float>(const uint4& u, float* f) {
+  f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+dec_self_attention_warp_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const int* __restrict__ row_bpos,
+                               const int* __restrict__ row_page, const float* __restrict__ qkv, T* __restrict__ pool,
+                               long long page_stride, int n_ctx, int n_blocks, int n_units, const int* __restrict__ page_table,
+                               const int* __restrict__ seq_first, const unsigned char* __restrict__ anc, int layer, int d,
+                               int n_rows, int n_head, T* __restrict__ out, unsigned long long* trace_buf) {
+  constexpr int VEC = Vec16<T>::N, LPR = 64 / VEC, PPI = 32 / LPR, U = 8;
+  __shared__ int s_pt[4][kMaxBeam * kMaxBlocks];  // page-table rows of each warp's request (its beam slots)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * 4 + warp;
+  unsigned long long* const trace = (unit == 0 && lane == 0) ? trace_buf : nullptr;
+  trace_mark(trace, (3u << 24) | 1);
+  pdl_trigger();
+  if (unit >= n_rows * n_head) return;  // warps are independent: no block-wide barrier below
+  const int r = unit / n_head, h = unit - r * n_head;
+  // Everything read before the dependency wait was written by earlier STEPS (control block, ancestry, page table
+  // entries of blocks that hold positions < bpos, cached K/V); only q and this step's own k/v rows need the wait.
+  const int s = row_seq[r], pos = row_pos[r], bpos = row_bpos[r];
+  const int sf = seq_first[s];
+  const bool single = (sf & kSingleBeamFlag) != 0;
+  const int first = sf & ~kSingleBeamFlag;
+  const unsigned char* my_anc = anc + (long long)s * n_ctx;
+  const int sub = lane % LPR, pg = lane / LPR;
+  int* pt = s_pt[warp];
+  if (bpos > 0) {
+    const int nu = single ? 1 : min(kMaxBeam, n_units - first);
+    for (int i = lane; i < nu * n_blocks; i += 32) pt[i] = page_table[(long long)first * n_blocks + i];
+    __syncwarp();
+  }
+  const long long plane = (long long)kPageTokens * d;                       // k plane -> v plane of a page's layer
+  const long long lane_off = (long long)layer * 2 * plane + h * 64 + sub * VEC;
+  auto load_batch = [&](int t0, uint4* kr, uint4* vr) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + u * PPI + pg;
+      if (t < bpos) {
+        const int page = pt[(single ? 0 : (int)my_anc[t]) * n_blocks + t / kPageTokens];
+        const T* kp = pool + (long long)page * page_stride + lane_off + (long long)(t % kPageTokens) * d;
+        kr[u] = ld_raw16<T>(kp);
+        vr[u] = ld_raw16<T>(kp + plane);
+      }
+    }
+  };
+  uint4 kr[U], vr[U];
+  load_batch(0, kr, vr);
+  pdl_wait();
+  trace_mark(trace, (3u << 24) | 2);
+  const float* qrow = qkv + (long long)r * 3 * d + h * 64;
+  // fused append: k / v of this row -> its page [layer][k | v][pos % kPageTokens]; 2 dims of each per lane
+  {
+    T* dst = pool + (long long)row_page[r] * page_stride + (long long)layer * 2 * plane + (long long)(pos % kPageTokens) * d + h * 64 + lane * 2;
+    dst[0] = from_f<T>(qrow[d + lane * 2]); dst[1] = from_f<T>(qrow[d + lane * 2 + 1]);
+    dst[plane] = from_f<T>(qrow[2 * d + lane * 2]); dst[plane + 1] = from_f<T>(qrow[2 * d + lane * 2 + 1]);
+  }
+  float qf[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) qf[i] = qrow[sub * VEC + i] * 0.125f;
+  float m = -INFINITY, l = 0.f, acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  auto fold = [&](const float* kf, const float* vf, bool valid) {
+    float sc = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) sc = fmaf(qf[i], kf[i], sc);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+    if (valid) {
+      const float m_new = fmaxf(m, sc);
+      const float a = exp_t<T>(m - m_new), pr = exp_t<T>(sc - m_new);
+      l = l * a + pr;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = fmaf(pr, vf[i], acc[i] * a);
+      m = m_new;
+    }
+  };
+  // cached positions [0, bpos): U passes of PPI positions per batch
+  for (int t0 = 0; t0 < bpos; t0 += PPI * U) {
+    if (t0 > 0) load_batch(t0, kr, vr);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (t0 + u * PPI >= bpos) break;  // warp-uniform
+      const bool valid = t0 + u * PPI + pg < bpos;
+      float kf[VEC], vf[VEC];
+      if (valid) { unpack16<T>(kr[u], kf); unpack16<T>(vr[u], vf); }
+      else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
+      }
+      fold(kf, vf, valid);
+    }
+  }
+  // positions fed in THIS step [bpos, pos]: fp32 rows of the qkv buffer, rounded like the pool copy
+  for (int t0 = bpos; t0 <= pos; t0 += PPI) {
+    const int t = t0 + pg;
+    const bool valid = t <= pos;
+    float kf[VEC], vf[VEC];
+    if (valid) {
+      const float* src = qkv + (long long)(r - (pos - t)) * 3 * d + d + h * 64 + sub * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { kf[i] = to_f(from_f<T>(src[i])); vf[i] = to_f(from_f<T>(src[d + i])); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
+    }
+    fold(kf, vf, valid);
+  }
+  // merge the PPI position groups of the warp
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+    const float M = fmaxf(m, m2);
+    const float e1 = (m == -INFINITY) ? 0.f : exp_t<T>(m - M), e2 = (m2 == -INFINITY) ? 0.f : exp_t<T>(m2 - M);
+    l = l * e1 + l2 * e2;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float a2 = __shfl_xor_sync(0xffffffffu, acc[i], o);
+      acc[i] = acc[i] * e1 + a2 * e2;
+    }
+    m = M;
+  }
+  if (pg == 0) {
+    const float inv = 1.f / l;
+    T* o = out + (long long)r * d + h * 64 + sub * VEC;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = from_f<T>(acc[i] * inv);
+  }
+  trace_mark(trace, (3u << 24) | 8);
+}
+
+// ------------------------------------------------------------------------------------------------
 constexpr int XW = 8;  // warps per cross-attention CTA
 constexpr int kMaxSplit = 8;
 
@@ -493,6 +645,15 @@ void dec_self_attention(const DecRows& rows, const float* qkv, const SelfKV& kv,
   if (rows.n_rows <= 0) return;
   BW_CHECK(kv.n_ctx <= 448 && kv.n_blocks <= kMaxBlocks && kv.n_blocks * kPageTokens >= kv.n_ctx, "n_text_ctx > 448 unsupported");
   BW_CHECK(rows.row_page && kv.page_table, "paged self-attention needs row_page and a page table");
+  static const bool staged = getenv("B200W_SELF_ATTN_V1") != nullptr;
+  if (!staged) {
+    const int units = n_head * rows.n_rows;
+    launch_kernel(dec_self_attention_warp_kernel<T>, dim3((units + 3) / 4), dim3(128), 0, stream, rows.row_seq, rows.row_pos, rows.row_bpos,
+                  rows.row_page, qkv, reinterpret_cast<T*>(kv.pool), kv.page_stride, kv.n_ctx, kv.n_blocks, kv.n_units, kv.page_table,
+                  kv.seq_first, kv.anc, layer, d, rows.n_rows, n_head, out, g_trace_dev);
+    ++g_kernel_launches;
+    return;
+  }
   dim3 grid(n_head, rows.n_rows);
   const int chunk = dec_self_chunk(rows.max_ctx);
   auto launch = [&](auto kern, int smem) {
