@@ -645,9 +645,13 @@ void dec_self_attention(const DecRows& rows, const float* qkv, const SelfKV& kv,
   if (rows.n_rows <= 0) return;
   BW_CHECK(kv.n_ctx <= 448 && kv.n_blocks <= kMaxBlocks && kv.n_blocks * kPageTokens >= kv.n_ctx, "n_text_ctx > 448 unsupported");
   BW_CHECK(rows.row_page && kv.page_table, "paged self-attention needs row_page and a page table");
-  static const bool staged = getenv("B200W_SELF_ATTN_V1") != nullptr;
-  if (!staged) {
-    const int units = n_head * rows.n_rows;
+  // Two kernels, chosen by the number of (row, head) units (A-B: profiles/r2_self_attention_ab.txt).  Many units (beam
+  // search: 64 windows x 5 hypotheses x 20 heads = 6400): one warp per unit, loads straight into registers -- the staged
+  // kernel fits only 6 units per SM and its per-unit latency chain is paid ~7 times over.  Fewer units (128 x 1 x 20 =
+  // 2560 and below): the staged kernel's one-shot cp.async burst keeps a unit's latency independent of its context.
+  static const int forced = getenv("B200W_SELF_ATTN") ? atoi(getenv("B200W_SELF_ATTN")) : 0;  // 1 = staged, 2 = warp
+  const int units = n_head * rows.n_rows;
+  if (forced == 2 || (forced == 0 && units >= 4000)) {
     launch_kernel(dec_self_attention_warp_kernel<T>, dim3((units + 3) / 4), dim3(128), 0, stream, rows.row_seq, rows.row_pos, rows.row_bpos,
                   rows.row_page, qkv, reinterpret_cast<T*>(kv.pool), kv.page_stride, kv.n_ctx, kv.n_blocks, kv.n_units, kv.page_table,
                   kv.seq_first, kv.anc, layer, d, rows.n_rows, n_head, out, g_trace_dev);
