@@ -13,7 +13,7 @@ namespace bw {
 namespace {
 
 constexpr int ST = 512;  // threads of the per-row kernels
-constexpr int SU = 8;    // logits loaded per thread per batch (keeps 8 coalesced loads in flight)
+constexpr int SU = 16;   // logits loaded per thread per batch (keeps 16 coalesced loads in flight: the kernel is a chain of memory latencies)
 
 struct RowRules {
   int tb, eot, no_ts_id;
