@@ -267,20 +267,9 @@ struct Impl {
   // per-row LayerNorm partials; each GEMM that used to read a LayerNorm output multiplies the raw bf16 rows with
   // W * gamma and normalises in its epilogue.  8 kernels per block instead of 11 (tools/trace_step.py: a LayerNorm
   // launch costs ~2.4 us of work + ~1.4 us of dependency release on the step's critical path).
-  // L2 prefetch request carried by a row GEMM (GemmArgs::pf_*)
-  struct L2Prefetch {
-    const char* base = nullptr;
-    const int* slots = nullptr;
-    int groups = 0;
-    long long slot_stride = 0, bytes = 0;
-  };
   void rows_gemm(const void* A, int R, int a_rows, const void* W, int N, int K, const float* bias, const float* residual, void* out,
-                 bool gelu, bool out_fp32, void* xb_out, float2* st_out, const float2* st_in, const float* c1,
-                 const L2Prefetch* pf = nullptr) const {
+                 bool gelu, bool out_fp32, void* xb_out, float2* st_out, const float2* st_in, const float* c1) const {
     GemmArgs g;
-    if (pf && pf->groups > 0) {
-      g.pf_base = pf->base; g.pf_slots = pf->slots; g.pf_groups = pf->groups; g.pf_slot_stride = pf->slot_stride; g.pf_bytes = pf->bytes;
-    }
     g.A = A; g.B = W; g.M = R; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldc = N; g.ldres = N; g.a_rows = a_rows;
     g.bias = bias; g.residual = residual; g.C = out; g.gelu = gelu; g.out_fp32 = out_fp32;
     g.xb_out = xb_out; g.ln_stats_out = st_out; g.ln_stats_in = st_in; g.ln_c1 = c1;
@@ -300,25 +289,15 @@ struct Impl {
     xkv.cache = e->cross_cache.p; xkv.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; xkv.T_enc = d.n_audio_ctx;
     xkv.n_slots = e->Q; xkv.n_layer = L;
     const int Ra = e->R_max;
-    // While the latency-bound chain between two cross-attention streams runs, HBM idles: the out-projection that follows
-    // layer l's cross-attention asks L2 for the cached K/V of layer l + 1 of the first request groups (the first waves of
-    // the next stream).  B200W_XKV_PREFETCH_MB sets the budget per layer (0 = off).
-    static const int pf_mb = getenv("B200W_XKV_PREFETCH_MB") ? atoi(getenv("B200W_XKV_PREFETCH_MB")) : 0;
-    const long long seg_bytes = (long long)d.n_audio_ctx * 2 * dm * 2;
-    L2Prefetch pf;
-    pf.slots = c.grp_x; pf.slot_stride = (long long)L * seg_bytes; pf.bytes = seg_bytes;
-    pf.groups = (int)std::min<long long>(c.n_groups, pf_mb > 0 ? std::max<long long>(1, (long long)pf_mb * 1000000 / seg_bytes) : 0);
     for (int l = 0; l < L; ++l) {
       const LayerW& w = e->w.dec[l];
-      pf.base = reinterpret_cast<const char*>(e->cross_cache.p) + (long long)(l + 1) * seg_bytes;
       rows_gemm(xb, c.R, Ra, w.wqkv, 3 * dm, dm, w.c2_qkv, nullptr, G.d_qkv.p, false, true, nullptr, nullptr, lst, w.c1_qkv);
       dec_self_attention<bf16>(rows, G.d_qkv.as<float>(), skv, l, dm, H, G.d_att.as<bf16>(), st);
       rows_gemm(G.d_att.p, c.R, Ra, w.wo, dm, dm, w.bo, x, x, false, true, xb, lst, nullptr, nullptr);
       rows_gemm(xb, c.R, Ra, w.wq_x, dm, dm, w.c2_qx, nullptr, G.d_q.p, false, true, nullptr, nullptr, lst, w.c1_qx);
       dec_cross_attention<bf16>(c.grp_first, c.grp_n, c.grp_x, c.n_groups, c.max_group_rows, c.R, G.d_q.as<float>(), xkv, l, dm, H,
                                 G.d_att.as<bf16>(), G.d_ws.as<float>(), st);
-      rows_gemm(G.d_att.p, c.R, Ra, w.wo_x, dm, dm, w.bo_x, x, x, false, true, xb, lst, nullptr, nullptr,
-                (l + 1 < L && pf.groups > 0) ? &pf : nullptr);
+      rows_gemm(G.d_att.p, c.R, Ra, w.wo_x, dm, dm, w.bo_x, x, x, false, true, xb, lst, nullptr, nullptr);
       rows_gemm(xb, c.R, Ra, w.w1, 4 * dm, dm, w.c2_w1, nullptr, G.d_h.p, true, false, nullptr, nullptr, lst, w.c1_w1);
       rows_gemm(G.d_h.p, c.R, Ra, w.w2, dm, 4 * dm, w.b2, x, x, false, true, xb, lst, nullptr, nullptr);
     }

@@ -41,13 +41,6 @@ struct GemmArgs {
   const float2* ln_stats_in = nullptr;
   const float* ln_c1 = nullptr;
   float ln_eps = 1e-5f;
-  // ---- L2 prefetch piggy-backed on a row GEMM (gemm_tc_rows only): while this latency-bound kernel runs, HBM is idle;
-  // its CTAs ask L2 for pf_groups contiguous regions of pf_bytes each, region g at pf_base + pf_slots[g] * pf_slot_stride
-  // (the next layer's cached cross K/V of the first request groups: the decoder's cross-attention then finds them in L2).
-  const char* pf_base = nullptr;
-  const int* pf_slots = nullptr;   // device
-  int pf_groups = 0;
-  long long pf_slot_stride = 0, pf_bytes = 0;
 };
 
 // bf16 inputs, fp32 accumulate, tcgen05.mma + TMEM + TMA. Throws on CUDA errors.

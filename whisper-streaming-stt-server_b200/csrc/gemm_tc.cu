@@ -46,11 +46,6 @@ struct GemmDev {
   const float* c1;        // consumer: row sums of the folded weight
   int st_in_tiles;
   float ln_eps;
-  // rows kernel: L2 prefetch of data a LATER kernel streams (see GemmArgs::pf_*)
-  const char* pf_base = nullptr;
-  const int* pf_slots = nullptr;
-  int pf_groups = 0;
-  long long pf_slot_stride = 0, pf_bytes = 0;
   int vec8 = 0;           // pair kernel: C / residual rows are 32-byte aligned -> 256-bit epilogue loads and stores
   int res_prefetch = 0;   // pair kernel: L2-prefetch the residual rows of a tile before waiting for its accumulator
 };
@@ -521,20 +516,6 @@ gemm_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tma_load_3d(smem + kb * R_STAGE_BYTES + R_A_BYTES, &tmB, &full_bar[kb], (kb0 + kb) * BK, n0, zb);
     }
     for (int kb = n_pre; kb < num_kb; ++kb) tma_prefetch_l2_3d(&tmB, (kb0 + kb) * BK, n0, zb);
-  }
-  if (p.pf_groups > 0 && threadIdx.x == 32) {
-    // piggy-backed L2 prefetch (read-only data of a later kernel): 32 KB pieces dealt round-robin to the CTAs
-    constexpr long long kPiece = 32768;
-    const long long per_group = (p.pf_bytes + kPiece - 1) / kPiece;
-    const long long total = per_group * p.pf_groups;
-    const long long n_cta = (long long)gridDim.x * gridDim.y * gridDim.z;
-    const long long me = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    for (long long c = me; c < total; c += n_cta) {
-      const long long g = c / per_group, off = (c - g * per_group) * kPiece;
-      const char* src = p.pf_base + (long long)p.pf_slots[g] * p.pf_slot_stride + off;
-      const unsigned bytes = (unsigned)min(kPiece, p.pf_bytes - off);
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-    }
   }
   if (threadIdx.x == 0) trace_mark(trace, ttag | 1);
   pdl_wait();
@@ -1114,9 +1095,6 @@ void launch_rows(const GemmArgs& g, cudaStream_t stream) {
   p.trace = g_trace_dev;
   p.xb = reinterpret_cast<bf16*>(g.xb_out); p.st_out = g.ln_stats_out; p.st_in = g.ln_stats_in; p.c1 = g.ln_c1;
   p.st_in_tiles = g.K / 64; p.ln_eps = g.ln_eps;
-  p.pf_base = g.pf_base; p.pf_slots = g.pf_slots; p.pf_groups = g.pf_slots ? g.pf_groups : 0; p.pf_slot_stride = g.pf_slot_stride;
-  p.pf_bytes = g.pf_bytes;
-  if (p.pf_groups > 0) BW_CHECK(g.pf_base && g.pf_bytes > 0 && g.pf_bytes % 16 == 0, "bad L2 prefetch region");
   if (g.ln_stats_in) BW_CHECK(g.ln_c1 && g.K % 64 == 0 && g.K / 64 <= 32 && g.Z == 1, "LayerNorm-fused GEMM needs K % 64 == 0, K <= 2048");
   if (g.ln_stats_out || g.xb_out) BW_CHECK(g.N % 64 == 0 && g.Z == 1 && g.out_fp32, "LayerNorm producer GEMM needs N % 64 == 0 and an fp32 C");
   cudaLaunchConfig_t cfg{};
