@@ -222,7 +222,9 @@ def test_gemm_throughput_report():
         print(f"GEMM {M}x{N}x{K}: ours {2 * M * N * K / ms / 1e9:.0f} TFLOP/s ({ms:.3f} ms), cuBLAS {2 * M * N * K / ms_ref / 1e9:.0f} TFLOP/s")
 
 
-@pytest.mark.parametrize("shape", [(128, 1280, 1280, 3840), (37, 1280, 5120, 1280), (300, 384, 384, 1536), (128, 1280, 0, 5120), (5, 512, 512, 512)])
+@pytest.mark.parametrize("shape", [(128, 1280, 1280, 3840), (37, 1280, 5120, 1280), (300, 384, 384, 1536), (128, 1280, 0, 5120), (5, 512, 512, 512),
+                                   # beam batches: several M tiles x a wide consumer -> the unsplit (KS = 1) single-wave path
+                                   (320, 1280, 1280, 5120), (320, 1280, 0, 3840), (200, 1280, 1280, 5120), (257, 1280, 0, 3840)])
 @pytest.mark.parametrize("gelu", [False, True])
 def test_layernorm_fused_row_gemms(shape, gelu):
     """decoder LayerNorm fusion: producer GEMM (x = res + A.Wp^T + b, plus bf16(x) and LayerNorm partials) feeding a

@@ -484,7 +484,7 @@ gemm_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * R_BN, m0 = blockIdx.y * BM;
   const int z = blockIdx.z / KS;
-  const int ks = (int)cluster_ctarank();  // == blockIdx.z % KS for cluster dims (1, 1, KS)
+  const int ks = KS == 1 ? 0 : (int)cluster_ctarank();  // == blockIdx.z % KS for cluster dims (1, 1, KS)
   const int total_kb = (p.K + BK - 1) / BK;
   const int kb0 = (int)((long long)ks * total_kb / KS);
   const int num_kb = (int)((long long)(ks + 1) * total_kb / KS) - kb0;  // >= 1: host guarantees KS <= total_kb
@@ -556,6 +556,67 @@ gemm_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   }
 
+  if constexpr (KS == 1) {
+    // No split: the accumulator in TMEM is final.  Used for the step's WIDE consumer GEMMs (qkv, mlp.0) once the rows fill
+    // more than one M tile (beam batches): tiles x 2 CTAs would not be co-resident, one wave of full-K CTAs is.
+    // One epilogue thread per accumulator row: LayerNorm statistics of the row, then 64 columns straight to global memory.
+    if (warp >= 2) {
+      const int wq = warp & 3;
+      const int gi = m0 + wq * 32 + lane;
+      const bool row_ok = gi < p.M;
+      float mean = 0.f, rstd = 1.f;
+      if (p.st_in && row_ok) {
+        const float2* sp = p.st_in + (long long)gi * p.st_in_tiles;
+        float ms = 0.f;
+        for (int i = 0; i < p.st_in_tiles; ++i) ms += sp[i].x;
+        mean = ms / (float)p.st_in_tiles;
+        float m2 = 0.f;
+        for (int i = 0; i < p.st_in_tiles; ++i) { const float2 q = sp[i]; m2 += q.y + 64.f * (q.x - mean) * (q.x - mean); }
+        rstd = rsqrtf(m2 / (64.f * (float)p.st_in_tiles) + p.ln_eps);
+      }
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < R_BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int j0 = n0 + c * 32 + g * 4;
+          if (!row_ok || j0 >= p.N) continue;
+          float v[4] = {__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3])};
+          if (p.st_in) {
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.c1 + j0));
+            v[0] = rstd * (v[0] - mean * c1.x); v[1] = rstd * (v[1] - mean * c1.y);
+            v[2] = rstd * (v[2] - mean * c1.z); v[3] = rstd * (v[3] - mean * c1.w);
+          }
+          if (p.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + (long long)z * p.bias_zstride + j0));
+            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+          }
+          if (p.gelu) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = gelu_erf_fast(v[q]);
+          }
+          if (p.residual) {
+            const float4 rr = *reinterpret_cast<const float4*>(p.residual + (long long)z * p.res_zstride + (long long)gi * p.ldres + j0);
+            v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+          }
+          const long long oi = (long long)z * p.c_zstride + (long long)gi * p.ldc + j0;
+          if (p.out_fp32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + oi) = make_float4(v[0], v[1], v[2], v[3]);
+          else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.C) + oi) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+        }
+      }
+      tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+      tc_fence_after();
+      tmem_dealloc(tmem_base, R_BN);
+    }
+    return;
+  }
   // ---- epilogue threads: what this thread will finalise after the reduction ----
   constexpr int RPC = BM / KS;      // tile rows owned (reduced + stored) by each CTA of the cluster
   constexpr int NI = RPC / 8;       // float4 granules per epilogue thread (RPC rows x 16 granules / 128 threads)
@@ -1102,6 +1163,7 @@ void launch_rows(const GemmArgs& g, cudaStream_t stream) {
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = R_SMEM_TOTAL;
   cfg.stream = stream;
+  if (KS == 1) BW_CHECK(!g.xb_out && !g.ln_stats_out, "the unsplit row GEMM has no LayerNorm-producer epilogue");
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = KS;
@@ -1167,10 +1229,15 @@ void gemm_tc_rows(const GemmArgs& g, cudaStream_t stream) {
            "row GEMM needs N, ldc, ldres % 4 == 0");
   const long long tiles64 = (long long)((g.M + BM - 1) / BM) * ((g.N + R_BN - 1) / R_BN) * g.Z;
   const int total_kb = (g.K + BK - 1) / BK;
-  int ks = 8;  // keep the grid within one co-resident wave when possible (see gemm_tc_bf16), never below 2
+  int ks = 8;  // keep the grid within one co-resident wave when possible (see gemm_tc_bf16)
   while (ks > 2 && (tiles64 * ks > (ks == 8 ? 256 : 288) || total_kb < 2 * ks)) ks >>= 1;
   // (capping KS at 4 / 2 so that every SM hosts one CTA was measured slower: 7.20 -> 7.26 / 7.75 ms per step)
   BW_CHECK(total_kb >= ks, "K too small for the row GEMM");
+  // More than one M tile (beam batches: 320 rows = 3 tiles) and a wide N: even KS = 2 is two waves.  One wave of unsplit
+  // CTAs instead (consumer / plain epilogues only; K <= 2048 keeps the serial main loop short).
+  static const bool no_unsplit = getenv("B200W_ROWS_NO_UNSPLIT") != nullptr;
+  if (!no_unsplit && ks == 2 && tiles64 * 2 > 288 && tiles64 <= 296 && total_kb <= 32 && !g.xb_out && !g.ln_stats_out)
+    return launch_rows<1>(g, stream);
   if (ks == 8) return launch_rows<8>(g, stream);
   if (ks == 4) return launch_rows<4>(g, stream);
   return launch_rows<2>(g, stream);
