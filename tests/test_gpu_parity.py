@@ -155,8 +155,10 @@ def test_beam_patience_and_length_penalty_fp32(beam, patience, length_penalty):
         _check_transcribe(backend("test-tiny", "float32", **kw), "test-tiny", synth_audio(seed, seconds), opts, **kw)
 
 
-def test_transcribe_bf16_first_divergence():
-    """bf16 product mode: report where the token stream first leaves the fp32 oracle's (north_star)."""
+def test_transcribe_bf16_segments_follow_the_oracle():
+    """bf16 product mode through the public transcribe(): the segments' token stream agrees with the fp32 oracle's on (nearly)
+    all leading tokens for this model (test-tiny: measured 100 %; the per-token statistics for every model size are
+    tests/test_gpu_bf16_decode.py::test_bf16_first_divergence_statistics, profiles/r2_bf16_divergence.json)."""
     b = backend("test-tiny", "bfloat16")
     opts = dict(REALTIME, language="en")
     total = agree = 0
@@ -171,7 +173,7 @@ def test_transcribe_bf16_first_divergence():
         total += max(len(want), 1)
         agree += first
     print(f"bf16 first-divergence: {agree}/{total} leading tokens agree with the fp32 oracle")
-    assert total > 0
+    assert total > 0 and agree >= 0.75 * total, (agree, total)
 
 
 def _raw_key(result):
