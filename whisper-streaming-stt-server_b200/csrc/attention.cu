@@ -371,12 +371,17 @@ dec_self_attention_warp_kernel(const int* __restrict__ row_seq, const int* __res
     dst[0] = from_f<T>(qrow[d + lane * 2]); dst[1] = from_f<T>(qrow[d + lane * 2 + 1]);
     dst[plane] = from_f<T>(qrow[2 * d + lane * 2]); dst[plane + 1] = from_f<T>(qrow[2 * d + lane * 2 + 1]);
   }
+  // bf16 mode works in the log2 domain (log2(e) folded into q: one MUFU.EX2 per exponential, no extra multiply);
+  // the fp32 validation mode keeps expf
+  constexpr bool kExp2 = !std::is_same<T, float>::value;
+  const float qscale = kExp2 ? 0.125f * 1.4426950408889634f : 0.125f;
   float qf[VEC];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) qf[i] = qrow[sub * VEC + i] * 0.125f;
+  for (int i = 0; i < VEC; ++i) qf[i] = qrow[sub * VEC + i] * qscale;
   float m = -INFINITY, l = 0.f, acc[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  auto ex = [&](float x) { return kExp2 ? fast_exp2(x) : expf(x); };
   auto fold = [&](const float* kf, const float* vf, bool valid) {
     float sc = 0.f;
 #pragma unroll
@@ -384,12 +389,17 @@ dec_self_attention_warp_kernel(const int* __restrict__ row_seq, const int* __res
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
     if (valid) {
-      const float m_new = fmaxf(m, sc);
-      const float a = exp_t<T>(m - m_new), pr = exp_t<T>(sc - m_new);
-      l = l * a + pr;
+      if (sc > m) {  // the running maximum moves (rare after the first positions): rescale
+        const float a = ex(m - sc);
+        l *= a;
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[i] = fmaf(pr, vf[i], acc[i] * a);
-      m = m_new;
+        for (int i = 0; i < VEC; ++i) acc[i] *= a;
+        m = sc;
+      }
+      const float pr = ex(sc - m);
+      l += pr;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = fmaf(pr, vf[i], acc[i]);
     }
   };
   // cached positions [0, bpos): U passes of PPI positions per batch
@@ -428,7 +438,7 @@ dec_self_attention_warp_kernel(const int* __restrict__ row_seq, const int* __res
   for (int o = LPR; o < 32; o <<= 1) {
     const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
     const float M = fmaxf(m, m2);
-    const float e1 = (m == -INFINITY) ? 0.f : exp_t<T>(m - M), e2 = (m2 == -INFINITY) ? 0.f : exp_t<T>(m2 - M);
+    const float e1 = (m == -INFINITY) ? 0.f : ex(m - M), e2 = (m2 == -INFINITY) ? 0.f : ex(m2 - M);
     l = l * e1 + l2 * e2;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {

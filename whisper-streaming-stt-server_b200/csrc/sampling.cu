@@ -12,8 +12,8 @@
 namespace bw {
 namespace {
 
-constexpr int ST = 512;  // threads of the per-row kernels
-constexpr int SU = 16;   // logits loaded per thread per batch (keeps 16 coalesced loads in flight: the kernel is a chain of memory latencies)
+constexpr int ST = 1024; // threads of the per-row kernels (one CTA per logits row: 32 warps per SM keep more loads in flight than 16)
+constexpr int SU = 8;    // logits loaded per thread per batch (keeps 8 coalesced loads in flight)
 
 struct RowRules {
   int tb, eot, no_ts_id;
