@@ -78,6 +78,13 @@ int bw_test_dec_self_attention(int32_t n_rows, const int32_t* row_seq, const int
  * cand_tok / cand_lp [n][9], unused entries untouched. */
 int bw_test_sample_topk(bw_engine*, const float* logits, int32_t n, const int32_t* state, int32_t* cand_tok, float* cand_lp);
 
+/* Host-only (no GPU needed): replays the scheduler's self-KV page bookkeeping for ONE request of n_hypotheses beams --
+ * n_initial prompt positions, then n_steps decoder steps whose beam reorder is parents[step * n_hypotheses + j] (the slot
+ * hypothesis j descends from, what beam_update reports back).  alloc_masks[step * 28 + block]: bit j set if (slot j, block)
+ * holds a page after that step's collection; pages_in_use[step].  Fails if a page leaks. */
+int bw_test_page_collector(int32_t n_hypotheses, int32_t n_initial, int32_t n_steps, const uint8_t* parents, uint8_t* alloc_masks,
+                           int32_t* pages_in_use);
+
 #ifdef __cplusplus
 }
 #endif

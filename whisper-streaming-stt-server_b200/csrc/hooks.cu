@@ -468,3 +468,12 @@ int bw_test_sample_topk(bw_engine* e, const float* logits, int32_t n, const int3
   BW_CUDA(cudaStreamSynchronize(st));
   BW_API_END
 }
+
+int bw_test_page_collector(int32_t n_hypotheses, int32_t n_initial, int32_t n_steps, const uint8_t* parents, uint8_t* alloc_masks,
+                           int32_t* pages_in_use) {
+  BW_API_BEGIN
+  BW_CHECK(parents && alloc_masks && pages_in_use && n_steps >= 1, "bad argument");
+  const int st = page_collector_replay(n_hypotheses, n_initial, n_steps, parents, alloc_masks, pages_in_use);
+  if (st != BW_OK) { last_error() = "page collector replay: bad geometry or pages leaked"; return st; }
+  BW_API_END
+}

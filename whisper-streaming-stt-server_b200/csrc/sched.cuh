@@ -65,6 +65,7 @@ void scheduler_main(bw_engine* e);
 int kv_blocks_for(int n_tokens);                       // pages one hypothesis needs for n_tokens positions
 int kv_page_of(bw_engine* e, Request* r, int slot, int block);  // the request's page for (beam slot, block), allocated on demand
 void kv_release(bw_engine* e, Request* r);             // every page + the reservation of a finished request
+int page_collector_replay(int G, int n_init, int n_steps, const unsigned char* parents, unsigned char* alloc_masks, int* pages_in_use);
 int submit_and_wait(bw_engine* e, Request& r);
 // one host thread hands a whole batch to the scheduler and waits for every request of it
 int submit_many_and_wait(bw_engine* e, const std::vector<Request*>& rs);

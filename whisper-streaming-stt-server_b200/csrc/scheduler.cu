@@ -157,6 +157,50 @@ void collect_pages(bw_engine* e, Request* r, const unsigned char* src, int next_
   }
 }
 
+}  // namespace
+
+// Host-only replay of the page bookkeeping of ONE request (no CUDA call): the same sequence decode_step() runs --
+// prefill pages of slot 0, then per step one page lookup per hypothesis slot, the ancestry masks, the collector.
+// alloc_masks[step * n_blocks + b] = bit j set if (slot j, block b) holds a page after that step's collection.
+int page_collector_replay(int G, int n_init, int n_steps, const unsigned char* parents, unsigned char* alloc_masks, int* pages_in_use) {
+  bw_engine e;  // default-constructed: no device memory, no streams
+  e.n_blocks = kMaxBlocks;
+  e.n_pages = kMaxBlocks * kMaxBeam;
+  for (int pg = e.n_pages - 1; pg >= 0; --pg) e.free_pages.push_back(pg);
+  Request r;
+  r.kind = REQ_DECODE;
+  r.G = G;
+  r.initial.assign((size_t)n_init, 0);
+  r.sample_len = n_steps;
+  e.dims.n_text_ctx = kMaxBlocks * kPageTokens;
+  if (G < 1 || G > kMaxBeam || n_init < 1 || n_init + n_steps > e.dims.n_text_ctx) return BW_ERR_INVALID;
+  kv_begin(&e, &r, kv_reserve(&e, &r));
+  const int NB = e.n_blocks;
+  for (int t = 0; t < n_init; ++t) kv_page_of(&e, &r, 0, t / kPageTokens);
+  for (int j = 0; j < G; ++j)
+    for (int b = 0; b <= (n_init - 1) / kPageTokens; ++b) r.ref_mask[(size_t)j * NB + b] |= 1u;
+  int cur_len = n_init;
+  for (int step = 0; step < n_steps; ++step) {
+    if (step > 0)  // cached step: slot j writes position cur_len - 1
+      for (int j = 0; j < G; ++j) {
+        kv_page_of(&e, &r, j, (cur_len - 1) / kPageTokens);
+        r.ref_mask[(size_t)j * NB + (cur_len - 1) / kPageTokens] |= (unsigned char)(1u << j);
+      }
+    cur_len += 1;
+    collect_pages(&e, &r, parents + (size_t)step * G, cur_len - 1);
+    for (int b = 0; b < NB; ++b) {
+      unsigned m = 0;
+      for (int j = 0; j < G; ++j) if (r.pages[(size_t)j * NB + b] >= 0) m |= 1u << j;
+      alloc_masks[(size_t)step * NB + b] = (unsigned char)m;
+    }
+    pages_in_use[step] = (int)e.stat_pages_in_use;
+  }
+  kv_release(&e, &r);
+  return (e.stat_pages_in_use == 0 && (int)e.free_pages.size() == e.n_pages && e.pages_reserved == 0) ? BW_OK : BW_ERR_STATE;
+}
+
+namespace {
+
 void release_slots(bw_engine* e, Request* r) {
   kv_release(e, r);
   if (r->q >= 0) e->free_q.push_back(r->q);
