@@ -10,6 +10,9 @@
 // shared memory, partials over T splits through the workspace + dec_cross_combine kernel (attention.cu).
 // Upstream: whisper/model.py MultiHeadAttention.forward with cached cross K/V (kv_cache hooks).
 #include <cuda.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "kernels.cuh"
 
@@ -23,9 +26,10 @@ namespace {
 constexpr int XT = 64;          // keys per tile
 constexpr int XSTAGES = 6;
 constexpr int XTILE_BYTES = XT * 128;  // one 64x64 bf16 tile
-constexpr int XSM_BAR = XSTAGES * 2 * XTILE_BYTES;
-constexpr int XSM_RED = XSM_BAR + 128;
-constexpr int XSM_TOTAL = XSM_RED + 4 * 8 * 66 * 4 + 1024;
+// shared memory: ring of n_stages K|V tiles, then the barriers, then the cross-warp reduction area
+__host__ __device__ constexpr int xsm_bar(int n_stages) { return n_stages * 2 * XTILE_BYTES; }
+__host__ __device__ constexpr int xsm_red(int n_stages) { return xsm_bar(n_stages) + 128; }
+__host__ __device__ constexpr int xsm_total(int n_stages) { return xsm_red(n_stages) + 4 * 8 * 66 * 4 + 1024; }
 constexpr int kMaxSplitX = 8;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -43,7 +47,7 @@ __device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uin
 __global__ void __launch_bounds__(160, 2)
 dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int* __restrict__ group_first_row,
                                const int* __restrict__ group_n_rows, const int* __restrict__ group_xslot,
-                               const float* __restrict__ q, int T_enc, int n_layer, int layer, int d, int n_split,
+                               const float* __restrict__ q, int T_enc, int n_layer, int layer, int d, int n_split, int n_stages,
                                bf16* __restrict__ out, float* __restrict__ ws, unsigned long long* trace_buf) {
   extern __shared__ uint8_t smem_raw[];
   unsigned long long* trace = nullptr;
@@ -54,9 +58,9 @@ dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int
   }
   trace_mark(trace, ttag | 1);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + XSM_BAR);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + xsm_bar(n_stages));
   uint64_t* empty_bar = full_bar + XSTAGES;
-  float* red = reinterpret_cast<float*>(smem + XSM_RED);  // [4 warps][8 rows][66]: m, l, o[64]
+  float* red = reinterpret_cast<float*>(smem + xsm_red(n_stages));  // [4 warps][8 rows][66]: m, l, o[64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, g = blockIdx.y, sp = blockIdx.z, n_head = gridDim.x;
@@ -67,7 +71,7 @@ dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm);
-    for (int s = 0; s < XSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
     fence_barrier_init();
   }
   __syncthreads();
@@ -79,8 +83,8 @@ dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int
     if (lane == 0) {
       const int zc = group_xslot[g] * n_layer + layer;
       for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % XSTAGES;
-        mbar_wait(&empty_bar[s], ((it / XSTAGES) & 1) ^ 1);
+        const int s = it % n_stages;
+        mbar_wait(&empty_bar[s], ((it / n_stages) & 1) ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], 2 * XTILE_BYTES);
         uint8_t* ks = smem + s * 2 * XTILE_BYTES;
         tma_load_3d(ks, &tm, &full_bar[s], h * 64, t0 + it * XT, zc);
@@ -112,8 +116,8 @@ dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int
     // ldmatrix lane roles
     const int lrow = lane & 7, lmat = lane >> 3;
     for (int it = 0; it < n_tiles; ++it) {
-      const int s = it % XSTAGES;
-      mbar_wait(&full_bar[s], (it / XSTAGES) & 1);
+      const int s = it % n_stages;
+      mbar_wait(&full_bar[s], (it / n_stages) & 1);
       const uint32_t kbase = smem_u32(smem + s * 2 * XTILE_BYTES);
       const uint32_t vbase = kbase + XTILE_BYTES;
       // ---- S[16 x 16 keys] = Q . K^T for this warp's keys [warp*16, +16) ----
@@ -220,7 +224,7 @@ void dec_cross_attention_mma(const int* group_first_row, const int* group_n_rows
   int dev = 0;
   BW_CUDA(cudaGetDevice(&dev));
   if (!(attr_set.load() >> dev & 1ull)) {
-    BW_CUDA(cudaFuncSetAttribute(dec_cross_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XSM_TOTAL));
+    BW_CUDA(cudaFuncSetAttribute(dec_cross_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xsm_total(XSTAGES)));
     attr_set.fetch_or(1ull << dev);
   }
   // one map per (cache pointer, geometry); cheap enough to rebuild, but the decoder calls this 32x per step
@@ -233,8 +237,9 @@ void dec_cross_attention_mma(const int* group_first_row, const int* group_n_rows
   }
   const CUtensorMap tm = cached_tm;
   dim3 grid(n_head, n_groups, n_split);
-  launch_kernel(dec_cross_attention_mma_kernel, grid, dim3(160), XSM_TOTAL, stream, tm, group_first_row, group_n_rows, group_xslot, q,
-                kv.T_enc, n_layer, layer, d, n_split, out, ws, g_trace_dev);
+  static const int n_stages = std::max(2, std::min(XSTAGES, getenv("B200W_XATTN_STAGES") ? atoi(getenv("B200W_XATTN_STAGES")) : XSTAGES));
+  launch_kernel(dec_cross_attention_mma_kernel, grid, dim3(160), (size_t)xsm_total(n_stages), stream, tm, group_first_row, group_n_rows,
+                group_xslot, q, kv.T_enc, n_layer, layer, d, n_split, n_stages, out, ws, g_trace_dev);
   ++g_kernel_launches;
 }
 
