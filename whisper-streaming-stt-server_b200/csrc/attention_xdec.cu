@@ -237,7 +237,8 @@ void dec_cross_attention_mma(const int* group_first_row, const int* group_n_rows
   }
   const CUtensorMap tm = cached_tm;
   dim3 grid(n_head, n_groups, n_split);
-  static const int n_stages = std::max(2, std::min(XSTAGES, getenv("B200W_XATTN_STAGES") ? atoi(getenv("B200W_XATTN_STAGES")) : XSTAGES));
+  static const int env_stages = getenv("B200W_XATTN_STAGES") ? atoi(getenv("B200W_XATTN_STAGES")) : 0;
+  const int n_stages = std::max(2, std::min(XSTAGES, kv.ring_stages > 0 ? kv.ring_stages : env_stages > 0 ? env_stages : XSTAGES));
   launch_kernel(dec_cross_attention_mma_kernel, grid, dim3(160), (size_t)xsm_total(n_stages), stream, tm, group_first_row, group_n_rows,
                 group_xslot, q, kv.T_enc, n_layer, layer, d, n_split, n_stages, out, ws, g_trace_dev);
   ++g_kernel_launches;
