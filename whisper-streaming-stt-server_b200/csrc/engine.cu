@@ -568,26 +568,34 @@ void engine_decoder_layers_pair(bw_engine* e, DecGroup& G0, const PairStepArgs& 
   cudaStream_t s0 = G0.stream, s1 = G1.stream;
   static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;
   static const int ring = getenv("B200W_PAIR_RING") ? atoi(getenv("B200W_PAIR_RING")) : 3;
+  // launch priorities: the chain kernels must win freed SM resources over the queued cross-attention CTAs
+  static int prio_lo = 0, prio_hi = 0;
+  static const bool use_prio = getenv("B200W_PAIR_NO_PRIO") == nullptr;
+  static const bool prio_init = (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi), true);
+  (void)prio_init;
+  const int p_chain = use_prio ? kPrioritySet + prio_hi : 0, p_x = use_prio ? kPrioritySet + prio_lo : 0;
   BW_CUDA(cudaEventRecord(e->pair_fork, s0));
   BW_CUDA(cudaStreamWaitEvent(s1, e->pair_fork, 0));
   const int L = e->dims.n_text_layer;
   {
     PdlScope pdl(use_pdl);
+    PriorityScope pr(p_chain);
     i0.fused_embed(c0, G0);
     i1.fused_embed(c1, G1);
   }
   for (int l = 0; l < L; ++l) {
-    { PdlScope pdl(use_pdl); i0.fused_pre(c0, G0, l); }
+    { PdlScope pdl(use_pdl); PriorityScope pr(p_chain); i0.fused_pre(c0, G0, l); }
     if (l > 0) BW_CUDA(cudaStreamWaitEvent(s0, e->pair_xdone[1], 0));
-    { PdlScope pdl(use_pdl && l == 0); i0.fused_xattn(c0, G0, l, ring); }  // behind a cross-stream wait: plain launch
+    { PdlScope pdl(use_pdl && l == 0); PriorityScope pr(p_x); i0.fused_xattn(c0, G0, l, ring); }  // behind a cross-stream wait: plain launch
     BW_CUDA(cudaEventRecord(e->pair_xdone[0], s0));
-    { PdlScope pdl(use_pdl); i1.fused_pre(c1, G1, l); }
+    { PdlScope pdl(use_pdl); PriorityScope pr(p_chain); i1.fused_pre(c1, G1, l); }
     BW_CUDA(cudaStreamWaitEvent(s1, e->pair_xdone[0], 0));
-    { PdlScope pdl(false); i1.fused_xattn(c1, G1, l, ring); }
+    { PdlScope pdl(false); PriorityScope pr(p_x); i1.fused_xattn(c1, G1, l, ring); }
     BW_CUDA(cudaEventRecord(e->pair_xdone[1], s1));
-    { PdlScope pdl(use_pdl); i0.fused_post(c0, G0, l); i1.fused_post(c1, G1, l); }
+    { PdlScope pdl(use_pdl); PriorityScope pr(p_chain); i0.fused_post(c0, G0, l); i1.fused_post(c1, G1, l); }
   }
   PdlScope pdl(use_pdl);
+  PriorityScope pr(p_chain);
   i0.fused_final(c0, G0);
   i1.fused_final(c1, G1);
 }
