@@ -47,7 +47,7 @@ __device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uin
 // Grid: 1-D.  One CTA per (head, group, split) item, or -- `persistent` launches -- 2 CTAs per SM that walk over the items
 // (head fastest).  The persistent form pins the kernel's footprint (2 x 58 KB of shared memory per SM with a 3-stage ring),
 // so that the OTHER request group's row-GEMM CTAs (105 KB) always find room next to it (paired decoder step).
-__global__ void __launch_bounds__(160, 2)
+__global__ void __launch_bounds__(160, 4)  // <= 102 registers: two of these CTAs and a row-GEMM CTA (168 registers x 192 threads) share an SM
 dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int* __restrict__ group_first_row,
                                const int* __restrict__ group_n_rows, const int* __restrict__ group_xslot,
                                const float* __restrict__ q, int T_enc, int n_layer, int layer, int d, int n_head, int n_groups,
