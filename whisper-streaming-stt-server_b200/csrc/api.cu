@@ -86,9 +86,6 @@ int bw_engine_create(const bw_model_dims* dims, const bw_engine_config* cfg, bw_
   e->fuse_ln = !e->fp32 && !e->force_simt && (dims->n_text_state % 64) == 0 && getenv("B200W_NO_LN_FUSION") == nullptr;
   BW_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   BW_CUDA(cudaEventCreateWithFlags(&e->enc_fork, cudaEventDisableTiming));
-  BW_CUDA(cudaEventCreateWithFlags(&e->pair_fork, cudaEventDisableTiming));
-  BW_CUDA(cudaEventCreateWithFlags(&e->pair_join, cudaEventDisableTiming));
-  for (auto& ev : e->pair_xdone) BW_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (int i = 0; i < bw_engine::kEncStreams; ++i) {
     BW_CUDA(cudaStreamCreateWithFlags(&e->enc_streams[i], cudaStreamNonBlocking));
     BW_CUDA(cudaEventCreateWithFlags(&e->enc_join[i], cudaEventDisableTiming));
@@ -351,9 +348,6 @@ int bw_engine_destroy(bw_engine* e) {
   if (e->h_fin) cudaFreeHost(e->h_fin);
   for (auto& s : e->front) if (s) cudaStreamDestroy(s);
   if (e->enc_fork) cudaEventDestroy(e->enc_fork);
-  if (e->pair_fork) cudaEventDestroy(e->pair_fork);
-  if (e->pair_join) cudaEventDestroy(e->pair_join);
-  for (auto& ev : e->pair_xdone) if (ev) cudaEventDestroy(ev);
   for (int i = 0; i < bw_engine::kEncStreams; ++i) {
     if (e->enc_join[i]) cudaEventDestroy(e->enc_join[i]);
     if (e->enc_streams[i]) cudaStreamDestroy(e->enc_streams[i]);

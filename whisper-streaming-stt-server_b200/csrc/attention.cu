@@ -17,7 +17,7 @@ namespace bw {
 
 void dec_cross_attention_mma(const int* group_first_row, const int* group_n_rows, const int* group_xslot, int n_groups,
                              const float* q, const CrossKV& kv, int n_layer, int layer, int d, int n_head, int n_split,
-                             bf16* out, float* ws, cudaStream_t stream);  // ring depth: kv.ring_stages
+                             bf16* out, float* ws, cudaStream_t stream);
 
 namespace {
 

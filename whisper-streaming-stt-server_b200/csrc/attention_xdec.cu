@@ -10,9 +10,6 @@
 // shared memory, partials over T splits through the workspace + dec_cross_combine kernel (attention.cu).
 // Upstream: whisper/model.py MultiHeadAttention.forward with cached cross K/V (kv_cache hooks).
 #include <cuda.h>
-#include <stdlib.h>
-
-#include <algorithm>
 
 #include "kernels.cuh"
 
@@ -26,10 +23,9 @@ namespace {
 constexpr int XT = 64;          // keys per tile
 constexpr int XSTAGES = 6;
 constexpr int XTILE_BYTES = XT * 128;  // one 64x64 bf16 tile
-// shared memory: ring of n_stages K|V tiles, then the barriers, then the cross-warp reduction area
-__host__ __device__ constexpr int xsm_bar(int n_stages) { return n_stages * 2 * XTILE_BYTES; }
-__host__ __device__ constexpr int xsm_red(int n_stages) { return xsm_bar(n_stages) + 128; }
-__host__ __device__ constexpr int xsm_total(int n_stages) { return xsm_red(n_stages) + 4 * 8 * 66 * 4 + 1024; }
+constexpr int XSM_BAR = XSTAGES * 2 * XTILE_BYTES;
+constexpr int XSM_RED = XSM_BAR + 128;
+constexpr int XSM_TOTAL = XSM_RED + 4 * 8 * 66 * 4 + 1024;
 constexpr int kMaxSplitX = 8;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -44,35 +40,34 @@ __device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uin
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// Grid: 1-D.  One CTA per (head, group, split) item, or -- `persistent` launches -- 2 CTAs per SM that walk over the items
-// (head fastest).  The persistent form pins the kernel's footprint (2 x 58 KB of shared memory per SM with a 3-stage ring),
-// so that the OTHER request group's row-GEMM CTAs (105 KB) always find room next to it (paired decoder step).
-__global__ void __launch_bounds__(160, 4)  // <= 102 registers: two of these CTAs and a row-GEMM CTA (168 registers x 192 threads) share an SM
+__global__ void __launch_bounds__(160, 2)
 dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int* __restrict__ group_first_row,
                                const int* __restrict__ group_n_rows, const int* __restrict__ group_xslot,
-                               const float* __restrict__ q, int T_enc, int n_layer, int layer, int d, int n_head, int n_groups,
-                               int n_split, int n_stages, bf16* __restrict__ out, float* __restrict__ ws,
-                               unsigned long long* trace_buf) {
+                               const float* __restrict__ q, int T_enc, int n_layer, int layer, int d, int n_split,
+                               bf16* __restrict__ out, float* __restrict__ ws, unsigned long long* trace_buf) {
   extern __shared__ uint8_t smem_raw[];
   unsigned long long* trace = nullptr;
   unsigned ttag = 4u << 24;
   if (threadIdx.x == 0) {
-    if (blockIdx.x == 0) trace = trace_buf;
-    else if (blockIdx.x == gridDim.x - 1) { trace = trace_buf; ttag = 5u << 24; }
+    if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0) trace = trace_buf;
+    else if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1) { trace = trace_buf; ttag = 5u << 24; }
   }
   trace_mark(trace, ttag | 1);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + xsm_bar(n_stages));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + XSM_BAR);
   uint64_t* empty_bar = full_bar + XSTAGES;
-  float* red = reinterpret_cast<float*>(smem + xsm_red(n_stages));  // [4 warps][8 rows][66]: m, l, o[64]
+  float* red = reinterpret_cast<float*>(smem + XSM_RED);  // [4 warps][8 rows][66]: m, l, o[64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = n_head * n_groups * n_split;
+  const int h = blockIdx.x, g = blockIdx.y, sp = blockIdx.z, n_head = gridDim.x;
+  const int row0 = group_first_row[g], nq = group_n_rows[g];
   const int chunk = ((T_enc + n_split - 1) / n_split + XT - 1) / XT * XT;
+  const int t0 = sp * chunk, t1 = min(T_enc, t0 + chunk);
+  const int n_tiles = (t1 - t0 + XT - 1) / XT;  // may be 0 for a trailing split
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm);
-    for (int s = 0; s < n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
+    for (int s = 0; s < XSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
     fence_barrier_init();
   }
   __syncthreads();
@@ -81,40 +76,22 @@ dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int
   pdl_trigger();
 
   if (warp == 4) {
-    // ---- producer: free-running over the CTA's items, throttled by the ring only ----
     if (lane == 0) {
-      int it_base = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int h = item % n_head, g = (item / n_head) % n_groups, sp = item / (n_head * n_groups);
-        const int t0 = sp * chunk, t1 = min(T_enc, t0 + chunk);
-        const int n_tiles = (t1 - t0 + XT - 1) / XT;  // may be 0 for a trailing split
-        const int zc = group_xslot[g] * n_layer + layer;
-        for (int it = 0; it < n_tiles; ++it) {
-          const int gi = it_base + it, s = gi % n_stages;
-          mbar_wait(&empty_bar[s], ((gi / n_stages) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], 2 * XTILE_BYTES);
-          uint8_t* ks = smem + s * 2 * XTILE_BYTES;
-          tma_load_3d(ks, &tm, &full_bar[s], h * 64, t0 + it * XT, zc);
-          tma_load_3d(ks + XTILE_BYTES, &tm, &full_bar[s], d + h * 64, t0 + it * XT, zc);
-        }
-        it_base += n_tiles;
+      const int zc = group_xslot[g] * n_layer + layer;
+      for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % XSTAGES;
+        mbar_wait(&empty_bar[s], ((it / XSTAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], 2 * XTILE_BYTES);
+        uint8_t* ks = smem + s * 2 * XTILE_BYTES;
+        tma_load_3d(ks, &tm, &full_bar[s], h * 64, t0 + it * XT, zc);
+        tma_load_3d(ks + XTILE_BYTES, &tm, &full_bar[s], d + h * 64, t0 + it * XT, zc);
       }
     }
     __syncwarp();
-    return;
-  }
-  // ---- consumers (4 warps): one item after the other; the 128 of them synchronise among themselves (bar 1) ----
-  pdl_wait();
-  trace_mark(trace, ttag | 2);
-  const int gid = lane >> 2, tig = lane & 3;  // query row (hypothesis) and column pair inside an n-tile
-  const int lrow = lane & 7, lmat = lane >> 3;  // ldmatrix lane roles
-  const float LOG2E = 1.4426950408889634f;
-  int it_base = 0;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int h = item % n_head, g = (item / n_head) % n_groups, sp = item / (n_head * n_groups);
-    const int row0 = group_first_row[g], nq = group_n_rows[g];
-    const int t0 = sp * chunk, t1 = min(T_enc, t0 + chunk);
-    const int n_tiles = (t1 - t0 + XT - 1) / XT;
+  } else {
+    pdl_wait();
+    trace_mark(trace, ttag | 2);
+    const int gid = lane >> 2, tig = lane & 3;  // query row (hypothesis) and column pair inside an n-tile
     // A fragments of q (rows 8..15 are zero): 4 k-steps of 16 dims; 1/sqrt(64) folded in (exact in bf16)
     uint32_t qa[4][2];
 #pragma unroll
@@ -127,13 +104,16 @@ dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int
       qa[ks][0] = pack_bf16x2(v0, v1);
       qa[ks][1] = pack_bf16x2(v2, v3);
     }
+    const float LOG2E = 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;  // running max (log2 domain) and this thread's partial row sum
     float o[8][4];
 #pragma unroll
     for (int nd = 0; nd < 8; ++nd) { o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f; }
+    // ldmatrix lane roles
+    const int lrow = lane & 7, lmat = lane >> 3;
     for (int it = 0; it < n_tiles; ++it) {
-      const int gi = it_base + it, s = gi % n_stages;
-      mbar_wait(&full_bar[s], (gi / n_stages) & 1);
+      const int s = it % XSTAGES;
+      mbar_wait(&full_bar[s], (it / XSTAGES) & 1);
       const uint32_t kbase = smem_u32(smem + s * 2 * XTILE_BYTES);
       const uint32_t vbase = kbase + XTILE_BYTES;
       // ---- S[16 x 16 keys] = Q . K^T for this warp's keys [warp*16, +16) ----
@@ -186,7 +166,6 @@ dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
-    it_base += n_tiles;
     // row sum over the 4 threads of a quad, then park this warp's partial
     l += __shfl_xor_sync(0xffffffffu, l, 1);
     l += __shfl_xor_sync(0xffffffffu, l, 2);
@@ -194,41 +173,40 @@ dec_cross_attention_mma_kernel(const __grid_constant__ CUtensorMap tm, const int
     if (tig == 0) { mine[0] = m; mine[1] = l; }
 #pragma unroll
     for (int nd = 0; nd < 8; ++nd) { mine[2 + nd * 8 + tig * 2] = o[nd][0]; mine[2 + nd * 8 + tig * 2 + 1] = o[nd][1]; }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    // merge the 4 warps: thread -> (row, 4 dims)
-    {
-      const int r = threadIdx.x >> 4, c4 = (threadIdx.x & 15) * 4;
-      if (r < nq) {
-        float M = -INFINITY;
+  }
+  __syncthreads();
+  // merge the 4 warps: thread -> (row, 4 dims)
+  if (threadIdx.x < 128) {
+    const int r = threadIdx.x >> 4, c4 = (threadIdx.x & 15) * 4;
+    if (r < nq) {
+      float M = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) M = fmaxf(M, red[(w * 8 + r) * 66]);
-        float num[4] = {0.f, 0.f, 0.f, 0.f}, den = 0.f;
-        if (M != -INFINITY) {
+      for (int w = 0; w < 4; ++w) M = fmaxf(M, red[(w * 8 + r) * 66]);
+      float num[4] = {0.f, 0.f, 0.f, 0.f}, den = 0.f;
+      if (M != -INFINITY) {
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const float* pr = red + (w * 8 + r) * 66;
-            const float e = fast_exp2(pr[0] - M);
-            den = fmaf(e, pr[1], den);
+        for (int w = 0; w < 4; ++w) {
+          const float* pr = red + (w * 8 + r) * 66;
+          const float e = fast_exp2(pr[0] - M);
+          den = fmaf(e, pr[1], den);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) num[i] = fmaf(e, pr[2 + c4 + i], num[i]);
-          }
-        }
-        const int row = row0 + r;
-        if (n_split == 1) {
-          const float inv = 1.f / den;
-          uint2 t;
-          t.x = pack_bf16x2(num[0] * inv, num[1] * inv);
-          t.y = pack_bf16x2(num[2] * inv, num[3] * inv);
-          *reinterpret_cast<uint2*>(out + (long long)row * d + h * 64 + c4) = t;
-        } else {
-          float* w = ws + (((long long)row * n_head + h) * kMaxSplitX + sp) * 66;
-          if (c4 == 0) { w[0] = (M == -INFINITY) ? -INFINITY : M * 0.6931471805599453f; w[1] = den; }  // natural-log max
-#pragma unroll
-          for (int i = 0; i < 4; ++i) w[2 + c4 + i] = num[i];
+          for (int i = 0; i < 4; ++i) num[i] = fmaf(e, pr[2 + c4 + i], num[i]);
         }
       }
+      const int row = row0 + r;
+      if (n_split == 1) {
+        const float inv = 1.f / den;
+        uint2 t;
+        t.x = pack_bf16x2(num[0] * inv, num[1] * inv);
+        t.y = pack_bf16x2(num[2] * inv, num[3] * inv);
+        *reinterpret_cast<uint2*>(out + (long long)row * d + h * 64 + c4) = t;
+      } else {
+        float* w = ws + (((long long)row * n_head + h) * kMaxSplitX + sp) * 66;
+        if (c4 == 0) { w[0] = (M == -INFINITY) ? -INFINITY : M * 0.6931471805599453f; w[1] = den; }  // natural-log max
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[2 + c4 + i] = num[i];
+      }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // `red` is free for the next item
   }
   trace_mark(trace, ttag | 8);
 }
@@ -242,7 +220,7 @@ void dec_cross_attention_mma(const int* group_first_row, const int* group_n_rows
   int dev = 0;
   BW_CUDA(cudaGetDevice(&dev));
   if (!(attr_set.load() >> dev & 1ull)) {
-    BW_CUDA(cudaFuncSetAttribute(dec_cross_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xsm_total(XSTAGES)));
+    BW_CUDA(cudaFuncSetAttribute(dec_cross_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XSM_TOTAL));
     attr_set.fetch_or(1ull << dev);
   }
   // one map per (cache pointer, geometry); cheap enough to rebuild, but the decoder calls this 32x per step
@@ -254,16 +232,9 @@ void dec_cross_attention_mma(const int* group_first_row, const int* group_n_rows
     cached_ptr = kv.cache; cached_geo[0] = d; cached_geo[1] = kv.T_enc; cached_geo[2] = kv.n_slots; cached_geo[3] = n_layer;
   }
   const CUtensorMap tm = cached_tm;
-  static const int env_stages = getenv("B200W_XATTN_STAGES") ? atoi(getenv("B200W_XATTN_STAGES")) : 0;
-  const int n_stages = std::max(2, std::min(XSTAGES, kv.ring_stages > 0 ? kv.ring_stages : env_stages > 0 ? env_stages : XSTAGES));
-  const int n_items = n_head * n_groups * n_split;
-  static int sm_count[64];
-  if (sm_count[dev] == 0) BW_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-  // kv.ring_stages > 0 (paired step): persistent grid of 2 CTAs per SM with a pinned shared-memory footprint
-  static const bool force_persistent = getenv("B200W_XATTN_PERSIST") != nullptr;  // tests: the persistent form for every launch
-  const int grid = (kv.ring_stages > 0 || force_persistent) ? std::min(n_items, 2 * sm_count[dev]) : n_items;
-  launch_kernel(dec_cross_attention_mma_kernel, dim3(grid), dim3(160), (size_t)xsm_total(n_stages), stream, tm, group_first_row,
-                group_n_rows, group_xslot, q, kv.T_enc, n_layer, layer, d, n_head, n_groups, n_split, n_stages, out, ws, g_trace_dev);
+  dim3 grid(n_head, n_groups, n_split);
+  launch_kernel(dec_cross_attention_mma_kernel, grid, dim3(160), XSM_TOTAL, stream, tm, group_first_row, group_n_rows, group_xslot, q,
+                kv.T_enc, n_layer, layer, d, n_split, out, ws, g_trace_dev);
   ++g_kernel_launches;
 }
 

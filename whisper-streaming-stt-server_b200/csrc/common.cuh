@@ -42,33 +42,15 @@ struct PdlScope {
   explicit PdlScope(bool on) : prev(tl_pdl) { tl_pdl = on; }
   ~PdlScope() { tl_pdl = prev; }
 };
-// Per-launch scheduling priority (cudaLaunchAttributePriority) of the kernels launched inside a PriorityScope; 0 = unset.
-// The paired decoder step gives the latency-bound chain kernels a higher priority than the cross-attention stream.
-extern thread_local int tl_priority;
-struct PriorityScope {
-  int prev;
-  explicit PriorityScope(int p) : prev(tl_priority) { tl_priority = p; }
-  ~PriorityScope() { tl_priority = prev; }
-};
-constexpr int kPrioritySet = 1 << 20;  // tl_priority = kPrioritySet + value (so that value 0 can be requested)
 template <typename... KArgs, typename... Args>
 inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  int na = 0;
-  if (tl_pdl) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
-  if (tl_priority != 0) {
-    attr[na].id = cudaLaunchAttributePriority;
-    attr[na].val.priority = tl_priority - kPrioritySet;
-    ++na;
-  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = na;
+  cfg.numAttrs = tl_pdl ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
   if (e != cudaSuccess) throw CudaError(std::string("kernel launch -> ") + cudaGetErrorString(e));
 }

@@ -275,65 +275,34 @@ struct Impl {
     g.xb_out = xb_out; g.ln_stats_out = st_out; g.ln_stats_in = st_in; g.ln_c1 = c1;
     gemm_tc_rows(g, stream);
   }
-  // ---- the fused-LayerNorm decoder step in pieces (one group = one set of activation buffers on this Impl's stream) ----
-  CrossKV cross_kv_desc(int ring_stages) const {
+  void decoder_layers_fused(const StepCtl& c, DecGroup& G, const DecRows& rows) const {
     const auto& d = D();
+    const int dm = d.n_text_state, L = d.n_text_layer, H = d.n_text_head;
+    cudaStream_t st = stream;
+    float* x = G.d_x.as<float>();
+    bf16* xb = G.d_xb.as<bf16>();
+    float2* lst = G.d_lnst.as<float2>();
+    dec_embed_ln<bf16>(rows, e->ss.next_tok, reinterpret_cast<const bf16*>(e->w.tok_emb), reinterpret_cast<const bf16*>(e->w.dec_pos), x, dm,
+                       xb, lst, e->d_page_table.as<int>(), e->n_blocks, st);
+    const SelfKV skv = self_kv();
     CrossKV xkv;
-    xkv.cache = e->cross_cache.p; xkv.slot_stride = (long long)d.n_text_layer * d.n_audio_ctx * 2 * d.n_text_state;
-    xkv.T_enc = d.n_audio_ctx; xkv.n_slots = e->Q; xkv.n_layer = d.n_text_layer; xkv.ring_stages = ring_stages;
-    return xkv;
-  }
-  DecRows rows_of(const StepCtl& c) const {
-    DecRows rows;
-    rows.n_rows = c.R; rows.row_seq = c.row_seq; rows.row_pos = c.row_pos; rows.row_tok = c.row_tok; rows.row_bpos = c.row_bpos;
-    rows.row_page = c.row_page; rows.max_ctx = c.max_ctx;
-    return rows;
-  }
-  void fused_embed(const StepCtl& c, DecGroup& G) const {
-    dec_embed_ln<bf16>(rows_of(c), e->ss.next_tok, reinterpret_cast<const bf16*>(e->w.tok_emb), reinterpret_cast<const bf16*>(e->w.dec_pos),
-                       G.d_x.as<float>(), D().n_text_state, G.d_xb.as<bf16>(), G.d_lnst.as<float2>(), e->d_page_table.as<int>(), e->n_blocks,
-                       stream);
-  }
-  // self-attention block + cross-attention query of layer l (everything in front of the cross-attention stream)
-  void fused_pre(const StepCtl& c, DecGroup& G, int l) const {
-    const int dm = D().n_text_state, H = D().n_text_head, Ra = e->R_max;
-    const LayerW& w = e->w.dec[l];
-    float* x = G.d_x.as<float>();
-    bf16* xb = G.d_xb.as<bf16>();
-    float2* lst = G.d_lnst.as<float2>();
-    rows_gemm(xb, c.R, Ra, w.wqkv, 3 * dm, dm, w.c2_qkv, nullptr, G.d_qkv.p, false, true, nullptr, nullptr, lst, w.c1_qkv);
-    dec_self_attention<bf16>(rows_of(c), G.d_qkv.as<float>(), self_kv(), l, dm, H, G.d_att.as<bf16>(), stream);
-    rows_gemm(G.d_att.p, c.R, Ra, w.wo, dm, dm, w.bo, x, x, false, true, xb, lst, nullptr, nullptr);
-    rows_gemm(xb, c.R, Ra, w.wq_x, dm, dm, w.c2_qx, nullptr, G.d_q.p, false, true, nullptr, nullptr, lst, w.c1_qx);
-  }
-  void fused_xattn(const StepCtl& c, DecGroup& G, int l, int ring_stages = 0) const {
-    dec_cross_attention<bf16>(c.grp_first, c.grp_n, c.grp_x, c.n_groups, c.max_group_rows, c.R, G.d_q.as<float>(), cross_kv_desc(ring_stages), l,
-                              D().n_text_state, D().n_text_head, G.d_att.as<bf16>(), G.d_ws.as<float>(), stream);
-  }
-  // cross-attention out-projection + MLP of layer l
-  void fused_post(const StepCtl& c, DecGroup& G, int l) const {
-    const int dm = D().n_text_state, Ra = e->R_max;
-    const LayerW& w = e->w.dec[l];
-    float* x = G.d_x.as<float>();
-    bf16* xb = G.d_xb.as<bf16>();
-    float2* lst = G.d_lnst.as<float2>();
-    rows_gemm(G.d_att.p, c.R, Ra, w.wo_x, dm, dm, w.bo_x, x, x, false, true, xb, lst, nullptr, nullptr);
-    rows_gemm(xb, c.R, Ra, w.w1, 4 * dm, dm, w.c2_w1, nullptr, G.d_h.p, true, false, nullptr, nullptr, lst, w.c1_w1);
-    rows_gemm(G.d_h.p, c.R, Ra, w.w2, dm, 4 * dm, w.b2, x, x, false, true, xb, lst, nullptr, nullptr);
-  }
-  void fused_final(const StepCtl& c, DecGroup& G) const {
-    const int dm = D().n_text_state;
-    layernorm_gather<bf16>(G.d_x.as<float>(), c.lrow_src, e->w.ln_g, e->w.ln_b, G.d_lnrows.as<bf16>(), c.n_lrows, dm, stream);
-    linear_rows(G.d_lnrows.as<bf16>(), c.n_lrows, e->LR_max, e->w.tok_emb, D().n_vocab, dm, nullptr, nullptr, G.d_logits.p, false, true);
-  }
-  void decoder_layers_fused(const StepCtl& c, DecGroup& G, const DecRows&) const {
-    fused_embed(c, G);
-    for (int l = 0; l < D().n_text_layer; ++l) {
-      fused_pre(c, G, l);
-      fused_xattn(c, G, l);
-      fused_post(c, G, l);
+    xkv.cache = e->cross_cache.p; xkv.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; xkv.T_enc = d.n_audio_ctx;
+    xkv.n_slots = e->Q; xkv.n_layer = L;
+    const int Ra = e->R_max;
+    for (int l = 0; l < L; ++l) {
+      const LayerW& w = e->w.dec[l];
+      rows_gemm(xb, c.R, Ra, w.wqkv, 3 * dm, dm, w.c2_qkv, nullptr, G.d_qkv.p, false, true, nullptr, nullptr, lst, w.c1_qkv);
+      dec_self_attention<bf16>(rows, G.d_qkv.as<float>(), skv, l, dm, H, G.d_att.as<bf16>(), st);
+      rows_gemm(G.d_att.p, c.R, Ra, w.wo, dm, dm, w.bo, x, x, false, true, xb, lst, nullptr, nullptr);
+      rows_gemm(xb, c.R, Ra, w.wq_x, dm, dm, w.c2_qx, nullptr, G.d_q.p, false, true, nullptr, nullptr, lst, w.c1_qx);
+      dec_cross_attention<bf16>(c.grp_first, c.grp_n, c.grp_x, c.n_groups, c.max_group_rows, c.R, G.d_q.as<float>(), xkv, l, dm, H,
+                                G.d_att.as<bf16>(), G.d_ws.as<float>(), st);
+      rows_gemm(G.d_att.p, c.R, Ra, w.wo_x, dm, dm, w.bo_x, x, x, false, true, xb, lst, nullptr, nullptr);
+      rows_gemm(xb, c.R, Ra, w.w1, 4 * dm, dm, w.c2_w1, nullptr, G.d_h.p, true, false, nullptr, nullptr, lst, w.c1_w1);
+      rows_gemm(G.d_h.p, c.R, Ra, w.w2, dm, 4 * dm, w.b2, x, x, false, true, xb, lst, nullptr, nullptr);
     }
-    fused_final(c, G);
+    layernorm_gather<bf16>(x, c.lrow_src, e->w.ln_g, e->w.ln_b, G.d_lnrows.as<bf16>(), c.n_lrows, dm, st);
+    linear_rows(G.d_lnrows.as<bf16>(), c.n_lrows, e->LR_max, e->w.tok_emb, d.n_vocab, dm, nullptr, nullptr, G.d_logits.p, false, true);
   }
 
   void window_to_A1(const float* logmel, int ld, int n_real, const int* gmax, int seek, int seg, int bi) const {
@@ -547,57 +516,6 @@ void engine_decoder_layers(bw_engine* e, DecGroup& G, int R, int n_groups, int m
     c.row_seq = row_seq; c.row_pos = row_pos; c.row_tok = row_tok; c.row_bpos = row_bpos; c.row_page = row_page; c.grp_first = grp_first; c.grp_n = grp_n; c.grp_x = grp_x; c.lrow_src = lrow_src;
     Impl<bf16>(e, G.stream).decoder_layers(c, G);
   }
-}
-// Two request groups through the decoder layers on two streams with a TURNSTILE on the cross-attention kernels: the
-// HBM-bound streams of the two groups strictly alternate (A.x(l), B.x(l), A.x(l+1), ...), so that while one group
-// streams its cached encoder K/V the other group's latency-bound chain (3 + 4 row GEMMs, self-attention) runs underneath
-// it.  Cross-attention runs with a 3-stage ring (59 KB per CTA, 2 CTAs per SM) so that a row-GEMM CTA (105 KB) of the other
-// group fits next to it on every SM.  s0 is the origin stream (graph capture starts there); s1 is forked from it here and
-// must be joined by the caller after it has enqueued the per-group sampling kernels.
-void engine_decoder_layers_pair(bw_engine* e, DecGroup& G0, const PairStepArgs& a0, DecGroup& G1, const PairStepArgs& a1) {
-  BW_CHECK(!e->fp32 && e->fuse_ln, "the paired decoder step exists for the bf16 product mode only");
-  auto ctl = [](const PairStepArgs& a) {
-    Impl<bf16>::StepCtl c;
-    c.R = a.R; c.n_groups = a.n_groups; c.max_group_rows = a.max_group_rows; c.n_lrows = a.n_lrows; c.max_ctx = a.max_ctx;
-    c.row_seq = a.row_seq; c.row_pos = a.row_pos; c.row_tok = a.row_tok; c.row_bpos = a.row_bpos; c.row_page = a.row_page;
-    c.grp_first = a.grp_first; c.grp_n = a.grp_n; c.grp_x = a.grp_x; c.lrow_src = a.lrow_src;
-    return c;
-  };
-  const Impl<bf16>::StepCtl c0 = ctl(a0), c1 = ctl(a1);
-  Impl<bf16> i0(e, G0.stream), i1(e, G1.stream);
-  cudaStream_t s0 = G0.stream, s1 = G1.stream;
-  static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;
-  static const int ring = getenv("B200W_PAIR_RING") ? atoi(getenv("B200W_PAIR_RING")) : 3;
-  // launch priorities: the chain kernels must win freed SM resources over the queued cross-attention CTAs
-  static int prio_lo = 0, prio_hi = 0;
-  static const bool use_prio = getenv("B200W_PAIR_NO_PRIO") == nullptr;
-  static const bool prio_init = (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi), true);
-  (void)prio_init;
-  const int p_chain = use_prio ? kPrioritySet + prio_hi : 0, p_x = use_prio ? kPrioritySet + prio_lo : 0;
-  BW_CUDA(cudaEventRecord(e->pair_fork, s0));
-  BW_CUDA(cudaStreamWaitEvent(s1, e->pair_fork, 0));
-  const int L = e->dims.n_text_layer;
-  {
-    PdlScope pdl(use_pdl);
-    PriorityScope pr(p_chain);
-    i0.fused_embed(c0, G0);
-    i1.fused_embed(c1, G1);
-  }
-  for (int l = 0; l < L; ++l) {
-    { PdlScope pdl(use_pdl); PriorityScope pr(p_chain); i0.fused_pre(c0, G0, l); }
-    if (l > 0) BW_CUDA(cudaStreamWaitEvent(s0, e->pair_xdone[1], 0));
-    { PdlScope pdl(use_pdl && l == 0); PriorityScope pr(p_x); i0.fused_xattn(c0, G0, l, ring); }  // behind a cross-stream wait: plain launch
-    BW_CUDA(cudaEventRecord(e->pair_xdone[0], s0));
-    { PdlScope pdl(use_pdl); PriorityScope pr(p_chain); i1.fused_pre(c1, G1, l); }
-    BW_CUDA(cudaStreamWaitEvent(s1, e->pair_xdone[0], 0));
-    { PdlScope pdl(false); PriorityScope pr(p_x); i1.fused_xattn(c1, G1, l, ring); }
-    BW_CUDA(cudaEventRecord(e->pair_xdone[1], s1));
-    { PdlScope pdl(use_pdl); PriorityScope pr(p_chain); i0.fused_post(c0, G0, l); i1.fused_post(c1, G1, l); }
-  }
-  PdlScope pdl(use_pdl);
-  PriorityScope pr(p_chain);
-  i0.fused_final(c0, G0);
-  i1.fused_final(c1, G1);
 }
 void engine_gather_final(bw_engine* e, const int* list_dev, int n, int blob_bytes, unsigned char* out_dev) {
   if (n <= 0) return;

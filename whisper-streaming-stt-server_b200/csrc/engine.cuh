@@ -76,18 +76,15 @@ enum ReqKind { REQ_DECODE = 0, REQ_LANG = 1, REQ_LOGITS = 2 };
 // underneath another group's HBM-bound cross-attention.
 struct StepGraphKey {
   int R, NG, LR, SR, NA, NNS, max_grp, anc, self_chunk;  // self_chunk: the self-attention launch geometry (dec_self_chunk)
-  int R1 = 0, NG1 = 0, LR1 = 0, SR1 = 0, NA1 = 0, NNS1 = 0, max_grp1 = 0, self_chunk1 = 0;  // second group of a paired step
   bool operator==(const StepGraphKey& o) const {
     return R == o.R && NG == o.NG && LR == o.LR && SR == o.SR && NA == o.NA && NNS == o.NNS && max_grp == o.max_grp && anc == o.anc &&
-           self_chunk == o.self_chunk && R1 == o.R1 && NG1 == o.NG1 && LR1 == o.LR1 && SR1 == o.SR1 && NA1 == o.NA1 && NNS1 == o.NNS1 &&
-           max_grp1 == o.max_grp1 && self_chunk1 == o.self_chunk1;
+           self_chunk == o.self_chunk;
   }
 };
 struct StepGraphKeyHash {
   size_t operator()(const StepGraphKey& k) const {
     size_t h = 1469598103934665603ull;
-    for (int v : {k.R, k.NG, k.LR, k.SR, k.NA, k.NNS, k.max_grp, k.anc, k.self_chunk, k.R1, k.NG1, k.LR1, k.SR1, k.NA1, k.NNS1, k.max_grp1,
-                  k.self_chunk1}) h = (h ^ (size_t)v) * 1099511628211ull;
+    for (int v : {k.R, k.NG, k.LR, k.SR, k.NA, k.NNS, k.max_grp, k.anc, k.self_chunk}) h = (h ^ (size_t)v) * 1099511628211ull;
     return h;
   }
 };
@@ -109,12 +106,6 @@ struct DecGroup {
   int* h_ctrl = nullptr;  // pinned host copy of the control block
 };
 constexpr int kMaxGroups = 4;
-
-// device-side description of one group's step (what engine_decoder_layers takes as separate arguments)
-struct PairStepArgs {
-  int R, n_groups, max_group_rows, n_lrows, max_ctx;
-  const int *row_seq, *row_pos, *row_tok, *row_bpos, *row_page, *grp_first, *grp_n, *grp_x, *lrow_src;
-};
 
 // polyphase filter bank of one source sample rate (bw_engine_set_resampler)
 struct Resampler {
@@ -196,7 +187,6 @@ struct bw_engine {
   static constexpr int kEncStreams = 3;                // extra streams for the sub-batches of a split encoder batch
   cudaStream_t enc_streams[kEncStreams]{};
   cudaEvent_t enc_fork = nullptr, enc_join[kEncStreams]{};
-  cudaEvent_t pair_fork = nullptr, pair_join = nullptr, pair_xdone[2]{};  // paired decoder step (two request groups, turnstile)
   static constexpr int kFrontStreams = 4;
   cudaStream_t front[kFrontStreams]{};
   std::mutex front_mu[kFrontStreams];

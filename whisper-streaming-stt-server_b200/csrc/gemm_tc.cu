@@ -21,7 +21,6 @@ namespace bw {
 
 std::atomic<long long> g_kernel_launches{0};
 thread_local bool tl_pdl = false;
-thread_local int tl_priority = 0;
 unsigned long long* g_trace_dev = nullptr;
 
 namespace {
@@ -1165,23 +1164,13 @@ void launch_rows(const GemmArgs& g, cudaStream_t stream) {
   cfg.dynamicSmemBytes = R_SMEM_TOTAL;
   cfg.stream = stream;
   if (KS == 1) BW_CHECK(!g.xb_out && !g.ln_stats_out, "the unsplit row GEMM has no LayerNorm-producer epilogue");
-  cudaLaunchAttribute attr[3];
-  int na = 0;
-  attr[na].id = cudaLaunchAttributeClusterDimension;
-  attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = KS;
-  ++na;
-  if (tl_pdl) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
-  if (tl_priority != 0) {
-    attr[na].id = cudaLaunchAttributePriority;
-    attr[na].val.priority = tl_priority - kPrioritySet;
-    ++na;
-  }
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = KS;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = na;
+  cfg.numAttrs = tl_pdl ? 2 : 1;
   BW_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   ++g_kernel_launches;
 }

@@ -184,8 +184,8 @@ void synthetic_step(bw_engine* e, Ctl* ctls, int n_segments, int n_group, int cu
       ++c.R; ++c.LR; ++c.SR;
     }
   }
-  const bool joined = enqueue_step(e, ctls, ng);
-  if (joined) {
+  for (int g = 0; g < ng; ++g) enqueue_group_step(e, e->grp[g], ctls[g]);
+  if (ng == 1) {
     BW_CUDA(cudaMemcpyAsync(e->h_flags, e->st_step.p, e->step_out_bytes, cudaMemcpyDeviceToHost, e->grp[0].stream));
     BW_CUDA(cudaStreamSynchronize(e->grp[0].stream));
   } else {

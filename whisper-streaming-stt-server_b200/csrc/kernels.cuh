@@ -116,7 +116,6 @@ struct CrossKV {
   int T_enc = 1500;
   int n_slots = 0;               // slots behind `cache` (TMA map extent)
   int n_layer = 0;
-  int ring_stages = 0;           // bf16 kernel: depth of the K|V tile ring per CTA (0 = default 6; 3 leaves room for a co-resident row GEMM)
 };
 template <typename T>
 void dec_cross_attention(const int* group_first_row, const int* group_n_rows, const int* group_xslot, int n_groups,

@@ -21,7 +21,6 @@ void engine_window_to_A1(bw_engine* e, const float* logmel, int ld, int n_real, 
 void engine_decoder_layers(bw_engine* e, DecGroup& G, int R, int n_groups, int max_group_rows, int n_lrows, int max_ctx, const int* row_seq,
                            const int* row_pos, const int* row_tok, const int* row_bpos, const int* row_page, const int* grp_first,
                            const int* grp_n, const int* grp_x, const int* lrow_src);
-void engine_decoder_layers_pair(bw_engine* e, DecGroup& G0, const PairStepArgs& a0, DecGroup& G1, const PairStepArgs& a1);
 void engine_init_requests(bw_engine* e, const int* init_dev, int n);
 void engine_fold_layernorms(bw_engine* e);
 void engine_gather_final(bw_engine* e, const int* list_dev, int n, int blob_bytes, unsigned char* out_dev);
@@ -60,9 +59,6 @@ struct Ctl {
 
 // scheduler.cu
 void enqueue_group_step(bw_engine* e, DecGroup& G, Ctl& c);
-// the whole step of `ng` request groups: one group -> enqueue_group_step; two groups -> the paired (turnstile) step when
-// enabled, else one independent stream per group.  Leaves everything joined on grp[0].stream when it returns true.
-bool enqueue_step(bw_engine* e, Ctl* ctls, int ng);
 int choose_groups(int n_segments);
 void scheduler_main(bw_engine* e);
 // self-KV page pool (host free list; scheduler thread / synthetic benches only)

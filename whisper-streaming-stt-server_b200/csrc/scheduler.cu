@@ -20,21 +20,12 @@ void finish_request(Request* r, int status, const std::string& err) {
 
 // H2D of the control block + the whole decoder step (all layers, logits, filters/top-k, beam update) of one group,
 // enqueued on the group's stream.  No host synchronisation here.
-// logit filters / top-k / beam update of one group on its stream (after its logits are there)
-void enqueue_group_sampling(bw_engine* e, DecGroup& G, Ctl& c);
-
 void enqueue_group_step_eager(bw_engine* e, DecGroup& G, Ctl& c) {
   int* dbase = G.d_ctrl.as<int>();
   auto dev = [&](int* h) { return dbase + (h - c.base); };
   BW_CUDA(cudaMemcpyAsync(dbase, c.base, c.total * 4, cudaMemcpyHostToDevice, G.stream));
   engine_decoder_layers(e, G, c.R, c.NG, c.max_grp, c.LR, c.max_ctx, dev(c.row_seq), dev(c.row_pos), dev(c.row_tok), dev(c.row_bpos),
                         dev(c.row_page), dev(c.grp_first), dev(c.grp_n), dev(c.grp_x), dev(c.lrow_src));
-  enqueue_group_sampling(e, G, c);
-}
-
-void enqueue_group_sampling(bw_engine* e, DecGroup& G, Ctl& c) {
-  int* dbase = G.d_ctrl.as<int>();
-  auto dev = [&](int* h) { return dbase + (h - c.base); };
   const float* logits = G.d_logits.as<float>();
   const int V = e->dims.n_vocab;
   static const bool use_pdl = getenv("B200W_NO_PDL") == nullptr;
@@ -94,72 +85,6 @@ void enqueue_group_step(bw_engine* e, DecGroup& G, Ctl& c) {
       G.graphs.erase(it);
     }
   }
-}
-
-namespace {
-
-PairStepArgs pair_args(DecGroup& G, Ctl& c) {
-  int* dbase = G.d_ctrl.as<int>();
-  auto dev = [&](int* h) { return dbase + (h - c.base); };
-  PairStepArgs a;
-  a.R = c.R; a.n_groups = c.NG; a.max_group_rows = c.max_grp; a.n_lrows = c.LR; a.max_ctx = c.max_ctx;
-  a.row_seq = dev(c.row_seq); a.row_pos = dev(c.row_pos); a.row_tok = dev(c.row_tok); a.row_bpos = dev(c.row_bpos);
-  a.row_page = dev(c.row_page); a.grp_first = dev(c.grp_first); a.grp_n = dev(c.grp_n); a.grp_x = dev(c.grp_x); a.lrow_src = dev(c.lrow_src);
-  return a;
-}
-
-// both groups of a paired step, forked from and joined back onto grp[0].stream
-void enqueue_pair_step_eager(bw_engine* e, Ctl& c0, Ctl& c1) {
-  DecGroup &G0 = e->grp[0], &G1 = e->grp[1];
-  BW_CUDA(cudaMemcpyAsync(G0.d_ctrl.p, c0.base, c0.total * 4, cudaMemcpyHostToDevice, G0.stream));
-  BW_CUDA(cudaMemcpyAsync(G1.d_ctrl.p, c1.base, c1.total * 4, cudaMemcpyHostToDevice, G0.stream));
-  engine_decoder_layers_pair(e, G0, pair_args(G0, c0), G1, pair_args(G1, c1));
-  enqueue_group_sampling(e, G0, c0);
-  enqueue_group_sampling(e, G1, c1);
-  BW_CUDA(cudaEventRecord(e->pair_join, G1.stream));
-  BW_CUDA(cudaStreamWaitEvent(G0.stream, e->pair_join, 0));
-}
-
-void enqueue_pair_step(bw_engine* e, Ctl& c0, Ctl& c1) {
-  e->stat_h2d += (long long)(c0.total + c1.total) * 4;
-  DecGroup& G = e->grp[0];
-  static const bool use_graphs = getenv("B200W_NO_GRAPH") == nullptr;
-  if (!use_graphs) return enqueue_pair_step_eager(e, c0, c1);
-  StepGraphKey key{c0.R, c0.NG, c0.LR, c0.SR, c0.NA, c0.NNS, c0.max_grp, e->anc_cur, dec_self_chunk(c0.max_ctx)};
-  key.R1 = c1.R; key.NG1 = c1.NG; key.LR1 = c1.LR; key.SR1 = c1.SR; key.NA1 = c1.NA; key.NNS1 = c1.NNS; key.max_grp1 = c1.max_grp;
-  key.self_chunk1 = dec_self_chunk(c1.max_ctx);
-  StepGraph& sg = G.graphs[key];
-  sg.last_use = ++G.graph_clock;
-  if (sg.exec) { BW_CUDA(cudaGraphLaunch(sg.exec, G.stream)); return; }
-  if (++sg.seen < 3) return enqueue_pair_step_eager(e, c0, c1);
-  cudaGraph_t graph = nullptr;
-  BW_CUDA(cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal));
-  try {
-    enqueue_pair_step_eager(e, c0, c1);
-  } catch (...) {
-    cudaStreamEndCapture(G.stream, &graph);
-    if (graph) cudaGraphDestroy(graph);
-    throw;
-  }
-  BW_CUDA(cudaStreamEndCapture(G.stream, &graph));
-  cudaGraphExec_t exec = nullptr;
-  const cudaError_t st = cudaGraphInstantiate(&exec, graph, 0);
-  cudaGraphDestroy(graph);
-  if (st != cudaSuccess) throw CudaError(std::string("cudaGraphInstantiate (paired step) -> ") + cudaGetErrorString(st));
-  sg.exec = exec;
-  BW_CUDA(cudaGraphLaunch(exec, G.stream));
-}
-
-}  // namespace
-
-bool enqueue_step(bw_engine* e, Ctl* ctls, int ng) {
-  static const bool pair = getenv("B200W_PAIR") != nullptr && atoi(getenv("B200W_PAIR")) != 0;
-  if (ng == 2 && pair && !e->fp32 && e->fuse_ln && ctls[0].R > 0 && ctls[1].R > 0) {
-    enqueue_pair_step(e, ctls[0], ctls[1]);
-    return true;
-  }
-  for (int g = 0; g < ng; ++g) enqueue_group_step(e, e->grp[g], ctls[g]);
-  return ng == 1;
 }
 
 int choose_groups(int n_segments) {
@@ -506,8 +431,7 @@ void decode_step(bw_engine* e, Ctl* ctls) {
     }
   }
   int total_rows = 0;
-  for (int g = 0; g < ng; ++g) total_rows += ctls[g].R;
-  const bool joined = enqueue_step(e, ctls, ng);  // everything ordered behind grp[0].stream
+  for (int g = 0; g < ng; ++g) { enqueue_group_step(e, e->grp[g], ctls[g]); total_rows += ctls[g].R; }
   const int V = d.n_vocab;
   for (auto& s : lang_reqs) {
     DecGroup& G = e->grp[s.grp];
@@ -526,10 +450,9 @@ void decode_step(bw_engine* e, Ctl* ctls) {
                             (size_t)V * 4, cudaMemcpyDeviceToHost, e->grp[s.grp].stream));
   // completion flags: one D2H behind the step on the step's own stream, one host synchronisation per step
   // completion flags + the beam reorder (parent slot of every surviving hypothesis, what the page collector needs)
-  if (joined) {
+  if (ng == 1) {
     BW_CUDA(cudaMemcpyAsync(e->h_flags, e->st_step.p, e->step_out_bytes, cudaMemcpyDeviceToHost, e->grp[0].stream));
     BW_CUDA(cudaStreamSynchronize(e->grp[0].stream));
-    for (int g = 1; g < ng; ++g) BW_CUDA(cudaStreamSynchronize(e->grp[g].stream));  // read-backs queued behind the join
   } else {
     for (int g = 0; g < ng; ++g) BW_CUDA(cudaStreamSynchronize(e->grp[g].stream));
     BW_CUDA(cudaMemcpyAsync(e->h_flags, e->st_step.p, e->step_out_bytes, cudaMemcpyDeviceToHost, e->stream));
