@@ -72,6 +72,10 @@ int bw_test_dec_self_attention(int32_t n_rows, const int32_t* row_seq, const int
                                const int32_t* row_page, const float* qkv, void* pool, int32_t n_layer, int32_t n_ctx, int32_t n_units,
                                const int32_t* page_table, const int32_t* seq_first, const uint8_t* anc, int32_t layer, int32_t d,
                                int32_t n_head, int32_t max_ctx, void* out, void* stream);
+/* Which decoder self-attention kernel the bf16 path launches (process-wide; A-B runs and kernel tests): 0 = automatic
+ * (the persistent ring kernel), 1 = staged CTA per (row, head), 2 = warp per (row, head), 3 = mma.sync warp per
+ * (row, head), 4 = persistent cp.async ring. */
+int bw_test_self_attention_mode(int32_t mode);
 /* sample_topk_kernel on n independent logits rows (host pointers).  state[i][10] = n_beam, greedy, cur_len,
  * sample_begin, without_ts, suppress_blank, max_initial_ts (-1 = none), last token, the token before it (-1 = none),
  * most recent sampled timestamp token (-1 = none).  Writes the top-(n_beam + 1) (1 if greedy) candidates of each row:

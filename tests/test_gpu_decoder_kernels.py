@@ -163,9 +163,20 @@ def _run_self(rows, qkv, pool, pt, seq_first_dev_vals, anc, layer, d, n_head, n_
     return out
 
 
-@pytest.mark.parametrize("ctx", [1, 31, 32, 63, 100, 447])  # staging of 32 / 64 / 128 positions per pass, 1 .. 4 passes
+SELF_MODES = {"staged": 1, "warp": 2, "mma": 3, "ring": 4, "smma": 5}  # bw_test_self_attention_mode
+
+
+@pytest.fixture(params=sorted(SELF_MODES))
+def self_mode(request):
+    lib = L.load()
+    L.check(lib.bw_test_self_attention_mode(SELF_MODES[request.param]), "bw_test_self_attention_mode")
+    yield request.param
+    L.check(lib.bw_test_self_attention_mode(0), "bw_test_self_attention_mode")
+
+
+@pytest.mark.parametrize("ctx", [1, 31, 32, 63, 64, 100, 193, 447])  # 1 .. 7 ring items / staging passes, page and chunk edges
 @pytest.mark.parametrize("G", [1, 5, 8])
-def test_self_attention_bf16_cached_decode_through_ancestry(ctx, G):
+def test_self_attention_bf16_cached_decode_through_ancestry(ctx, G, self_mode):
     """one new token per hypothesis at position `ctx` (the step's row), `ctx` cached positions behind it.  G > 1: every
     cached position of every hypothesis lives in a RANDOM beam slot of its request (what beam reordering leaves behind);
     every (slot, block) sits on a random page of the pool."""
@@ -206,7 +217,28 @@ def test_self_attention_bf16_cached_decode_through_ancestry(ctx, G):
     assert not changed.any(), "the kernel wrote outside this step's (page, layer, position) rows"
 
 
-def test_self_attention_bf16_prefill_rows():
+def test_self_attention_bf16_many_units_per_cta(self_mode):
+    """more (row, head) units than resident CTAs: the persistent ring kernel walks several units per CTA, with contexts of
+    different lengths (0 .. 5 ring items) interleaved, so items cross unit boundaries in the ring"""
+    n_head, n_layer, layer, n_ctx = 6, 2, 1, 448
+    d = 64 * n_head
+    S = 300
+    g = torch.Generator(device=DEV).manual_seed(5)
+    pool, pt, nb = _paged_pool(S, n_layer, n_ctx, d, g, 11)
+    pool_before = pool.clone()
+    ctxs = [(7 * i * i + 3 * i) % 200 for i in range(S)]
+    ctxs[3] = 0; ctxs[50] = 0; ctxs[51] = 64; ctxs[52] = 128; ctxs[99] = 299
+    rows = {"seq": list(range(S)), "pos": ctxs, "bpos": ctxs}
+    anc = torch.zeros((S, n_ctx), dtype=torch.int64)
+    qkv = torch.randn((S, 3 * d), device=DEV, generator=g) * 1.5
+    out = _run_self(rows, qkv, pool, pt, [s | 0x40000000 for s in range(S)], anc, layer, d, n_head, n_ctx, n_layer)
+    ref = _self_ref(qkv, pool_before, pt, rows, list(range(S)), anc, layer, d, n_head)
+    assert torch.isfinite(out.float()).all()
+    per_row = (out.float() - ref).norm(dim=1) / ref.norm(dim=1)
+    assert _rel(out, ref) < 5e-3 and per_row.max().item() < 2.5e-2, (self_mode, _rel(out, ref), per_row.max().item())
+
+
+def test_self_attention_bf16_prefill_rows(self_mode):
     """prefill: n rows of one sequence fed in one step (bpos = 0): causal attention among this step's own rows, plus a
     second sequence continuing from a cached prefix in the same launch"""
     n_head, n_layer, layer, n_ctx = 20, 2, 0, 448

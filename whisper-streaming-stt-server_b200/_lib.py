@@ -105,6 +105,7 @@ SIGNATURES = {
     "bw_test_dec_cross_attention": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]),
     "bw_test_dec_self_attention": (C.c_int, [C.c_int32] + [C.c_void_p] * 6 + [C.c_int32] * 3 + [C.c_void_p] * 3 +
                                    [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]),
+    "bw_test_self_attention_mode": (C.c_int, [C.c_int32]),
     "bw_test_sample_topk": (C.c_int, [C.c_void_p, c_f32_p, C.c_int32, c_i32_p, c_i32_p, c_f32_p]),
     "bw_test_page_collector": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), c_i32_p]),
 }

@@ -244,6 +244,8 @@ int bw_engine_finalize(bw_engine* e) {
       BW_CUDA(cudaMemset(G.d_xb.p, 0, G.d_xb.bytes));
       BW_CUDA(cudaMemset(G.d_lnst.p, 0, G.d_lnst.bytes));
     }
+    G.d_pospage.alloc(R * (size_t)d.n_text_ctx * 4);
+    BW_CUDA(cudaMemset(G.d_pospage.p, 0, G.d_pospage.bytes));
     G.d_logits.alloc(LR * (size_t)d.n_vocab * 4);
     G.d_ws.alloc(dec_cross_workspace_floats((int)R, d.n_text_head) * 4);
     G.d_cand_tok.alloc(LR * kMaxCand * 4); G.d_cand_lp.alloc(LR * kMaxCand * 4);

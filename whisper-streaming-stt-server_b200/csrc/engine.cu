@@ -212,7 +212,7 @@ struct Impl {
     int R = 0, n_groups = 0, max_group_rows = 1, n_lrows = 0, max_ctx = 0;
     const int *row_seq, *row_pos, *row_tok, *row_bpos, *row_page, *grp_first, *grp_n, *grp_x, *lrow_src;
   };
-  SelfKV self_kv() const {
+  SelfKV self_kv(const DecGroup& G) const {
     const auto& d = D();
     SelfKV skv;
     skv.pool = e->self_pool.p;
@@ -220,6 +220,7 @@ struct Impl {
     skv.n_ctx = d.n_text_ctx; skv.n_blocks = e->n_blocks; skv.n_units = e->S;
     skv.page_table = e->d_page_table.as<int>();
     skv.seq_first = e->ss.seq_first; skv.anc = e->ss.anc[e->anc_cur];
+    skv.pospage = G.d_pospage.as<int>();
     return skv;
   }
   void decoder_layers(const StepCtl& c, DecGroup& G) const {
@@ -237,7 +238,8 @@ struct Impl {
     }
     dec_embed<T>(rows, e->ss.next_tok, reinterpret_cast<const T*>(e->w.tok_emb), reinterpret_cast<const T*>(e->w.dec_pos), x, dm,
                  e->d_page_table.as<int>(), e->n_blocks, st);
-    const SelfKV skv = self_kv();
+    const SelfKV skv = self_kv(G);
+    dec_self_pospage(rows, skv, st);
     CrossKV xkv;
     xkv.cache = e->cross_cache.p; xkv.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; xkv.T_enc = d.n_audio_ctx;
     xkv.n_slots = e->Q; xkv.n_layer = L;
@@ -284,7 +286,8 @@ struct Impl {
     float2* lst = G.d_lnst.as<float2>();
     dec_embed_ln<bf16>(rows, e->ss.next_tok, reinterpret_cast<const bf16*>(e->w.tok_emb), reinterpret_cast<const bf16*>(e->w.dec_pos), x, dm,
                        xb, lst, e->d_page_table.as<int>(), e->n_blocks, st);
-    const SelfKV skv = self_kv();
+    const SelfKV skv = self_kv(G);
+    dec_self_pospage(rows, skv, st);
     CrossKV xkv;
     xkv.cache = e->cross_cache.p; xkv.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; xkv.T_enc = d.n_audio_ctx;
     xkv.n_slots = e->Q; xkv.n_layer = L;

@@ -103,6 +103,7 @@ struct DecGroup {
   unsigned long long graph_clock = 0;
   DevBuf d_x, d_xn, d_qkv, d_att, d_q, d_h, d_lnrows, d_logits, d_ws, d_cand_tok, d_cand_lp, d_ctrl;
   DevBuf d_xb, d_lnst;  // LayerNorm fusion: bf16 copy of the residual stream, per-row / per-64-column partials
+  DevBuf d_pospage;     // [R_max][n_text_ctx] page of (row, position) for the step's self-attention (dec_self_pospage)
   int* h_ctrl = nullptr;  // pinned host copy of the control block
 };
 constexpr int kMaxGroups = 4;

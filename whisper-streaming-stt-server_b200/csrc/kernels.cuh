@@ -101,7 +101,13 @@ struct SelfKV {
   const int* page_table = nullptr;     // [n_units][n_blocks]
   const int* seq_first = nullptr;      // [S] first sequence slot of the owning request
   const unsigned char* anc = nullptr;  // [S][n_ctx] beam slot holding position t (current ping-pong buffer)
+  int* pospage = nullptr;              // [rows of the step][n_ctx] scratch: page of (row, position), see dec_self_pospage
 };
+// Once per step, after the embed kernel: resolves seq_first / ancestry / page table into pospage[r][t] for t < row_bpos[r],
+// so that the 32 layers' self-attention kernels follow one indirection instead of three.
+void dec_self_pospage(const DecRows& rows, const SelfKV& kv, cudaStream_t stream);
+// test / A-B hook: 0 = automatic, 1 = staged, 2 = warp per unit, 3 = mma, 4 = persistent ring (needs pospage)
+void dec_self_attention_mode(int mode);
 // out[r] = softmax(q_r . K[0..pos_r]) V   (head dim 64); q = first d columns of the fp32 qkv rows.
 // Also appends this step's k/v (columns d..3d of the row) to the row's page.
 template <typename T>
