@@ -66,15 +66,15 @@ int bw_test_dec_cross_attention(const void* cache, int32_t n_slots, int32_t n_la
                                 int32_t force_split, void* out, void* stream);
 /* dec_self_attention<bf16> (+ fused K/V append) on device pointers over a paged pool: pages of 16 positions,
  * [n_pages][n_layer][2][16][d] bf16; page_table int32 [n_units][ceil(n_ctx / 16)]; row_page[r] = page that receives row
- * r's k / v.  max_ctx = longest context (row_pos + 1) among the rows or 0: picks the staging size (32 / 64 / 128 positions
- * per pass).  Other arguments as bw::SelfKV / bw::DecRows. */
+ * r's k / v.  max_ctx = longest context (row_pos + 1) among the rows or 0: picks the staged kernel's staging size (32 / 64 /
+ * 128 positions per pass).  Other arguments as bw::SelfKV / bw::DecRows.  Runs dec_self_pospage first, like the step. */
 int bw_test_dec_self_attention(int32_t n_rows, const int32_t* row_seq, const int32_t* row_pos, const int32_t* row_bpos,
                                const int32_t* row_page, const float* qkv, void* pool, int32_t n_layer, int32_t n_ctx, int32_t n_units,
                                const int32_t* page_table, const int32_t* seq_first, const uint8_t* anc, int32_t layer, int32_t d,
                                int32_t n_head, int32_t max_ctx, void* out, void* stream);
 /* Which decoder self-attention kernel the bf16 path launches (process-wide; A-B runs and kernel tests): 0 = automatic
- * (the persistent ring kernel), 1 = staged CTA per (row, head), 2 = warp per (row, head), 3 = mma.sync warp per
- * (row, head), 4 = persistent cp.async ring. */
+ * (persistent warps from ~1000 (row, head) units upwards, else staged), 1 = staged CTA per (row, head), 2 = warp per
+ * (row, head), 3 = persistent warps on mma.sync. */
 int bw_test_self_attention_mode(int32_t mode);
 /* sample_topk_kernel on n independent logits rows (host pointers).  state[i][10] = n_beam, greedy, cur_len,
  * sample_begin, without_ts, suppress_blank, max_initial_ts (-1 = none), last token, the token before it (-1 = none),

@@ -90,6 +90,46 @@ def _logit_stats(got, ref):
 
 @pytest.mark.parametrize("name,n_sessions", [("test-tiny", 20), ("test-v3", 16), ("tiny.en", 16)])
 def test_teacher_forced_cached_decode_matches_oracle_logits(name, n_sessions):
+    _teacher_forced(name, n_sessions, f"r2_teacher_forced_{name}.json")
+
+
+def test_persistent_warp_self_attention_inside_the_engine():
+    """The test models are too small to reach the unit count from which the step takes the persistent-warp self-attention
+    kernel (large-v3 batches do: bench.py).  Force it process-wide and repeat (i) the teacher-forced cached decode against
+    the oracle's logits and (ii) a mixed greedy / beam-5 batch against the same batch under the staged kernel: identical
+    token streams, through beam reordering, paged K/V and prompt prefill rows."""
+    from b200_whisper import _lib as L
+
+    lib = L.load()
+
+    def mixed_batch(mode):
+        L.check(lib.bw_test_self_attention_mode(mode), "bw_test_self_attention_mode")
+        b = backend("test-tiny")
+        opts = dict(REALTIME, language="en")
+        audios = [synth_audio(700 + i, 2.5 + 0.5 * i) for i in range(12)]
+        out = [None] * len(audios)
+
+        def work(i):
+            out[i] = b.transcribe_raw(audios[i], **b._normalize_options(opts if i % 3 else dict(ACCURATE, language="en")))
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(len(audios))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        return [[s["tokens"] for s in r["segments"]] for r in out]
+
+    try:
+        L.check(lib.bw_test_self_attention_mode(3), "bw_test_self_attention_mode")
+        _teacher_forced("test-tiny", 12, "r2_teacher_forced_test-tiny_persistent_warps.json")
+        persistent = mixed_batch(3)
+        staged = mixed_batch(1)
+    finally:
+        L.check(lib.bw_test_self_attention_mode(0), "bw_test_self_attention_mode")
+    same = sum(a == c for a, c in zip(persistent, staged))
+    assert all(len(t) > 0 for r in persistent for t in r)
+    assert same >= len(staged) - 1, (same, len(staged))  # both kernels: fp32 math on the same bf16 K/V, different summation order
+
+
+def _teacher_forced(name, n_sessions, report_name):
     model = oracle_model(name)
     b = backend(name)
     audios = [synth_audio(300 + i, 2.0 + 0.45 * i) for i in range(n_sessions)]
@@ -117,7 +157,7 @@ def test_teacher_forced_cached_decode_matches_oracle_logits(name, n_sessions):
     rep = {"model": name, "sessions": n_sessions, "steps_per_session": int(np.mean([len(s) for s in streams])),
            "scheduler_steps": int(n_steps), "worst_step_rel_l2": worst, "argmax_agreement": float(agree_all.mean()),
            "oracle_argmax_in_bf16_top5": float(in5_all.mean())}
-    _report(f"r2_teacher_forced_{name}.json", rep)
+    _report(report_name, rep)
     assert in5_all.mean() >= 0.97 and agree_all.mean() >= 0.80, rep
 
 

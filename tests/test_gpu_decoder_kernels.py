@@ -163,7 +163,7 @@ def _run_self(rows, qkv, pool, pt, seq_first_dev_vals, anc, layer, d, n_head, n_
     return out
 
 
-SELF_MODES = {"staged": 1, "warp": 2, "mma": 3, "ring": 4, "smma": 5}  # bw_test_self_attention_mode
+SELF_MODES = {"staged": 1, "warp": 2, "persistent": 3}  # bw_test_self_attention_mode
 
 
 @pytest.fixture(params=sorted(SELF_MODES))
@@ -174,7 +174,7 @@ def self_mode(request):
     L.check(lib.bw_test_self_attention_mode(0), "bw_test_self_attention_mode")
 
 
-@pytest.mark.parametrize("ctx", [1, 31, 32, 63, 64, 100, 193, 447])  # 1 .. 7 ring items / staging passes, page and chunk edges
+@pytest.mark.parametrize("ctx", [1, 31, 32, 63, 64, 100, 193, 447])  # 1 .. 15 ring items / 1 .. 4 staging passes, page and chunk edges
 @pytest.mark.parametrize("G", [1, 5, 8])
 def test_self_attention_bf16_cached_decode_through_ancestry(ctx, G, self_mode):
     """one new token per hypothesis at position `ctx` (the step's row), `ctx` cached positions behind it.  G > 1: every
@@ -218,9 +218,9 @@ def test_self_attention_bf16_cached_decode_through_ancestry(ctx, G, self_mode):
 
 
 def test_self_attention_bf16_many_units_per_cta(self_mode):
-    """more (row, head) units than resident CTAs: the persistent ring kernel walks several units per CTA, with contexts of
-    different lengths (0 .. 5 ring items) interleaved, so items cross unit boundaries in the ring"""
-    n_head, n_layer, layer, n_ctx = 6, 2, 1, 448
+    """more (row, head) units than resident warps: the persistent kernel walks several units per warp, with contexts of
+    different lengths (1 .. 10 ring items) interleaved, so items cross unit boundaries in the ring"""
+    n_head, n_layer, layer, n_ctx = 20, 2, 1, 448  # 6000 units: 3 - 4 per resident warp
     d = 64 * n_head
     S = 300
     g = torch.Generator(device=DEV).manual_seed(5)

@@ -11,7 +11,7 @@ from b200_whisper import _lib as L  # noqa: E402
 n_req = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 G = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 ctx = int(sys.argv[3]) if len(sys.argv) > 3 else 100
-modes = [int(m) for m in os.environ.get("MODES", "1,2,3,4").split(",")]
+modes = [int(m) for m in os.environ.get("MODES", "1,2,3").split(",")]
 n_head, n_layer, n_ctx, P = 20, 4, 448, 16
 d = 64 * n_head
 dev = "cuda:0"

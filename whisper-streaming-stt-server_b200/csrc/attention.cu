@@ -457,30 +457,10 @@ dec_self_attention_warp_kernel(const int* __restrict__ row_seq, const int* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// v3 (bf16 product mode): one warp per (row, head) on mma.sync.m16n8k16, K / V straight from HBM into the B-operand
-// registers -- no shared-memory staging, no shuffles in the position loop.  ncu of the two kernels above shows them
-// INSTRUCTION-bound (profiles/r2_selfattn_warp_ncu.txt: ~3900 warp instructions per unit at context 100, issue slots
-// 46 % active; unpacking bf16 and the per-position address arithmetic dominate).  Here a 16-position block costs
-// 8 LDG.128 + 16 mma + 16 PRMT + a 4-value softmax, ~90 warp instructions.
-//   q.K^T : A = q (row 0: bf16 high part, row 8: low part -> fp32-accurate q for free, M = 16 is otherwise wasted),
-//           B = K.  The dot product does not care in which order head dims meet the MMA's k index, and the softmax does
-//           not care which position sits in which column, so both are permuted to make each lane's fragment one
-//           contiguous 16-byte load: lane (g, tig) reads dims [8 tig, 8 tig + 8) and [32 + 8 tig, ...) of position
-//           4 (g / 2) + (g % 2) (+ 2 for the second n-tile of the block).
-//   P.V   : the score fragment of lanes 0..3 IS the A fragment of P for positions 4 tig .. 4 tig + 3 (again high part in
-//           row 0, low part in row 8), B = V: lane (g, tig) reads dims [8 g, 8 g + 8) of those four positions and
-//           interleaves position pairs with PRMT; n-tile e holds dims { 8 n + e }.
-// Blocks that lie entirely in the cache ([0, bpos), one page each) are software-pipelined two blocks ahead in
-// registers; the block(s) holding this step's own rows go through a generic per-position fetch.
 __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-  return r;
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -493,201 +473,14 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, u
   hi = *reinterpret_cast<const uint32_t*>(&hv);
   lo = pack_bf16x2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
 }
-
-__global__ void __launch_bounds__(128, 3)
-dec_self_attention_mma_kernel(const int* __restrict__ row_seq, const int* __restrict__ row_pos, const int* __restrict__ row_bpos,
-                              const int* __restrict__ row_page, const float* __restrict__ qkv, bf16* __restrict__ pool,
-                              long long page_stride, int n_ctx, int n_blocks, int n_units, const int* __restrict__ page_table,
-                              const int* __restrict__ seq_first, const unsigned char* __restrict__ anc, int layer, int d,
-                              int n_rows, int n_head, bf16* __restrict__ out, unsigned long long* trace_buf) {
-  static_assert(kPageTokens == 16, "one MMA k-step of P.V = one page");
-  __shared__ int s_pt[4][kMaxBeam * kMaxBlocks];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * 4 + warp;
-  unsigned long long* const trace = (unit == 0 && lane == 0) ? trace_buf : nullptr;
-  trace_mark(trace, (3u << 24) | 1);
-  pdl_trigger();
-  if (unit >= n_rows * n_head) return;  // warps are independent: no block-wide barrier below
-  const int r = unit / n_head, h = unit - r * n_head;
-  const int g = lane >> 2, tig = lane & 3;
-  // Read before the dependency wait: only what earlier STEPS wrote (see the staged kernel above).
-  const int s = row_seq[r], pos = row_pos[r], bpos = row_bpos[r];
-  const int sf = seq_first[s];
-  const bool single = (sf & kSingleBeamFlag) != 0;
-  const int first = sf & ~kSingleBeamFlag;
-  const unsigned char* my_anc = anc + (long long)s * n_ctx;
-  int* pt = s_pt[warp];
-  if (bpos > 0) {
-    const int nu = single ? 1 : min(kMaxBeam, n_units - first);
-    for (int i = lane; i < nu * n_blocks; i += 32) pt[i] = page_table[(long long)first * n_blocks + i];
-    __syncwarp();
-  }
-  const long long plane = (long long)kPageTokens * d;  // k plane -> v plane of a page's layer
-  const bf16* const lbase = pool + (long long)layer * 2 * plane + h * 64;
-  const int pk = 4 * (g >> 1) + (g & 1);               // this lane's K position inside a block (second n-tile: + 2)
-  auto page_of = [&](int t) { return pt[(single ? 0 : (int)my_anc[t]) * n_blocks + (t >> 4)]; };
-  // cached block b (all 16 positions < bpos)
-  auto load_k = [&](int b, uint4* k) {
-    const int t0 = b * 16 + pk;
-    const bf16* p0 = lbase + (long long)page_of(t0) * page_stride + (long long)pk * d + tig * 8;
-    const bf16* p1 = lbase + (long long)page_of(t0 + 2) * page_stride + (long long)(pk + 2) * d + tig * 8;
-    k[0] = ld_raw16<bf16>(p0); k[1] = ld_raw16<bf16>(p0 + 32);
-    k[2] = ld_raw16<bf16>(p1); k[3] = ld_raw16<bf16>(p1 + 32);
-  };
-  auto load_v = [&](int b, uint4* v) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int tl = 4 * tig + i;
-      v[i] = ld_raw16<bf16>(lbase + (long long)page_of(b * 16 + tl) * page_stride + plane + (long long)tl * d + g * 8);
-    }
-  };
-  const int n_full = bpos >> 4;
-  uint4 ka[4], va[4], kb[4], vb[4];
-  if (n_full > 0) { load_k(0, ka); load_v(0, va); }
-  if (n_full > 1) { load_k(1, kb); load_v(1, vb); }
-  pdl_wait();
-  trace_mark(trace, (3u << 24) | 2);
-  const float* qrow = qkv + (long long)r * 3 * d + h * 64;
-  // fused append: k / v of this row -> its page [layer][k | v][pos % 16]; 2 dims of each per lane
-  {
-    bf16* dst = pool + (long long)row_page[r] * page_stride + (long long)layer * 2 * plane + (long long)(pos % kPageTokens) * d + h * 64 + lane * 2;
-    const float2 kx = *reinterpret_cast<const float2*>(qrow + d + lane * 2), vx = *reinterpret_cast<const float2*>(qrow + 2 * d + lane * 2);
-    *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(kx.x, kx.y);
-    *reinterpret_cast<uint32_t*>(dst + plane) = pack_bf16x2(vx.x, vx.y);
-  }
-  // q fragments (log2 domain: one EX2 per exponential); only matrix rows 0 (high) and 8 (low) are non-zero
-  uint32_t qa[4][4];
-  {
-    const float qscale = 0.125f * 1.4426950408889634f;
-    const float4 x0 = *reinterpret_cast<const float4*>(qrow + tig * 8), x1 = *reinterpret_cast<const float4*>(qrow + tig * 8 + 4);
-    const float4 y0 = *reinterpret_cast<const float4*>(qrow + 32 + tig * 8), y1 = *reinterpret_cast<const float4*>(qrow + 32 + tig * 8 + 4);
-    const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-    const float ys[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t h0, l0, h1, l1;
-      split_bf16x2(xs[2 * j] * qscale, xs[2 * j + 1] * qscale, h0, l0);
-      split_bf16x2(ys[2 * j] * qscale, ys[2 * j + 1] * qscale, h1, l1);
-      qa[j][0] = g == 0 ? h0 : 0u; qa[j][1] = g == 0 ? l0 : 0u; qa[j][2] = g == 0 ? h1 : 0u; qa[j][3] = g == 0 ? l1 : 0u;
-    }
-  }
-  float m = -INFINITY, l = 0.f, o[8][4];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) { o[e][0] = o[e][1] = o[e][2] = o[e][3] = 0.f; }
-
-  // scores of the block's 16 positions: lanes 0..3 get positions 4 tig .. 4 tig + 3 in sc[0..3]
-  auto scores = [&](const uint4* k, float* sc) {
-    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-    const uint32_t* k0a = reinterpret_cast<const uint32_t*>(&k[0]);
-    const uint32_t* k0b = reinterpret_cast<const uint32_t*>(&k[1]);
-    const uint32_t* k1a = reinterpret_cast<const uint32_t*>(&k[2]);
-    const uint32_t* k1b = reinterpret_cast<const uint32_t*>(&k[3]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      mma16816(c0, qa[j][0], qa[j][1], qa[j][2], qa[j][3], k0a[j], k0b[j]);
-      mma16816(c1, qa[j][0], qa[j][1], qa[j][2], qa[j][3], k1a[j], k1b[j]);
-    }
-    sc[0] = c0[0] + c0[2]; sc[1] = c0[1] + c0[3]; sc[2] = c1[0] + c1[2]; sc[3] = c1[1] + c1[3];
-  };
-  // online softmax over the 4-lane group + P.V
-  auto fold = [&](const float* sc, const uint4* v) {
-    float bm = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
-    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
-    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
-    if (bm > m) {  // the running maximum moves (rare after the first blocks): rescale
-      const float a = fast_exp2(m - bm);
-      l *= a;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { o[e][0] *= a; o[e][1] *= a; o[e][2] *= a; o[e][3] *= a; }
-      m = bm;
-    }
-    const float p0 = fast_exp2(sc[0] - m), p1 = fast_exp2(sc[1] - m), p2 = fast_exp2(sc[2] - m), p3 = fast_exp2(sc[3] - m);
-    l += (p0 + p1) + (p2 + p3);
-    uint32_t a0, a1, a2, a3;
-    split_bf16x2(p0, p1, a0, a1);
-    split_bf16x2(p2, p3, a2, a3);
-    if (g != 0) { a0 = a1 = a2 = a3 = 0u; }
-    const uint32_t* v0 = reinterpret_cast<const uint32_t*>(&v[0]);
-    const uint32_t* v1 = reinterpret_cast<const uint32_t*>(&v[1]);
-    const uint32_t* v2 = reinterpret_cast<const uint32_t*>(&v[2]);
-    const uint32_t* v3 = reinterpret_cast<const uint32_t*>(&v[3]);
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      mma16816(o[2 * w], a0, a1, a2, a3, prmt(v0[w], v1[w], 0x5410u), prmt(v2[w], v3[w], 0x5410u));
-      mma16816(o[2 * w + 1], a0, a1, a2, a3, prmt(v0[w], v1[w], 0x7632u), prmt(v2[w], v3[w], 0x7632u));
-    }
-  };
-  // cached blocks, two blocks ahead: K of block b + 2 is requested as soon as the scores of block b are issued,
-  // V of block b + 2 after its P.V
-  for (int b = 0; b < n_full; b += 2) {
-    float sc[4];
-    scores(ka, sc);
-    if (b + 2 < n_full) load_k(b + 2, ka);
-    fold(sc, va);
-    if (b + 2 < n_full) load_v(b + 2, va);
-    if (b + 1 < n_full) {
-      scores(kb, sc);
-      if (b + 3 < n_full) load_k(b + 3, kb);
-      fold(sc, vb);
-      if (b + 3 < n_full) load_v(b + 3, vb);
-    }
-  }
-  // blocks that hold positions fed in THIS step [bpos, pos] (fp32 rows of the qkv buffer, rounded like the pool copy)
-  auto fetch = [&](int t, int kv, int dim0) -> uint4 {
-    uint4 u = make_uint4(0u, 0u, 0u, 0u);
-    if (t < bpos) {
-      u = ld_raw16<bf16>(lbase + (long long)page_of(t) * page_stride + kv * plane + (long long)(t & 15) * d + dim0);
-    } else if (t <= pos) {
-      const float* src = qkv + (long long)(r - (pos - t)) * 3 * d + (1 + kv) * d + h * 64 + dim0;
-      const float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
-      u.x = pack_bf16x2(x0.x, x0.y); u.y = pack_bf16x2(x0.z, x0.w); u.z = pack_bf16x2(x1.x, x1.y); u.w = pack_bf16x2(x1.z, x1.w);
-    }
-    return u;
-  };
-  for (int b = n_full; b * 16 <= pos; ++b) {
-    uint4 k[4], v[4];
-    const int t0 = b * 16 + pk;
-    k[0] = fetch(t0, 0, tig * 8); k[1] = fetch(t0, 0, 32 + tig * 8);
-    k[2] = fetch(t0 + 2, 0, tig * 8); k[3] = fetch(t0 + 2, 0, 32 + tig * 8);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = fetch(b * 16 + 4 * tig + i, 1, g * 8);
-    float sc[4];
-    scores(k, sc);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (b * 16 + 4 * tig + i > pos) sc[i] = -INFINITY;
-    fold(sc, v);
-  }
-  l += __shfl_xor_sync(0xffffffffu, l, 1);
-  l += __shfl_xor_sync(0xffffffffu, l, 2);
-  if (g == 0) {  // lane tig holds dims [16 tig, 16 tig + 16): n-tile e, columns 2 tig and 2 tig + 1
-    const float inv = 1.f / l;
-    uint4 w0, w1;
-    w0.x = pack_bf16x2((o[0][0] + o[0][2]) * inv, (o[1][0] + o[1][2]) * inv);
-    w0.y = pack_bf16x2((o[2][0] + o[2][2]) * inv, (o[3][0] + o[3][2]) * inv);
-    w0.z = pack_bf16x2((o[4][0] + o[4][2]) * inv, (o[5][0] + o[5][2]) * inv);
-    w0.w = pack_bf16x2((o[6][0] + o[6][2]) * inv, (o[7][0] + o[7][2]) * inv);
-    w1.x = pack_bf16x2((o[0][1] + o[0][3]) * inv, (o[1][1] + o[1][3]) * inv);
-    w1.y = pack_bf16x2((o[2][1] + o[2][3]) * inv, (o[3][1] + o[3][3]) * inv);
-    w1.z = pack_bf16x2((o[4][1] + o[4][3]) * inv, (o[5][1] + o[5][3]) * inv);
-    w1.w = pack_bf16x2((o[6][1] + o[6][3]) * inv, (o[7][1] + o[7][3]) * inv);
-    bf16* dst = out + (long long)r * d + h * 64 + tig * 16;
-    *reinterpret_cast<uint4*>(dst) = w0;
-    *reinterpret_cast<uint4*>(dst + 8) = w1;
-  }
-  trace_mark(trace, (3u << 24) | 8);
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
-
-// ------------------------------------------------------------------------------------------------
-// v4 (bf16 product mode): PERSISTENT CTAs over a cp.async ring.  The kernels above give every (row, head) unit its own
-// CTA / warp, so each unit pays its own latency chain (control block -> page table -> ancestry -> K/V) and the step
-// pays it once per WAVE of units: 2560 units at 6 resident CTAs per SM are 2.9 waves of ~6 us for 65 MB of K/V that HBM
-// delivers in 9 us (tools/trace_step.py; the mma kernel with 5x fewer instructions was no faster: the bound is latency,
-// not issue).  Here a CTA walks units c, c + G, c + 2G, ... and the K/V of the NEXT units are already in flight while
-// one is being folded: work item = 64 cached positions of one unit (K and V head slices, 16 KB), kRingStages items
-// deep, fed in consumption order across unit boundaries.  The per-position page comes from `pospage` (one load instead
-// of the three-level chain), built once per step by dec_self_pospage_kernel.
-constexpr int kRingPos = 64, kRingStages = 4, kRingUnits = 32;
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // pospage[r][t] = pool page that holds position t of row r's hypothesis, t < bpos (later positions are fed in this step).
 // Deliberately WITHOUT an early launch_dependents: the self-attention of layer 0 reads the table before its own
@@ -709,387 +502,227 @@ dec_self_pospage_kernel(const int* __restrict__ row_seq, const int* __restrict__
   }
 }
 
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// ------------------------------------------------------------------------------------------------
+// v3 (bf16 product mode, the default): PERSISTENT WARPS on mma.sync.  A CTA is one warp; it owns units w, w + G, ... and
+// a ring of kPwNB buffers of kPwCB positions (K and V head slices, 16-byte chunks XOR-swizzled by the row) that is fed with
+// cp.async in consumption order ACROSS unit boundaries: while one item is folded the next is in flight, and the next unit's
+// q / k / v rows and the next item's page lookups are already in registers.  Nothing in the loop is a block-wide barrier.
+//   q.K^T : A = q (matrix row 0: bf16 high part, row 8: low part -> fp32-accurate q for free, M = 16 is otherwise wasted),
+//           B = K via ldmatrix;  P.V : the score fragment of lanes 0..3 IS the A fragment of P (high / low parts again),
+//           B = V via ldmatrix.trans.  ~65 warp instructions per 16 positions instead of ~600 in the SIMT kernels.
+// How it got here (profiles/r2_notes.md, code of the discarded variants in commit e4f8ffe): v1 and v2 run in lockstep WAVES --
+// every resident unit walks "control words -> page table -> K/V burst -> q -> fold" at the same time, so HBM idles while the
+// SMs fold and the SMs idle while HBM streams (ncu: 2.9 waves of ~8 us for 65 MB that HBM delivers in 9 us), and their fp32
+// FMAs on unpacked bf16 make the fold itself issue-bound (7000 warp instructions per unit).  A register-fed mma kernel,
+// a CTA-wide persistent ring and a staged mma kernel each fixed one of the two and were no faster; this one fixes both.
+// positions per ring buffer, buffers, resident warps per SM asked of the compiler (165 registers), most units per warp, and the
+// unit count from which the kernel is taken.  A-B of the ring geometry: profiles/r2_selfattn_pw_configs.txt
+constexpr int kPwCfgCB = 32, kPwCfgNB = 2, kPwCfgWarps = 12, kPwUnits = 32, kPwMinUnits = 1000;  // A-B of 9 configurations: profiles/r2_selfattn_pw_configs.txt
 
-__global__ void __launch_bounds__(128)
-dec_self_attention_ring_kernel(const int* __restrict__ row_pos, const int* __restrict__ row_bpos, const int* __restrict__ row_page,
-                               const float* __restrict__ qkv, bf16* __restrict__ pool, long long page_stride, int n_ctx,
-                               const int* __restrict__ pospage, int layer, int d, int n_rows, int n_head, bf16* __restrict__ out,
-                               unsigned long long* trace_buf) {
-  extern __shared__ __align__(16) unsigned char ring_smem[];  // kRingStages x { K [64][64], V [64][64] } bf16
-  bf16* const ring = reinterpret_cast<bf16*>(ring_smem);
-  __shared__ int s_pos[kRingUnits], s_bpos[kRingUnits];
-  __shared__ float part[4][66];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int sub = lane & 7, rg = lane >> 3;  // 8 lanes share one position (8 dims each), 4 positions per warp pass
-  const int n_units = n_rows * n_head, G = gridDim.x;
-  const int K = (n_units - (int)blockIdx.x + G - 1) / G;  // units of this CTA: blockIdx.x + k G
-  unsigned long long* const trace = (blockIdx.x == 0 && tid == 0) ? trace_buf : nullptr;
+template <int kPwCB, int kPwNB, int kPwMinWarps>
+__global__ void __launch_bounds__(32, kPwMinWarps)
+dec_self_attention_pw_kernel(const int* __restrict__ row_pos, const int* __restrict__ row_bpos, const int* __restrict__ row_page,
+                             const float* __restrict__ qkv, bf16* __restrict__ pool, long long page_stride, int n_ctx,
+                             const int* __restrict__ pospage, int layer, int d, int n_rows, int n_head, bf16* __restrict__ out,
+                             unsigned long long* trace_buf) {
+  extern __shared__ __align__(128) unsigned char smp[];  // kPwNB x { K [32][128 B], V [32][128 B] }
+  constexpr uint32_t kBuf = kPwCB * 256u, kVOff = kPwCB * 128u;
+  const int lane = threadIdx.x;
+  const int G = gridDim.x, n_units = n_rows * n_head;
+  const int K = (n_units - (int)blockIdx.x + G - 1) / G;  // units of this warp: blockIdx.x + k G
+  unsigned long long* const trace = (blockIdx.x == 0 && lane == 0) ? trace_buf : nullptr;
   trace_mark(trace, (3u << 24) | 1);
   pdl_trigger();
-  // Read before the dependency wait: the control block, pospage (see above) and cached K/V of earlier steps.
-  for (int k = tid; k < K; k += 128) {
-    const int r = ((int)blockIdx.x + k * G) / n_head;
-    s_pos[k] = row_pos[r]; s_bpos[k] = row_bpos[r];
+  // Read before the dependency wait: the control block, pospage (dec_self_pospage_kernel) and cached K/V of earlier steps.
+  int my_pos = 0, my_bpos = 0, my_page = 0;  // lane k: control words of unit k
+  if (lane < K) {
+    const int r = ((int)blockIdx.x + lane * G) / n_head;
+    my_pos = row_pos[r]; my_bpos = row_bpos[r]; my_page = row_page[r];
   }
-  __syncthreads();
+  const int grp = lane >> 3, ch8 = lane & 7;
+  const int g = lane >> 2, tig = lane & 3;
   const long long plane = (long long)kPageTokens * d;
-  // ---- producer: items in consumption order ----
-  int pk = 0, pc = 0, issued = 0;
-  const int ch = tid & 7, kvsel = (tid >> 3) & 1, tl0 = tid >> 4;
-  auto issue = [&]() {
-    while (pk < K && pc * kRingPos >= s_bpos[pk]) { ++pk; pc = 0; }
-    if (pk < K) {
-      const int u = (int)blockIdx.x + pk * G;
-      const int r = u / n_head, h = u - r * n_head;
-      const int c0 = pc * kRingPos, cn = min(kRingPos, s_bpos[pk] - c0);
-      bf16* dst = ring + (size_t)(issued % kRingStages) * (2 * kRingPos * 64) + kvsel * (kRingPos * 64) + ch * 8;
-      const bf16* src = pool + ((long long)layer * 2 + kvsel) * plane + h * 64 + ch * 8;
-      const int* pp = pospage + (long long)r * n_ctx + c0;
+  const uint32_t sbase = smem_u32(smp);
+  // ---- producer side: items (unit, chunk of kPwCB positions) in consumption order ----
+  int pu = 0, pc = 0, p_r = (int)blockIdx.x / n_head, p_h = (int)blockIdx.x - p_r * n_head, p_bpos = 0, p_n = 1;
+  int pg[kPwCB / 4];
+  auto p_lookup = [&]() {  // pages of item (pu, pc); speculative (no dependence on the control words)
+    const int* pp = pospage + (long long)p_r * n_ctx + pc * kPwCB;
 #pragma unroll
-      for (int j = 0; j < kRingPos / 8; ++j) {
-        const int tl = tl0 + 8 * j;
-        if (tl < cn) cp_async_16(dst + tl * 64, src + (long long)pp[tl] * page_stride + (long long)((c0 + tl) & (kPageTokens - 1)) * d);
-      }
-      ++pc;
-    }
-    cp_async_commit();  // an empty group when nothing is left: the wait below counts groups
-    ++issued;
+    for (int i = 0; i < kPwCB / 4; ++i) pg[i] = (pc * kPwCB + grp + 4 * i < n_ctx) ? __ldg(pp + grp + 4 * i) : 0;
   };
-#pragma unroll 1
-  for (int i = 0; i < kRingStages - 1; ++i) issue();
+  p_lookup();
+  p_bpos = __shfl_sync(0xffffffffu, my_bpos, 0);
+  p_n = __shfl_sync(0xffffffffu, my_pos, 0) + 1;
+  auto p_request = [&](int slot) {  // item (pu, pc) -> buffer `slot`; then move on and look the next item's pages up
+    if (pu < K) {
+      const bf16* src0 = pool + (long long)layer * 2 * plane + p_h * 64 + ch8 * 8;
+      const uint32_t dst0 = sbase + (uint32_t)slot * kBuf;
+#pragma unroll
+      for (int i = 0; i < kPwCB / 4; ++i) {
+        const int tl = grp + 4 * i, t = pc * kPwCB + tl;
+        if (t < p_bpos) {
+          const bf16* src = src0 + (long long)pg[i] * page_stride + (long long)(t & (kPageTokens - 1)) * d;
+          const uint32_t dst = dst0 + (uint32_t)tl * 128u + (uint32_t)((ch8 ^ (tl & 7)) << 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + kVOff), "l"(src + plane) : "memory");
+        }
+      }
+      if (++pc * kPwCB >= p_n) {
+        pc = 0;
+        if (++pu < K) {
+          const int u = (int)blockIdx.x + pu * G;
+          p_r = u / n_head; p_h = u - p_r * n_head;
+          p_bpos = __shfl_sync(0xffffffffu, my_bpos, pu);
+          p_n = __shfl_sync(0xffffffffu, my_pos, pu) + 1;
+        }
+      }
+      if (pu < K) p_lookup();
+    }
+    cp_async_commit();  // an empty group when nothing is left: the consumer's wait counts groups
+  };
+#pragma unroll
+  for (int i = 0; i < kPwNB - 1; ++i) p_request(i);  // the ring runs kPwNB - 1 items ahead of the fold
   pdl_wait();
   trace_mark(trace, (3u << 24) | 2);
-  const float qscale = 0.125f * 1.4426950408889634f;  // log2 domain
-  int consumed = 0;
-  float qn[8];
-  {
-    const int u = (int)blockIdx.x;
+  // ---- consumer side ----
+  float2 qx[4], qy[4], kx, vx;  // raw q (lanes 0..3 only) and this row's k / v (2 dims per lane) of the NEXT unit to start
+  auto q_prefetch = [&](int k) {
+    const int u = (int)blockIdx.x + k * G;
     const int r = u / n_head, h = u - r * n_head;
-    const float* qrow = qkv + (long long)r * 3 * d + h * 64 + sub * 8;
-    const float4 a = *reinterpret_cast<const float4*>(qrow), b = *reinterpret_cast<const float4*>(qrow + 4);
-    qn[0] = a.x; qn[1] = a.y; qn[2] = a.z; qn[3] = a.w; qn[4] = b.x; qn[5] = b.y; qn[6] = b.z; qn[7] = b.w;
-  }
+    const float* qrow = qkv + (long long)r * 3 * d + h * 64;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      qx[j] = make_float2(0.f, 0.f); qy[j] = make_float2(0.f, 0.f);
+      if (g == 0) { qx[j] = *reinterpret_cast<const float2*>(qrow + 16 * j + 2 * tig); qy[j] = *reinterpret_cast<const float2*>(qrow + 16 * j + 8 + 2 * tig); }
+    }
+    kx = *reinterpret_cast<const float2*>(qrow + d + lane * 2);
+    vx = *reinterpret_cast<const float2*>(qrow + 2 * d + lane * 2);
+  };
+  q_prefetch(0);
+  const int k_row = lane & 7, k_chunk = lane >> 3;
+  const int v_row = (lane & 7) + ((lane >> 3) & 1) * 8, v_chunk = lane >> 4;
+  int it = 0;
 #pragma unroll 1
   for (int k = 0; k < K; ++k) {
     const int u = (int)blockIdx.x + k * G;
     const int r = u / n_head, h = u - r * n_head;
-    const int pos = s_pos[k], bpos = s_bpos[k];
-    const float* qrow = qkv + (long long)r * 3 * d + h * 64;
+    const int pos = __shfl_sync(0xffffffffu, my_pos, k), bpos = __shfl_sync(0xffffffffu, my_bpos, k);
+    const int page = __shfl_sync(0xffffffffu, my_page, k);
+    const int n = pos + 1;
+    // q fragments in the log2 domain; matrix row 0 = bf16 high part, row 8 = low part, other rows zero
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float qscale = 0.125f * 1.4426950408889634f;
+      split_bf16x2(qx[j].x * qscale, qx[j].y * qscale, qa[j][0], qa[j][1]);
+      split_bf16x2(qy[j].x * qscale, qy[j].y * qscale, qa[j][2], qa[j][3]);
+    }
+    const uint32_t own_k = pack_bf16x2(kx.x, kx.y), own_v = pack_bf16x2(vx.x, vx.y);
     {  // fused append: k / v of this row -> its page [layer][k | v][pos % 16]
-      const int c = tid & 63, sel = tid >> 6;
-      pool[(long long)row_page[r] * page_stride + ((long long)layer * 2 + sel) * plane + (long long)(pos & (kPageTokens - 1)) * d + h * 64 + c] =
-          __float2bfloat16_rn(qrow[(1 + sel) * d + c]);
+      bf16* dst = pool + (long long)page * page_stride + (long long)layer * 2 * plane + (long long)(pos & (kPageTokens - 1)) * d + h * 64 + lane * 2;
+      *reinterpret_cast<uint32_t*>(dst) = own_k;
+      *reinterpret_cast<uint32_t*>(dst + plane) = own_v;
     }
-    float qf[8];
+    if (k + 1 < K) q_prefetch(k + 1);  // in flight while this unit is folded
+    float m = -INFINITY, l = 0.f, o[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) qf[i] = qn[i] * qscale;
-    if (k + 1 < K) {  // q of the next unit: in flight while this one is folded
-      const int u2 = u + G;
-      const int r2 = u2 / n_head, h2 = u2 - r2 * n_head;
-      const float* q2 = qkv + (long long)r2 * 3 * d + h2 * 64 + sub * 8;
-      const float4 a = *reinterpret_cast<const float4*>(q2), b = *reinterpret_cast<const float4*>(q2 + 4);
-      qn[0] = a.x; qn[1] = a.y; qn[2] = a.z; qn[3] = a.w; qn[4] = b.x; qn[5] = b.y; qn[6] = b.z; qn[7] = b.w;
-    }
-    float m = -INFINITY, l = 0.f, acc[8];
+    for (int e = 0; e < 8; ++e) { o[e][0] = o[e][1] = o[e][2] = o[e][3] = 0.f; }
+    const int n_items = (n + kPwCB - 1) / kPwCB;
+#pragma unroll 1
+    for (int c = 0; c < n_items; ++c, ++it) {
+      const int c0 = c * kPwCB;
+      const uint32_t kb = sbase + (uint32_t)(it % kPwNB) * kBuf, vb = kb + kVOff;
+      const int cn = min(kPwCB, n - c0);  // positions of this item, cached or fed in this step
+      if (c0 + cn > bpos) {
+        // positions fed in THIS step [bpos, pos] and zero rows behind the last position (P = 0 there, but 0 x garbage
+        // must not become NaN)
+        const int t_hi = (cn + 15) & ~15;
+        if (bpos == pos) {  // decode row: its own k / v are already in registers
+          const int tl = pos - c0;
+          const uint32_t a = (uint32_t)tl * 128u + (uint32_t)(((lane >> 2) ^ (tl & 7)) << 4) + (uint32_t)(lane & 3) * 4u;
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(kb + a), "r"(own_k) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(vb + a), "r"(own_v) : "memory");
+          for (int z = cn; z < t_hi; ++z) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(kb + (uint32_t)z * 128u + (uint32_t)lane * 4u), "r"(0u) : "memory");
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(vb + (uint32_t)z * 128u + (uint32_t)lane * 4u), "r"(0u) : "memory");
+          }
+        } else {  // prefill rows: fp32 rows of the qkv buffer, rounded like the pool copy
+          const int t_lo = max(bpos, c0) - c0;
+          for (int idx = t_lo * 16 + lane; idx < t_hi * 16; idx += 32) {
+            const int tl = idx >> 4, cc = idx & 15, sel = cc >> 3, ch = cc & 7;
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            if (tl < cn) {
+              const float* src = qkv + (long long)(r - (pos - (c0 + tl))) * 3 * d + (1 + sel) * d + h * 64 + ch * 8;
+              const float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
+              w.x = pack_bf16x2(x0.x, x0.y); w.y = pack_bf16x2(x0.z, x0.w); w.z = pack_bf16x2(x1.x, x1.y); w.w = pack_bf16x2(x1.z, x1.w);
+            }
+            const uint32_t dst = (sel ? vb : kb) + (uint32_t)tl * 128u + (uint32_t)((ch ^ (tl & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+          }
+        }
+      }
+      cp_async_wait_group<kPwNB - 2>();  // item `it` has landed (groups are committed in item order, kPwNB - 1 ahead)
+      __syncwarp();                      // ... and the buffer refilled next (item it - 1's) is no longer being read
+      p_request((it + kPwNB - 1) % kPwNB);
+      for (int b0 = 0; b0 < cn; b0 += 16) {
+        float c0f[4] = {0.f, 0.f, 0.f, 0.f}, c1f[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    auto fold = [&](const float* kf, const float* vf, bool valid) {
-      float sc = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sc = fmaf(qf[i], kf[i], sc);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-      if (valid) {
-        if (sc > m) {  // the running maximum moves (rare after the first positions): rescale
-          const float a = fast_exp2(m - sc);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r0, r1, r2, r3;
+          const int row0 = b0 + k_row, row1 = row0 + 8;
+          ldsm_x4(kb + (uint32_t)row0 * 128u + (uint32_t)(((k_chunk + 4 * half) ^ (row0 & 7)) << 4), r0, r1, r2, r3);
+          mma16816(c0f, qa[2 * half][0], qa[2 * half][1], qa[2 * half][2], qa[2 * half][3], r0, r1);
+          mma16816(c0f, qa[2 * half + 1][0], qa[2 * half + 1][1], qa[2 * half + 1][2], qa[2 * half + 1][3], r2, r3);
+          ldsm_x4(kb + (uint32_t)row1 * 128u + (uint32_t)(((k_chunk + 4 * half) ^ (row1 & 7)) << 4), r0, r1, r2, r3);
+          mma16816(c1f, qa[2 * half][0], qa[2 * half][1], qa[2 * half][2], qa[2 * half][3], r0, r1);
+          mma16816(c1f, qa[2 * half + 1][0], qa[2 * half + 1][1], qa[2 * half + 1][2], qa[2 * half + 1][3], r2, r3);
+        }
+        float sc[4] = {c0f[0] + c0f[2], c0f[1] + c0f[3], c1f[0] + c1f[2], c1f[1] + c1f[3]};
+        if (b0 + 16 > cn) {
+          const int t = b0 + 2 * tig;
+          if (t >= cn) sc[0] = -INFINITY;
+          if (t + 1 >= cn) sc[1] = -INFINITY;
+          if (t + 8 >= cn) sc[2] = -INFINITY;
+          if (t + 9 >= cn) sc[3] = -INFINITY;
+        }
+        float bm = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+        if (bm > m) {
+          const float a = fast_exp2(m - bm);
           l *= a;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] *= a;
-          m = sc;
+          for (int e = 0; e < 8; ++e) { o[e][0] *= a; o[e][1] *= a; o[e][2] *= a; o[e][3] *= a; }
+          m = bm;
         }
-        const float pr = fast_exp2(sc - m);
-        l += pr;
+        const float p0 = fast_exp2(sc[0] - m), p1 = fast_exp2(sc[1] - m), p2 = fast_exp2(sc[2] - m), p3 = fast_exp2(sc[3] - m);
+        l += (p0 + p1) + (p2 + p3);
+        uint32_t a0, a1, a2, a3;
+        split_bf16x2(p0, p1, a0, a1);
+        split_bf16x2(p2, p3, a2, a3);
+        if (g != 0) { a0 = a1 = a2 = a3 = 0u; }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, vf[i], acc[i]);
-      }
-    };
-    const int n_chunks = (bpos + kRingPos - 1) / kRingPos;
-#pragma unroll 1
-    for (int c = 0; c < n_chunks; ++c) {
-      cp_async_wait_group<kRingStages - 2>();  // this thread's copies of item `consumed` have landed ...
-      __syncthreads();                         // ... everybody's have, and the stage refilled next is no longer being read
-      issue();
-      const bf16* Ks = ring + (size_t)(consumed % kRingStages) * (2 * kRingPos * 64);
-      const bf16* Vs = Ks + kRingPos * 64;
-      const int cn = min(kRingPos, bpos - c * kRingPos);
-#pragma unroll 2
-      for (int tg = warp * 4; tg < cn; tg += 16) {
-        const int tl = tg + rg;
-        const bool valid = tl < cn;
-        float kf[8], vf[8];
-        if (valid) {
-          load_smem_vec<bf16>(Ks + tl * 64 + sub * 8, kf);
-          load_smem_vec<bf16>(Vs + tl * 64 + sub * 8, vf);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
+        for (int e2 = 0; e2 < 4; ++e2) {
+          uint32_t r0, r1, r2, r3;
+          const int row = b0 + v_row;
+          ldsm_x4_t(vb + (uint32_t)row * 128u + (uint32_t)(((2 * e2 + v_chunk) ^ (row & 7)) << 4), r0, r1, r2, r3);
+          mma16816(o[2 * e2], a0, a1, a2, a3, r0, r1);
+          mma16816(o[2 * e2 + 1], a0, a1, a2, a3, r2, r3);
         }
-        fold(kf, vf, valid);
-      }
-      ++consumed;
-    }
-    // positions fed in THIS step [bpos, pos]: fp32 rows of the qkv buffer, rounded like the pool copy
-    for (int t0 = bpos + warp * 4; t0 <= pos; t0 += 16) {
-      const int t = t0 + rg;
-      const bool valid = t <= pos;
-      float kf[8], vf[8];
-      if (valid) {
-        const float* src = qkv + (long long)(r - (pos - t)) * 3 * d + d + h * 64 + sub * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { kf[i] = to_f(__float2bfloat16_rn(src[i])); vf[i] = to_f(__float2bfloat16_rn(src[d + i])); }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
-      }
-      fold(kf, vf, valid);
-    }
-    // merge the 4 position groups of the warp, then the 4 warps
-#pragma unroll
-    for (int o = 8; o < 32; o <<= 1) {
-      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
-      const float M = fmaxf(m, m2);
-      const float e1 = (m == -INFINITY) ? 0.f : fast_exp2(m - M), e2 = (m2 == -INFINITY) ? 0.f : fast_exp2(m2 - M);
-      l = l * e1 + l2 * e2;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float a2 = __shfl_xor_sync(0xffffffffu, acc[i], o);
-        acc[i] = acc[i] * e1 + a2 * e2;
-      }
-      m = M;
-    }
-    if (rg == 0) {
-      if (sub == 0) { part[warp][0] = m; part[warp][1] = l; }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) part[warp][2 + sub * 8 + i] = acc[i];
-    }
-    __syncthreads();
-    if (tid < 64) {
-      const float M = fmaxf(fmaxf(part[0][0], part[1][0]), fmaxf(part[2][0], part[3][0]));
-      float num = 0.f, den = 0.f;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const float e = (part[w][0] == -INFINITY) ? 0.f : fast_exp2(part[w][0] - M);
-        num = fmaf(e, part[w][2 + tid], num);
-        den = fmaf(e, part[w][1], den);
-      }
-      out[(long long)r * d + h * 64 + tid] = __float2bfloat16_rn(num / den);
-    }
-    __syncthreads();  // `part` is free again
-  }
-  cp_async_wait_group<0>();
-  trace_mark(trace, (3u << 24) | 8);
-}
-
-// ------------------------------------------------------------------------------------------------
-// v5 (bf16 product mode): ONE WARP per (row, head) unit, K / V staged with cp.async like the v1 kernel (everything the
-// unit needs is requested at once, before the dependency wait), folded with ldmatrix + mma.sync like v3.
-// Why: tools/trace_step.py shows a v1 CTA needing 6.5 us AFTER the dependency wait although its K / V have been sitting
-// in shared memory for microseconds -- 24 warps per SM with ~1000 instructions each are issue-bound (fp32 FMAs on
-// unpacked bf16, index arithmetic per 16-byte request); v3 cut the instructions 5x but walks the context two blocks at a
-// time (a round trip per pair of blocks); v4's persistent CTAs serialise issue / wait / fold behind block barriers.
-// Here a unit costs ~25 staging iterations (page lookup in `pospage`, K + V request) + ~65 instructions per 16 positions.
-//   smem per unit: 2 buffers x CB positions x (K 128 B + V 128 B), 16-byte chunks XOR-swizzled by the row;
-//   contexts beyond 2 CB positions are double-buffered.
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-
-__global__ void __launch_bounds__(32, 12)
-dec_self_attention_smma_kernel(const int* __restrict__ row_pos, const int* __restrict__ row_bpos, const int* __restrict__ row_page,
-                               const float* __restrict__ qkv, bf16* __restrict__ pool, long long page_stride, int n_ctx,
-                               const int* __restrict__ pospage, int layer, int d, int CB, bf16* __restrict__ out,
-                               unsigned long long* trace_buf) {
-  extern __shared__ __align__(128) unsigned char sm5[];  // 2 x { K [CB][128 B], V [CB][128 B] }
-  const int lane = threadIdx.x;
-  const int h = blockIdx.x, r = blockIdx.y;
-  unsigned long long* const trace = ((blockIdx.x | blockIdx.y) == 0 && lane == 0) ? trace_buf : nullptr;
-  trace_mark(trace, (3u << 24) | 1);
-  pdl_trigger();
-  // The unit's latency chain is what the step pays per wave of units, so it is kept at three round trips:
-  //   1. control block + page lookups of the first two chunks (speculative: they do not wait for bpos),
-  //   2. every cached K / V row of those chunks (cp.async),            -- 1 and 2 run before the dependency wait
-  //   3. q and this step's own k / v rows from the qkv buffer.
-  // Read before the wait: the control block, pospage (dec_self_pospage_kernel) and cached K/V of earlier steps.
-  const int* const pp = pospage + (long long)r * n_ctx;
-  const int grp = lane >> 3, ch8 = lane & 7;
-  int pg0[16], pg1[16];  // CB <= 64: at most 16 positions per 8-lane group and chunk
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int tl = grp + 4 * i;
-    pg0[i] = (tl < CB && tl < n_ctx) ? __ldg(pp + tl) : 0;
-    pg1[i] = (tl < CB && CB + tl < n_ctx) ? __ldg(pp + CB + tl) : 0;
-  }
-  const int pos = row_pos[r], bpos = row_bpos[r], my_page = row_page[r];
-  const int n = pos + 1;
-  const int g = lane >> 2, tig = lane & 3;
-  const long long plane = (long long)kPageTokens * d;
-  const uint32_t sbase = smem_u32(sm5);
-  const uint32_t buf_bytes = (uint32_t)CB * 256u, v_off = (uint32_t)CB * 128u;
-  const bf16* const src0 = pool + (long long)layer * 2 * plane + h * 64 + ch8 * 8;
-  // chunk k = positions [k CB, (k + 1) CB): its cached part (t < bpos) -> buffer k & 1; always commits one group
-  auto request = [&](int k, const int* pg) {
-    const int c0 = k * CB;
-    const uint32_t dst0 = sbase + (uint32_t)(k & 1) * buf_bytes;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int tl = grp + 4 * i, t = c0 + tl;
-      if (tl < CB && t < bpos) {
-        const bf16* src = src0 + (long long)pg[i] * page_stride + (long long)(t & (kPageTokens - 1)) * d;
-        const uint32_t dst = dst0 + (uint32_t)tl * 128u + (uint32_t)((ch8 ^ (tl & 7)) << 4);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + v_off), "l"(src + plane) : "memory");
       }
     }
-    cp_async_commit();
-  };
-  request(0, pg0);
-  request(1, pg1);
-  pdl_wait();
-  trace_mark(trace, (3u << 24) | 2);
-  const float* qrow = qkv + (long long)r * 3 * d + h * 64;
-  float2 qx[4], qy[4];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    if (g == 0) {  // lane tig: dims 8 e + 2 tig, + 1
+      const float inv = 1.f / l;
+      bf16* dst = out + (long long)r * d + h * 64 + 2 * tig;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    qx[j] = make_float2(0.f, 0.f); qy[j] = make_float2(0.f, 0.f);
-    if (g == 0) { qx[j] = *reinterpret_cast<const float2*>(qrow + 16 * j + 2 * tig); qy[j] = *reinterpret_cast<const float2*>(qrow + 16 * j + 8 + 2 * tig); }
-  }
-  const float2 kx = *reinterpret_cast<const float2*>(qrow + d + lane * 2), vx = *reinterpret_cast<const float2*>(qrow + 2 * d + lane * 2);
-  // positions fed in THIS step [bpos, pos] (fp32 rows of the qkv buffer, rounded like the pool copy) -> chunk k's buffer,
-  // and zero rows behind the last position (P = 0 there, but 0 x garbage must not become NaN)
-  auto fill_tail = [&](int k) {
-    const int c0 = k * CB;
-    const int cn = min(CB, n - c0);
-    if (cn <= 0) return;
-    const uint32_t kb = sbase + (uint32_t)(k & 1) * buf_bytes, vb = kb + v_off;
-    const int t_lo = max(bpos, c0) - c0, t_hi = (cn + 15) & ~15;
-    for (int idx = t_lo * 16 + lane; idx < t_hi * 16; idx += 32) {
-      const int tl = idx >> 4, c = idx & 15, sel = c >> 3, ch = c & 7;
-      uint4 u = make_uint4(0u, 0u, 0u, 0u);
-      if (tl < cn) {
-        const float* src = qkv + (long long)(r - (pos - (c0 + tl))) * 3 * d + (1 + sel) * d + h * 64 + ch * 8;
-        const float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
-        u.x = pack_bf16x2(x0.x, x0.y); u.y = pack_bf16x2(x0.z, x0.w); u.z = pack_bf16x2(x1.x, x1.y); u.w = pack_bf16x2(x1.z, x1.w);
-      }
-      const uint32_t dst = (sel ? vb : kb) + (uint32_t)tl * 128u + (uint32_t)((ch ^ (tl & 7)) << 4);
-      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
-    }
-  };
-  fill_tail(0);
-  fill_tail(1);
-  {  // fused append: k / v of this row -> its page [layer][k | v][pos % 16]; 2 dims of each per lane
-    bf16* dst = pool + (long long)my_page * page_stride + (long long)layer * 2 * plane + (long long)(pos & (kPageTokens - 1)) * d + h * 64 + lane * 2;
-    *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(kx.x, kx.y);
-    *reinterpret_cast<uint32_t*>(dst + plane) = pack_bf16x2(vx.x, vx.y);
-  }
-  // q fragments in the log2 domain; matrix row 0 = bf16 high part, row 8 = low part, other rows zero
-  uint32_t qa[4][4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float qscale = 0.125f * 1.4426950408889634f;
-    split_bf16x2(qx[j].x * qscale, qx[j].y * qscale, qa[j][0], qa[j][1]);
-    split_bf16x2(qy[j].x * qscale, qy[j].y * qscale, qa[j][2], qa[j][3]);
-  }
-  float m = -INFINITY, l = 0.f, o[8][4];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) { o[e][0] = o[e][1] = o[e][2] = o[e][3] = 0.f; }
-  // ldmatrix lane roles.  K (non-transposed): matrix i = 16-byte chunk i (+ 4) of 8 position rows; V (transposed):
-  // matrices (rows 0-7 | 8-15) x (chunk 2e | 2e + 1)
-  const int k_row = lane & 7, k_chunk = lane >> 3;
-  const int v_row = (lane & 7) + ((lane >> 3) & 1) * 8, v_chunk = lane >> 4;
-  const int n_chunks = (n + CB - 1) / CB;
-  for (int k = 0; k < n_chunks; ++k) {
-    const int c0 = k * CB;
-    const uint32_t kb = sbase + (uint32_t)(k & 1) * buf_bytes, vb = kb + v_off;
-    const int cn = min(CB, n - c0);  // positions of this chunk, cached or fed in this step
-    if (k >= 2) fill_tail(k);
-    cp_async_wait_group<1>();  // groups are committed in chunk order, two ahead
-    __syncwarp();
-    for (int b0 = 0; b0 < cn; b0 += 16) {
-      // scores of 16 positions: n-tile 0 = positions b0 .. b0 + 7, n-tile 1 = b0 + 8 .. b0 + 15
-      float c0f[4] = {0.f, 0.f, 0.f, 0.f}, c1f[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {  // head dims [32 half, 32 half + 32): k-steps 2 half, 2 half + 1
-        uint32_t r0, r1, r2, r3;
-        const int row0 = b0 + k_row, row1 = row0 + 8;
-        ldsm_x4(kb + (uint32_t)row0 * 128u + (uint32_t)(((k_chunk + 4 * half) ^ (row0 & 7)) << 4), r0, r1, r2, r3);
-        mma16816(c0f, qa[2 * half][0], qa[2 * half][1], qa[2 * half][2], qa[2 * half][3], r0, r1);
-        mma16816(c0f, qa[2 * half + 1][0], qa[2 * half + 1][1], qa[2 * half + 1][2], qa[2 * half + 1][3], r2, r3);
-        ldsm_x4(kb + (uint32_t)row1 * 128u + (uint32_t)(((k_chunk + 4 * half) ^ (row1 & 7)) << 4), r0, r1, r2, r3);
-        mma16816(c1f, qa[2 * half][0], qa[2 * half][1], qa[2 * half][2], qa[2 * half][3], r0, r1);
-        mma16816(c1f, qa[2 * half + 1][0], qa[2 * half + 1][1], qa[2 * half + 1][2], qa[2 * half + 1][3], r2, r3);
-      }
-      // lanes 0..3: positions b0 + 2 tig, + 1 (tile 0) and b0 + 8 + 2 tig, + 1 (tile 1)
-      float sc[4] = {c0f[0] + c0f[2], c0f[1] + c0f[3], c1f[0] + c1f[2], c1f[1] + c1f[3]};
-      if (b0 + 16 > cn) {
-        const int t = b0 + 2 * tig;
-        if (t >= cn) sc[0] = -INFINITY;
-        if (t + 1 >= cn) sc[1] = -INFINITY;
-        if (t + 8 >= cn) sc[2] = -INFINITY;
-        if (t + 9 >= cn) sc[3] = -INFINITY;
-      }
-      float bm = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
-      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
-      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
-      if (bm > m) {  // the running maximum moves (rare after the first blocks): rescale
-        const float a = fast_exp2(m - bm);
-        l *= a;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { o[e][0] *= a; o[e][1] *= a; o[e][2] *= a; o[e][3] *= a; }
-        m = bm;
-      }
-      const float p0 = fast_exp2(sc[0] - m), p1 = fast_exp2(sc[1] - m), p2 = fast_exp2(sc[2] - m), p3 = fast_exp2(sc[3] - m);
-      l += (p0 + p1) + (p2 + p3);
-      uint32_t a0, a1, a2, a3;
-      split_bf16x2(p0, p1, a0, a1);
-      split_bf16x2(p2, p3, a2, a3);
-      if (g != 0) { a0 = a1 = a2 = a3 = 0u; }
-#pragma unroll
-      for (int e2 = 0; e2 < 4; ++e2) {  // head dims [16 e2, 16 e2 + 16)
-        uint32_t r0, r1, r2, r3;
-        const int row = b0 + v_row;
-        ldsm_x4_t(vb + (uint32_t)row * 128u + (uint32_t)(((2 * e2 + v_chunk) ^ (row & 7)) << 4), r0, r1, r2, r3);
-        mma16816(o[2 * e2], a0, a1, a2, a3, r0, r1);
-        mma16816(o[2 * e2 + 1], a0, a1, a2, a3, r2, r3);
-      }
-    }
-    if ((k + 2) * CB < bpos) {  // contexts beyond two chunks: refill this buffer with chunk k + 2
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int tl = grp + 4 * i, t = (k + 2) * CB + tl;
-        pg0[i] = (tl < CB && t < bpos) ? __ldg(pp + t) : 0;
-      }
-      request(k + 2, pg0);
-    } else {
-      cp_async_commit();  // keeps the group count in step with the chunk index
+      for (int e = 0; e < 8; ++e)
+        *reinterpret_cast<uint32_t*>(dst + 8 * e) = pack_bf16x2((o[e][0] + o[e][2]) * inv, (o[e][1] + o[e][3]) * inv);
     }
   }
   cp_async_wait_group<0>();
-  l += __shfl_xor_sync(0xffffffffu, l, 1);
-  l += __shfl_xor_sync(0xffffffffu, l, 2);
-  if (g == 0) {  // lane tig: dims 8 e + 2 tig, + 1
-    const float inv = 1.f / l;
-    bf16* dst = out + (long long)r * d + h * 64 + 2 * tig;
-#pragma unroll
-    for (int e = 0; e < 8; ++e)
-      *reinterpret_cast<uint32_t*>(dst + 8 * e) = pack_bf16x2((o[e][0] + o[e][2]) * inv, (o[e][1] + o[e][3]) * inv);
-  }
   trace_mark(trace, (3u << 24) | 8);
 }
 
@@ -1289,8 +922,22 @@ template void attn_encoder_simt<bf16>(const bf16*, bf16*, int, int, int, cudaStr
 namespace { std::atomic<int> g_self_attn_mode{0}; }
 void dec_self_attention_mode(int mode) { g_self_attn_mode.store(mode); }
 
-void dec_self_pospage(const DecRows& rows, const SelfKV& kv, cudaStream_t stream) {
-  if (rows.n_rows <= 0 || !kv.pospage) return;
+namespace {
+int self_attn_mode() {
+  static const int forced = getenv("B200W_SELF_ATTN") ? atoi(getenv("B200W_SELF_ATTN")) : 0;  // 1 = staged, 2 = warp, 3 = persistent warps
+  const int m = g_self_attn_mode.load();
+  return m ? m : forced;
+}
+// bf16 product mode: persistent warps from ~1000 (row, head) units upwards; below that a unit per warp leaves most SMs with
+// one warp and the staged kernel's 4 warps per unit are as fast (A-B: profiles/r2_selfattn_pw_ab.txt)
+bool use_persistent_warps(const SelfKV& kv, int units) {
+  const int mode = self_attn_mode();
+  return kv.pospage && (mode == 3 || (mode == 0 && units >= kPwMinUnits));
+}
+}  // namespace
+
+void dec_self_pospage(const DecRows& rows, const SelfKV& kv, int n_head, cudaStream_t stream) {
+  if (rows.n_rows <= 0 || !use_persistent_warps(kv, rows.n_rows * n_head)) return;  // only the persistent kernel reads the table
   launch_kernel(dec_self_pospage_kernel, dim3(rows.n_rows), dim3(128), 0, stream, rows.row_seq, rows.row_bpos, kv.n_ctx, kv.n_blocks,
                 kv.n_units, kv.page_table, kv.seq_first, kv.anc, kv.pospage);
   ++g_kernel_launches;
@@ -1302,46 +949,27 @@ void dec_self_attention(const DecRows& rows, const float* qkv, const SelfKV& kv,
   if (rows.n_rows <= 0) return;
   BW_CHECK(kv.n_ctx <= 448 && kv.n_blocks <= kMaxBlocks && kv.n_blocks * kPageTokens >= kv.n_ctx, "n_text_ctx > 448 unsupported");
   BW_CHECK(rows.row_page && kv.page_table, "paged self-attention needs row_page and a page table");
-  // Two kernels, chosen by the number of (row, head) units (A-B: profiles/r2_self_attention_ab.txt).  Many units (beam
-  // search: 64 windows x 5 hypotheses x 20 heads = 6400): one warp per unit, loads straight into registers -- the staged
-  // kernel fits only 6 units per SM and its per-unit latency chain is paid ~7 times over.  Fewer units (128 x 1 x 20 =
-  // 2560 and below): the staged kernel's one-shot cp.async burst keeps a unit's latency independent of its context.
-  static const int forced = getenv("B200W_SELF_ATTN") ? atoi(getenv("B200W_SELF_ATTN")) : 0;  // 1 = staged, 2 = warp, 3 = mma
   const int units = n_head * rows.n_rows;
-  const int mode = g_self_attn_mode.load() ? g_self_attn_mode.load() : forced;
+  const int mode = self_attn_mode();
   if constexpr (std::is_same<T, bf16>::value) {
-    if (kv.pospage && (mode == 4 || mode == 0)) {
-      // persistent CTAs, 3 per SM (4 x 16 KB ring each); never more than kRingUnits units per CTA
-      int dev = 0, sms = 148;
+    if (use_persistent_warps(kv, units)) {
+      int dev = 0;
       BW_CUDA(cudaGetDevice(&dev));
-      static std::atomic<unsigned long long> ring_attr{0};
-      constexpr int kRingBytes = kRingStages * 2 * kRingPos * 64 * (int)sizeof(bf16);
-      if (!(ring_attr.load() >> dev & 1ull)) {
-        BW_CUDA(cudaFuncSetAttribute(dec_self_attention_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes));
-        ring_attr.fetch_or(1ull << dev);
+      BW_CHECK(dev >= 0 && dev < 64, "device index");
+      constexpr size_t smem = (size_t)kPwCfgNB * kPwCfgCB * 256;
+      static std::atomic<int> pw_slots[64];  // resident warps of the kernel per device (occupancy x SMs)
+      int slots = pw_slots[dev].load();
+      if (slots == 0) {
+        int occ = 0, sms = 0;
+        BW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dec_self_attention_pw_kernel<kPwCfgCB, kPwCfgNB, kPwCfgWarps>, 32, smem));
+        BW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        slots = std::max(occ, 1) * std::max(sms, 1);
+        pw_slots[dev].store(slots);
       }
-      BW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      const int grid = std::min(units, std::max(3 * sms, (units + kRingUnits - 1) / kRingUnits));
-      launch_kernel(dec_self_attention_ring_kernel, dim3(grid), dim3(128), (size_t)kRingBytes, stream, rows.row_pos, rows.row_bpos,
-                    rows.row_page, qkv, reinterpret_cast<bf16*>(kv.pool), kv.page_stride, kv.n_ctx, (const int*)kv.pospage, layer, d,
-                    rows.n_rows, n_head, out, g_trace_dev);
-      ++g_kernel_launches;
-      return;
-    }
-    if (kv.pospage && mode == 5) {
-      static const int cb_cap = getenv("B200W_SELF_CB") ? atoi(getenv("B200W_SELF_CB")) : 64;
-      const int CB = std::min(dec_self_chunk(rows.max_ctx) / 2, cb_cap);  // 2 buffers cover max_ctx up to 128; longer contexts are double-buffered
-      const size_t smem = (size_t)2 * CB * 256;
-      launch_kernel(dec_self_attention_smma_kernel, dim3(n_head, rows.n_rows), dim3(32), smem, stream, rows.row_pos, rows.row_bpos,
-                    rows.row_page, qkv, reinterpret_cast<bf16*>(kv.pool), kv.page_stride, kv.n_ctx, (const int*)kv.pospage, layer, d, CB,
-                    out, g_trace_dev);
-      ++g_kernel_launches;
-      return;
-    }
-    if (mode == 3) {
-      launch_kernel(dec_self_attention_mma_kernel, dim3((units + 3) / 4), dim3(128), 0, stream, rows.row_seq, rows.row_pos, rows.row_bpos,
-                    rows.row_page, qkv, reinterpret_cast<bf16*>(kv.pool), kv.page_stride, kv.n_ctx, kv.n_blocks, kv.n_units, kv.page_table,
-                    kv.seq_first, kv.anc, layer, d, rows.n_rows, n_head, out, g_trace_dev);
+      BW_CHECK((units + slots - 1) / slots <= kPwUnits, "too many self-attention units for one launch");
+      launch_kernel(dec_self_attention_pw_kernel<kPwCfgCB, kPwCfgNB, kPwCfgWarps>, dim3(std::min(units, slots)), dim3(32), smem, stream,
+                    rows.row_pos, rows.row_bpos, rows.row_page, qkv, reinterpret_cast<bf16*>(kv.pool), kv.page_stride, kv.n_ctx,
+                    (const int*)kv.pospage, layer, d, rows.n_rows, n_head, out, g_trace_dev);
       ++g_kernel_launches;
       return;
     }

@@ -239,7 +239,7 @@ struct Impl {
     dec_embed<T>(rows, e->ss.next_tok, reinterpret_cast<const T*>(e->w.tok_emb), reinterpret_cast<const T*>(e->w.dec_pos), x, dm,
                  e->d_page_table.as<int>(), e->n_blocks, st);
     const SelfKV skv = self_kv(G);
-    dec_self_pospage(rows, skv, st);
+    dec_self_pospage(rows, skv, H, st);
     CrossKV xkv;
     xkv.cache = e->cross_cache.p; xkv.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; xkv.T_enc = d.n_audio_ctx;
     xkv.n_slots = e->Q; xkv.n_layer = L;
@@ -287,7 +287,7 @@ struct Impl {
     dec_embed_ln<bf16>(rows, e->ss.next_tok, reinterpret_cast<const bf16*>(e->w.tok_emb), reinterpret_cast<const bf16*>(e->w.dec_pos), x, dm,
                        xb, lst, e->d_page_table.as<int>(), e->n_blocks, st);
     const SelfKV skv = self_kv(G);
-    dec_self_pospage(rows, skv, st);
+    dec_self_pospage(rows, skv, H, st);
     CrossKV xkv;
     xkv.cache = e->cross_cache.p; xkv.slot_stride = (long long)L * d.n_audio_ctx * 2 * dm; xkv.T_enc = d.n_audio_ctx;
     xkv.n_slots = e->Q; xkv.n_layer = L;

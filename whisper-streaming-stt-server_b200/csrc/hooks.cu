@@ -425,7 +425,7 @@ int bw_test_dec_self_attention(int32_t n_rows, const int32_t* row_seq, const int
   DevBuf pospage;
   pospage.alloc((size_t)n_rows * n_ctx * 4);
   kv.pospage = pospage.as<int>();
-  dec_self_pospage(rows, kv, st);
+  dec_self_pospage(rows, kv, n_head, st);
   dec_self_attention<bf16>(rows, qkv, kv, layer, d, n_head, reinterpret_cast<bf16*>(out), st);
   BW_CUDA(cudaStreamSynchronize(st));
   BW_API_END
@@ -433,7 +433,7 @@ int bw_test_dec_self_attention(int32_t n_rows, const int32_t* row_seq, const int
 
 int bw_test_self_attention_mode(int32_t mode) {
   BW_API_BEGIN
-  BW_CHECK(mode >= 0 && mode <= 5, "mode: 0 automatic, 1 staged, 2 warp, 3 mma, 4 ring, 5 staged mma");
+  BW_CHECK(mode >= 0 && mode <= 3, "mode: 0 automatic, 1 staged, 2 warp per unit, 3 persistent warps");
   dec_self_attention_mode(mode);
   BW_API_END
 }

@@ -104,9 +104,11 @@ struct SelfKV {
   int* pospage = nullptr;              // [rows of the step][n_ctx] scratch: page of (row, position), see dec_self_pospage
 };
 // Once per step, after the embed kernel: resolves seq_first / ancestry / page table into pospage[r][t] for t < row_bpos[r],
-// so that the 32 layers' self-attention kernels follow one indirection instead of three.
-void dec_self_pospage(const DecRows& rows, const SelfKV& kv, cudaStream_t stream);
-// test / A-B hook: 0 = automatic, 1 = staged, 2 = warp per unit, 3 = mma, 4 = persistent ring (needs pospage)
+// so that the 32 layers' self-attention kernels follow one indirection instead of three (no-op when the step's shape does not
+// take the persistent-warp kernel, the only reader).
+void dec_self_pospage(const DecRows& rows, const SelfKV& kv, int n_head, cudaStream_t stream);
+// test / A-B hook: 0 = automatic, 1 = staged CTA per (row, head), 2 = warp per (row, head), 3 = persistent warps on mma.sync
+// (bf16 only, needs pospage)
 void dec_self_attention_mode(int mode);
 // out[r] = softmax(q_r . K[0..pos_r]) V   (head dim 64); q = first d columns of the fp32 qkv rows.
 // Also appends this step's k/v (columns d..3d of the row) to the row's page.
