@@ -73,7 +73,7 @@ int bw_test_dec_self_attention(int32_t n_rows, const int32_t* row_seq, const int
                                const int32_t* page_table, const int32_t* seq_first, const uint8_t* anc, int32_t layer, int32_t d,
                                int32_t n_head, int32_t max_ctx, void* out, void* stream);
 /* Which decoder self-attention kernel the bf16 path launches (process-wide; A-B runs and kernel tests): 0 = automatic
- * (persistent warps from ~1000 (row, head) units upwards, else staged), 1 = staged CTA per (row, head), 2 = warp per
+ * (persistent warps from 512 (row, head) units upwards, else staged), 1 = staged CTA per (row, head), 2 = warp per
  * (row, head), 3 = persistent warps on mma.sync. */
 int bw_test_self_attention_mode(int32_t mode);
 /* sample_topk_kernel on n independent logits rows (host pointers).  state[i][10] = n_beam, greedy, cur_len,

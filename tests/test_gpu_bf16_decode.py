@@ -94,7 +94,7 @@ def test_teacher_forced_cached_decode_matches_oracle_logits(name, n_sessions):
 
 
 def test_persistent_warp_self_attention_inside_the_engine():
-    """The test models are too small to reach the unit count from which the step takes the persistent-warp self-attention
+    """The test models are too small to reach the unit count (512) from which the step takes the persistent-warp self-attention
     kernel (large-v3 batches do: bench.py).  Force it process-wide and repeat (i) the teacher-forced cached decode against
     the oracle's logits and (ii) a mixed greedy / beam-5 batch against the same batch under the staged kernel: identical
     token streams, through beam reordering, paged K/V and prompt prefill rows."""

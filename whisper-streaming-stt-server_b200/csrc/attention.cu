@@ -517,7 +517,7 @@ dec_self_pospage_kernel(const int* __restrict__ row_seq, const int* __restrict__
 // a CTA-wide persistent ring and a staged mma kernel each fixed one of the two and were no faster; this one fixes both.
 // positions per ring buffer, buffers, resident warps per SM asked of the compiler (165 registers), most units per warp, and the
 // unit count from which the kernel is taken.  A-B of the ring geometry: profiles/r2_selfattn_pw_configs.txt
-constexpr int kPwCfgCB = 32, kPwCfgNB = 2, kPwCfgWarps = 12, kPwUnits = 32, kPwMinUnits = 1000;  // A-B of 9 configurations: profiles/r2_selfattn_pw_configs.txt
+constexpr int kPwCfgCB = 32, kPwCfgNB = 2, kPwCfgWarps = 12, kPwUnits = 32, kPwMinUnits = 512;  // A-B of 9 configurations: profiles/r2_selfattn_pw_configs.txt
 
 template <int kPwCB, int kPwNB, int kPwMinWarps>
 __global__ void __launch_bounds__(32, kPwMinWarps)
@@ -928,8 +928,9 @@ int self_attn_mode() {
   const int m = g_self_attn_mode.load();
   return m ? m : forced;
 }
-// bf16 product mode: persistent warps from ~1000 (row, head) units upwards; below that a unit per warp leaves most SMs with
-// one warp and the staged kernel's 4 warps per unit are as fast (A-B: profiles/r2_selfattn_pw_ab.txt)
+// bf16 product mode: persistent warps from 512 (row, head) units upwards (640 units: 0.4 - 1.7 % faster steps, 160 units: a tie);
+// below that a unit per warp leaves most SMs with one warp and the staged kernel's 4 warps per unit are as fast
+// (A-B: profiles/r2_selfattn_pw_ab.txt)
 bool use_persistent_warps(const SelfKV& kv, int units) {
   const int mode = self_attn_mode();
   return kv.pospage && (mode == 3 || (mode == 0 && units >= kPwMinUnits));
